@@ -1,0 +1,167 @@
+// Shared device/host helpers for libpolus_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/polus_b200.h"
+
+typedef __nv_bfloat16 bf16;
+
+// ---------------------------------------------------------------------------------------------
+// error convention: every entry point returns 0 or a negative class; message kept
+// thread-local and returned by polus_last_error().
+// ---------------------------------------------------------------------------------------------
+void polus_set_error(const char* fmt, ...);
+
+#define POLUS_CHECK_CUDA(expr)                                                            \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            polus_set_error("%s:%d CUDA error %d (%s) in `%s`", __FILE__, __LINE__,       \
+                            (int)_e, cudaGetErrorString(_e), #expr);                      \
+            return POLUS_ERR_CUDA;                                                        \
+        }                                                                                 \
+    } while (0)
+
+#define POLUS_REQUIRE(cond, ...)                                                          \
+    do {                                                                                  \
+        if (!(cond)) {                                                                    \
+            polus_set_error(__VA_ARGS__);                                                 \
+            return POLUS_ERR_INVALID;                                                     \
+        }                                                                                 \
+    } while (0)
+
+#define POLUS_LAUNCH_CHECK()                                                              \
+    do {                                                                                  \
+        cudaError_t _e = cudaGetLastError();                                              \
+        if (_e != cudaSuccess) {                                                          \
+            polus_set_error("%s:%d launch error %d (%s)", __FILE__, __LINE__, (int)_e,    \
+                            cudaGetErrorString(_e));                                      \
+            return POLUS_ERR_CUDA;                                                        \
+        }                                                                                 \
+    } while (0)
+
+int polus_num_sms();
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+struct __align__(16) bf16x8 {
+    __nv_bfloat162 v[4];
+};
+
+__device__ __forceinline__ void unpack8(const bf16x8& p, float* f) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 t = __bfloat1622float2(p.v[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+__device__ __forceinline__ bf16x8 pack8(const float* f) {
+    bf16x8 p;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    return p;
+}
+
+// streaming (read-once) 16-byte load that does not allocate in L1
+__device__ __forceinline__ bf16x8 ld_stream8(const bf16* p) {
+    bf16x8 r;
+    uint32_t* u = reinterpret_cast<uint32_t*>(&r);
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3])
+                 : "l"(p));
+    return r;
+}
+
+// ---- Philox4x32-10 (Salmon et al. 2011). Counter = (idx_lo, idx_hi, site, step); key = seed.
+// The numpy restatement in oracle/philox.py regenerates identical streams, so dropout masks are
+// bit-identical between the oracle and the device.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0;
+        key.y += W1;
+    }
+    return ctr;
+}
+
+// Dropout decisions for 8 consecutive elements starting at element index `idx8*8`.
+// keep bit i set <=> 16-bit lane i >= thresh16 (thresh16 = round(p * 65536)).
+__device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint32_t site, uint32_t step,
+                                                  uint64_t idx8, uint32_t thresh16) {
+    uint4 r = philox4x32_10(make_uint4((uint32_t)idx8, (uint32_t)(idx8 >> 32), site, step),
+                            make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        m |= ((w[i] & 0xFFFFu) >= thresh16 ? 1u : 0u) << (2 * i);
+        m |= ((w[i] >> 16) >= thresh16 ? 1u : 0u) << (2 * i + 1);
+    }
+    return m;
+}
+
+// activations (polus_act_t)
+__device__ __forceinline__ float act_fwd(int act, float x) {
+    switch (act) {
+        case POLUS_ACT_GELU: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+        case POLUS_ACT_RELU: return fmaxf(x, 0.0f);
+        case POLUS_ACT_SWISH: return x / (1.0f + __expf(-x));
+        case POLUS_ACT_TANH: return tanhf(x);
+        case POLUS_ACT_MISH: {
+            float sp = (x > 20.0f) ? x : log1pf(__expf(x));
+            return x * tanhf(sp);
+        }
+        default: return x;
+    }
+}
+__device__ __forceinline__ float act_grad(int act, float x) {
+    switch (act) {
+        case POLUS_ACT_GELU: {
+            float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+            float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+            return cdf + x * pdf;
+        }
+        case POLUS_ACT_RELU: return x > 0.0f ? 1.0f : 0.0f;
+        case POLUS_ACT_SWISH: {
+            float s = 1.0f / (1.0f + __expf(-x));
+            return s * (1.0f + x * (1.0f - s));
+        }
+        case POLUS_ACT_TANH: {
+            float t = tanhf(x);
+            return 1.0f - t * t;
+        }
+        case POLUS_ACT_MISH: {
+            float sp = (x > 20.0f) ? x : log1pf(__expf(x));
+            float t = tanhf(sp);
+            float s = 1.0f / (1.0f + __expf(-x));
+            return t + x * (1.0f - t * t) * s;
+        }
+        default: return 1.0f;
+    }
+}
+
+#endif  // __CUDACC__

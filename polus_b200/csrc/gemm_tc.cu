@@ -1,0 +1,442 @@
+// Batched bf16 GEMM on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM, operands staged
+// by TMA with 128-byte swizzle).  C[b] = act(alpha * A[b] . B[b]^T + bias), fp32 accumulate.
+//
+// Replaces the cuBLAS calls TensorFlow makes on behalf of HF TFBertLayer (reference
+// polus/models.py:205-213), the NER head Dense (polus/ner/models.py:36) and every gradient GEMM that
+// tf.GradientTape derives from them (polus/training.py:185).
+//
+// Kernel shape (persistent, warp-specialised, one CTA per SM):
+//   warp 0      TMA producer       global -> smem ring (kStages x {A 128x64, B BNx64} bf16)
+//   warp 1      MMA issuer         one thread issues 4 x tcgen05.mma (K=16) per stage
+//   warp 2      TMEM alloc/dealloc 2 x BN fp32 columns: accumulator double buffer
+//   warps 4-7   epilogue           tcgen05.ld -> alpha/bias/activation -> bf16|fp32 global stores
+// Three mbarrier pipelines: smem full/empty, TMEM full/empty; tiles = batch x M/128 x N/BN x split_k.
+// Either operand may be K-major (reduction dim contiguous) or MN-major (the other dim contiguous), so
+// forward (X.W), dgrad (dY.W^T) and wgrad (X^T.dY) all read row-major tensors with no transposes.
+#include "common.cuh"
+#include "ptx.cuh"
+#include <cuda.h>
+#include <atomic>
+
+extern std::atomic<long long> g_launch_count;
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
+constexpr int kThreads = 256;
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+
+struct TcParams {
+    int M, N, K;
+    int batch0;
+    int m_tiles, n_tiles, split_k, kb_total, kb_per_split;
+    int num_tiles;
+    void* C;
+    void* C2;
+    long long ldc, cbs0, cbs1;
+    const float* bias;
+    float alpha;
+    int act;
+    int c_f32;
+    int accumulate;
+};
+
+template <int BN>
+struct Cfg {
+    static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int B_STAGE_BYTES = BN * BK * 2;
+    static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+    static constexpr int kSmemBytes = 1024 + kStages * (A_STAGE_BYTES + B_STAGE_BYTES) + 256;
+};
+
+__device__ __forceinline__ void store_chunk(const TcParams& p, float* v, long long row_off, int col0,
+                                            int ncols_valid) {
+    // v[0..31]: alpha*acc (+bias) before activation for columns col0..col0+31 of one row
+    if (p.C2 != nullptr) {
+        bf16* z = reinterpret_cast<bf16*>(p.C2) + row_off + col0;
+        if (ncols_valid == 32) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<bf16x8*>(z + 8 * j) = pack8(v + 8 * j);
+        } else {
+            _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < ncols_valid) z[j] = __float2bfloat16(v[j]);
+        }
+    }
+    if (p.act != POLUS_ACT_NONE) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = act_fwd(p.act, v[j]);
+    }
+    if (p.c_f32) {
+        float* c = reinterpret_cast<float*>(p.C) + row_off + col0;
+        if (p.accumulate) {
+            _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < ncols_valid) atomicAdd(c + j, v[j]);
+        } else if (ncols_valid == 32) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(c + 4 * j) =
+                    make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+            _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < ncols_valid) c[j] = v[j];
+        }
+    } else {
+        bf16* c = reinterpret_cast<bf16*>(p.C) + row_off + col0;
+        if (ncols_valid == 32) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<bf16x8*>(c + 8 * j) = pack8(v + 8 * j);
+        } else {
+            _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < ncols_valid) c[j] = __float2bfloat16(v[j]);
+        }
+    }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const TcParams p) {
+    using C = Cfg<BN>;
+    constexpr int kStages = C::kStages;
+    constexpr int B_STAGE_BYTES = C::B_STAGE_BYTES;
+    constexpr uint32_t kStageTx = A_STAGE_BYTES + B_STAGE_BYTES;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                               ~static_cast<uintptr_t>(1023));
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + kStages * A_STAGE_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * (A_STAGE_BYTES + B_STAGE_BYTES));
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tfull_bar = empty_bar + kStages;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tmA);
+        ptx::prefetch_tensormap(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(&tfull_bar[s], 1);
+            ptx::mbar_init(&tempty_bar[s], 4);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) ptx::tmem_alloc<C::kTmemCols>(tmem_slot);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto decode = [&](int t, int& mt, int& nt, int& sp, int& b0, int& b1) {
+        mt = t % p.m_tiles;
+        t /= p.m_tiles;
+        nt = t % p.n_tiles;
+        t /= p.n_tiles;
+        sp = t % p.split_k;
+        t /= p.split_k;
+        b0 = t % p.batch0;
+        b1 = t / p.batch0;
+    };
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+                int mt, nt, sp, b0, b1;
+                decode(t, mt, nt, sp, b0, b1);
+                const int kb0 = sp * p.kb_per_split;
+                const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    ptx::mbar_expect_tx(&full_bar[stage], kStageTx);
+                    uint8_t* a = sA + stage * A_STAGE_BYTES;
+                    uint8_t* b = sB + stage * B_STAGE_BYTES;
+                    if (!A_MN) {
+                        ptx::tma_load_4d(a, &tmA, &full_bar[stage], kb * BK, mt * BM, b0, b1);
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < BM / 64; ++g)
+                            ptx::tma_load_4d(a + g * (BK * 128), &tmA, &full_bar[stage],
+                                             mt * BM + g * 64, kb * BK, b0, b1);
+                    }
+                    if (!B_MN) {
+                        ptx::tma_load_4d(b, &tmB, &full_bar[stage], kb * BK, nt * BN, b0, b1);
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < BN / 64; ++g)
+                            ptx::tma_load_4d(b + g * (BK * 128), &tmB, &full_bar[stage],
+                                             nt * BN + g * 64, kb * BK, b0, b1);
+                    }
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+            const uint64_t adesc_base = A_MN ? ptx::umma_desc_base(BK * 128, 1024) : ptx::umma_desc_base(16, 1024);
+            const uint64_t bdesc_base = B_MN ? ptx::umma_desc_base(BK * 128, 1024) : ptx::umma_desc_base(16, 1024);
+            constexpr uint32_t a_kstep = A_MN ? 2048 : 32;  // bytes per UMMA_K=16 step
+            constexpr uint32_t b_kstep = B_MN ? 2048 : 32;
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+                int mt, nt, sp, b0, b1;
+                decode(t, mt, nt, sp, b0, b1);
+                const int kb0 = sp * p.kb_per_split;
+                const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+                ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint32_t a_addr = ptx::smem_u32(sA + stage * A_STAGE_BYTES);
+                    const uint32_t b_addr = ptx::smem_u32(sB + stage * B_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        ptx::umma_bf16(tmem_d, ptx::umma_desc(adesc_base, a_addr + k * a_kstep),
+                                       ptx::umma_desc(bdesc_base, b_addr + k * b_kstep), idesc,
+                                       (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
+                    ptx::umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                ptx::umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------ epilogue (TMEM lane = row)
+        const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32)
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+            int mt, nt, sp, b0, b1;
+            decode(t, mt, nt, sp, b0, b1);
+            ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+            ptx::tc_fence_after();
+            const int row = mt * BM + quad * 32 + lane;
+            const long long row_off = (long long)b0 * p.cbs0 + (long long)b1 * p.cbs1 + (long long)row * p.ldc;
+            const bool add_bias = (p.bias != nullptr) && (sp == 0);
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                const int col0 = nt * BN + c * 32;
+                if (col0 >= p.N) break;  // warp-uniform
+                float v[32];
+                ptx::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + c * 32, v);
+                ptx::tmem_ld_wait();
+                const int nvalid = min(32, p.N - col0);
+                if (row < p.M) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+                    if (add_bias) {
+                        if (nvalid == 32) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
+                                v[4 * j] += bv.x;
+                                v[4 * j + 1] += bv.y;
+                                v[4 * j + 2] += bv.z;
+                                v[4 * j + 3] += bv.w;
+                            }
+                        } else {
+                            _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nvalid) v[j] += __ldg(p.bias + col0 + j);
+                        }
+                    }
+                    store_chunk(p, v, row_off, col0, nvalid);
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<C::kTmemCols>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(f);
+    }
+    return fn;
+}
+
+// 4-D view (dim0 contiguous, rows, batch0, batch1) of one operand; box = {64, box_rows, 1, 1}.
+int make_map(CUtensorMap* map, const polus_operand_t& op, long long mn_len, long long k_len, int batch0,
+             int batch1, int box_mn) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) {
+        polus_set_error("cuTensorMapEncodeTiled entry point not found (driver too old?)");
+        return POLUS_ERR_CUDA;
+    }
+    cuuint64_t dims[4];
+    cuuint64_t strides[3];
+    cuuint32_t box[4];
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    const long long inner = op.mn_major ? mn_len : k_len;
+    const long long rows = op.mn_major ? k_len : mn_len;
+    dims[0] = (cuuint64_t)inner;
+    dims[1] = (cuuint64_t)rows;
+    dims[2] = (cuuint64_t)batch0;
+    dims[3] = (cuuint64_t)batch1;
+    strides[0] = (cuuint64_t)op.ld * 2;
+    strides[1] = (cuuint64_t)(batch0 > 1 ? op.bs0 * 2 : rows * op.ld * 2);
+    strides[2] = (cuuint64_t)(batch1 > 1 ? op.bs1 * 2 : strides[1] * (cuuint64_t)batch0);
+    box[0] = 64;
+    box[1] = op.mn_major ? BK : (cuuint32_t)box_mn;
+    box[2] = 1;
+    box[3] = 1;
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(op.ptr), dims, strides, box,
+                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        polus_set_error("cuTensorMapEncodeTiled failed (%d): ptr=%p inner=%lld rows=%lld ld=%lld b0=%d/%lld b1=%d/%lld",
+                        (int)r, op.ptr, inner, rows, (long long)op.ld, batch0, (long long)op.bs0, batch1,
+                        (long long)op.bs1);
+        return POLUS_ERR_INVALID;
+    }
+    return 0;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, cudaStream_t st) {
+    auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        POLUS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes));
+        attr_set = true;
+    }
+    int grid = p.num_tiles < polus_num_sms() ? p.num_tiles : polus_num_sms();
+    kern<<<grid, kThreads, Cfg<BN>::kSmemBytes, st>>>(ta, tb, p);
+    g_launch_count++;
+    POLUS_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int BN>
+int launch_major(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p,
+                 cudaStream_t st) {
+    if (!a_mn && !b_mn) return launch<BN, false, false>(ta, tb, p, st);
+    if (!a_mn && b_mn) return launch<BN, false, true>(ta, tb, p, st);
+    if (a_mn && !b_mn) return launch<BN, true, false>(ta, tb, p, st);
+    return launch<BN, true, true>(ta, tb, p, st);
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+const char* why_unsupported(const polus_gemm_t* g) {
+    if (g->A.dtype != POLUS_BF16 || g->B.dtype != POLUS_BF16) return "operands must be bf16";
+    if (g->M < 1 || g->N < 1 || g->K < 1) return "empty problem";
+    if (!aligned16(g->A.ptr) || !aligned16(g->B.ptr) || !aligned16(g->C)) return "pointers must be 16-byte aligned";
+    if (g->A.ld % 8 || g->B.ld % 8) return "operand leading dims must be multiples of 8 elements";
+    if ((g->batch0 > 1 && (g->A.bs0 % 8 || g->B.bs0 % 8)) || (g->batch1 > 1 && (g->A.bs1 % 8 || g->B.bs1 % 8)))
+        return "batch strides must be multiples of 8 elements";
+    const int cvec = g->c_dtype == POLUS_F32 ? 4 : 8;
+    if (g->ldc % cvec || g->cbs0 % cvec || g->cbs1 % cvec) return "C strides must be 16-byte multiples";
+    if (g->N % 8) return "N must be a multiple of 8";
+    if (g->C2 && (g->c_dtype != POLUS_BF16 || !aligned16(g->C2))) return "C2 requires bf16 C";
+    if (g->bias && !aligned16(g->bias)) return "bias must be 16-byte aligned";
+    if (g->accumulate && g->c_dtype != POLUS_F32) return "accumulate requires fp32 C";
+    if (g->split_k > 1 && (!g->accumulate || g->act != POLUS_ACT_NONE || g->C2)) return "split_k needs accumulate, no activation";
+    if (g->c_dtype != POLUS_F32 && g->c_dtype != POLUS_BF16) return "C dtype";
+    return nullptr;
+}
+
+}  // namespace
+
+extern "C" int polus_gemm_tc_supported(const polus_gemm_t* g) { return why_unsupported(g) == nullptr ? 1 : 0; }
+
+extern "C" int polus_gemm_tc(const polus_gemm_t* g, void* stream) {
+    const char* why = why_unsupported(g);
+    POLUS_REQUIRE(why == nullptr, "polus_gemm_tc: unsupported problem (%s) M=%d N=%d K=%d", why, g->M, g->N, g->K);
+    const int batch0 = g->batch0 < 1 ? 1 : g->batch0;
+    const int batch1 = g->batch1 < 1 ? 1 : g->batch1;
+    const int sms = polus_num_sms();
+
+    // tile width: widest tile that still yields >= one wave of CTAs; narrow tiles for narrow N
+    int BN;
+    const long long mt = cdiv(g->M, BM);
+    const long long nb = (long long)batch0 * batch1;
+    if (g->N <= 64) BN = 64;
+    else if (g->N <= 128) BN = 128;
+    else {
+        const long long tiles256 = mt * cdiv(g->N, 256) * nb * (g->split_k > 1 ? g->split_k : 1);
+        BN = tiles256 >= sms ? 256 : 128;
+    }
+
+    TcParams p;
+    p.M = g->M;
+    p.N = g->N;
+    p.K = g->K;
+    p.batch0 = batch0;
+    p.m_tiles = (int)mt;
+    p.n_tiles = cdiv(g->N, BN);
+    p.kb_total = cdiv(g->K, BK);
+    int split = g->split_k < 1 ? 1 : g->split_k;
+    if (split > p.kb_total) split = p.kb_total;
+    p.kb_per_split = cdiv(p.kb_total, split);
+    p.split_k = cdiv(p.kb_total, p.kb_per_split);
+    p.num_tiles = (int)(mt * p.n_tiles * p.split_k * nb);
+    p.C = g->C;
+    p.C2 = g->C2;
+    p.ldc = g->ldc;
+    p.cbs0 = g->cbs0;
+    p.cbs1 = g->cbs1;
+    p.bias = g->bias;
+    p.alpha = g->alpha;
+    p.act = g->act;
+    p.c_f32 = g->c_dtype == POLUS_F32;
+    p.accumulate = g->accumulate;
+
+    CUtensorMap ta, tb;
+    int rc = make_map(&ta, g->A, g->M, g->K, batch0, batch1, BM);
+    if (rc) return rc;
+    rc = make_map(&tb, g->B, g->N, g->K, batch0, batch1, BN);
+    if (rc) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (BN == 64) return launch_major<64>(g->A.mn_major, g->B.mn_major, ta, tb, p, st);
+    if (BN == 128) return launch_major<128>(g->A.mn_major, g->B.mn_major, ta, tb, p, st);
+    return launch_major<256>(g->A.mn_major, g->B.mn_major, ta, tb, p, st);
+}
