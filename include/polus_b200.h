@@ -4,7 +4,7 @@
  * The reference (bioinformatics-ua/polus) has no FFI: its device work is TensorFlow / HuggingFace /
  * tensorflow_addons / Horovod library calls made from Python.  Each entry point
  * below therefore cites the *reference call site* whose device work it replaces.  The Python host
- * (polus_b200/*.py) binds these with ctypes; nothing here takes or returns a torch / numpy type.
+ * (the polus_b200 package) binds these with ctypes; nothing here takes or returns a torch / numpy type.
  *
  * Conventions
  *   - every function returns 0 on success or a negative polus_status_t; polus_last_error() gives
@@ -130,9 +130,11 @@ int polus_embed_ln_fwd(const int32_t* d_ids, const int32_t* d_tt, const float* d
                        polus_bf16_t* d_y, float* d_z, float* d_mean, float* d_rstd, void* stream);
 int polus_embed_ln_bwd(const polus_bf16_t* d_dy, const float* d_z, const float* d_mean,
                        const float* d_rstd, const float* d_gamma, const int32_t* d_ids,
-                       const int32_t* d_tt, int B, int S, int H, float p_drop, uint64_t seed,
-                       uint32_t site, const uint32_t* d_step, float* d_gword, float* d_gpos,
-                       float* d_gtype, float* d_ggamma, float* d_gbeta, float* d_ws, void* stream);
+                       const int32_t* d_tt, int B, int S, int H, int vocab, int n_types, float p_drop,
+                       uint64_t seed, uint32_t site, const uint32_t* d_step, float* d_gword,
+                       float* d_gpos, float* d_gtype, float* d_ggamma, float* d_gbeta, float* d_ws,
+                       void* stream);
+size_t polus_embed_ws_floats(int B, int S, int H); /* size of d_ws above */
 
 /* HF TFBertSelfOutput / TFBertOutput: y = LN(dropout(x) + res), eps 1e-12.  x is overwritten with
  * z = dropout(x)+res (kept for backward).  res may be NULL. */
@@ -186,6 +188,10 @@ int polus_crf_decode(const float* d_emis, const int32_t* d_lens, const float* d_
 int polus_crf_mask_transitions(const float* d_trans, const float* d_mask, int K, float* d_out,
                                void* stream);
 
+/* CRF.loss_sample_weights (polus/layers.py:116-121): per-sequence weight from one-hot labels [B,T,K] */
+int polus_crf_sample_weights(const float* d_y_true, const float* d_mask_positive, float negative_weight,
+                             int B, int T, int K, float* d_out, void* stream);
+
 /* kind 0: SparseCategoricalCrossentropy(from_logits) (tutorials/classifier_example.py:55), labels int32
  * kind 1: weighted softmax CE, one-hot/soft labels fp32 (polus/losses.py:5-18)
  * kind 2: weighted sigmoid CE, multi-hot labels fp32 (polus/losses.py:21-42)
@@ -219,7 +225,8 @@ int polus_fill_f32(float* d_dst, float value, int64_t n, void* stream);
  * of length `b_n` broadcast over rows (n % b_n == 0). */
 int polus_binary_f32(int op, const float* d_a, const float* d_b, int64_t n, int64_t b_n,
                      float* d_out, void* stream);
-/* op: polus_act_t codes 0..5, plus 16 exp, 17 log, 18 softplus, 19 sigmoid, 20 neg, 21 square;
+/* op: polus_act_t codes 0..5, plus 16 exp, 17 log, 18 softplus, 19 sigmoid, 20 neg, 21 square,
+ * 22 scale-by-alpha;
  * grad=1 computes dy * f'(x) into d_out (d_dy required). */
 int polus_unary_f32(int op, const float* d_x, const float* d_dy, int grad, int64_t n, float* d_out,
                     float alpha, void* stream);
@@ -235,6 +242,8 @@ int polus_confusion_matrix(const int32_t* d_true, const int32_t* d_pred, int64_t
 int polus_gather_rows(const void* d_x, int64_t row_stride_bytes, int64_t row_bytes,
                       int64_t first_row, int64_t row_step, int64_t n_rows, void* d_out,
                       void* stream);
+int polus_add_bf16(const polus_bf16_t* d_a, const polus_bf16_t* d_b, polus_bf16_t* d_out, int64_t n,
+                   void* stream);
 int polus_scatter_rows_add_bf16(const polus_bf16_t* d_g, int64_t cols, int64_t first_row,
                                 int64_t row_step, int64_t n_rows, polus_bf16_t* d_out, void* stream);
 /* global L2 norm (post_process_grads clipping, training.py:187-189) */

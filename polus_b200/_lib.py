@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libpolus_b200.so")
 
 F32, BF16, I32, U8 = 0, 1, 2, 3
 ACT = {None: 0, "linear": 0, "none": 0, "gelu": 1, "relu": 2, "swish": 3, "silu": 3, "tanh": 4, "mish": 5}
-UNARY = {"exp": 16, "log": 17, "softplus": 18, "sigmoid": 19, "neg": 20, "square": 21,
+UNARY = {"exp": 16, "log": 17, "softplus": 18, "sigmoid": 19, "neg": 20, "square": 21, "scale": 22,
          "gelu": 1, "relu": 2, "swish": 3, "tanh": 4, "mish": 5, "identity": 0}
 
 
@@ -82,7 +82,9 @@ _SIGS = {
     "polus_gemm_small": [C.POINTER(Gemm), p],
     "polus_gemm_tc_supported": [C.POINTER(Gemm)],
     "polus_embed_ln_fwd": [p, p, p, p, p, p, p, i32, i32, i32, i32, i32, f32, f32, u64, u32, p, p, p, p, p, p],
-    "polus_embed_ln_bwd": [p, p, p, p, p, p, p, i32, i32, i32, f32, u64, u32, p, p, p, p, p, p, p, p],
+    "polus_embed_ln_bwd": [p, p, p, p, p, p, p, i32, i32, i32, i32, i32, f32, u64, u32, p, p, p, p, p, p, p, p],
+    "polus_embed_ws_floats": [i32, i32, i32],
+    "polus_add_bf16": [p, p, p, i64, p],
     "polus_ln_res_fwd": [p, p, p, p, i32, i32, f32, f32, u64, u32, p, p, p, p, p],
     "polus_ln_res_bwd": [p, p, p, p, p, i32, i32, f32, u64, u32, p, p, p, i32, p, p, p, p],
     "polus_ln_ws_floats": [i32],
@@ -94,6 +96,7 @@ _SIGS = {
     "polus_crf_nll": [p, p, p, p, p, i32, i32, i32, p, p, p, p, p],
     "polus_crf_decode": [p, p, p, i32, i32, i32, p, p, p],
     "polus_crf_mask_transitions": [p, p, i32, p, p],
+    "polus_crf_sample_weights": [p, p, f32, i32, i32, i32, p, p],
     "polus_xent": [i32, p, p, p, f32, i32, i32, p, p, p],
     "polus_adam": [p, p, p, p, p, p, i64, C.POINTER(AdamCfg), p, i32, p],
     "polus_cast": [p, i32, p, i32, i64, p],
@@ -117,10 +120,11 @@ _SIGS = {
     "polus_comm_allgather": [p, p, sz, p],
     "polus_comm_destroy": [],
 }
-_RET = {"polus_launch_count": C.c_int64, "polus_ln_ws_floats": sz, "polus_colsum_ws_floats": sz}
+_RET = {"polus_launch_count": C.c_int64, "polus_ln_ws_floats": sz, "polus_colsum_ws_floats": sz,
+        "polus_embed_ws_floats": sz}
 # functions whose int return is a value, not a status
 _VALUE_RET = {"polus_version", "polus_gemm_tc_supported", "polus_comm_size", "polus_comm_rank",
-              "polus_launch_count", "polus_ln_ws_floats", "polus_colsum_ws_floats"}
+              "polus_launch_count", "polus_ln_ws_floats", "polus_colsum_ws_floats", "polus_embed_ws_floats"}
 
 EXPORTS = ["polus_last_error"] + list(_SIGS)
 

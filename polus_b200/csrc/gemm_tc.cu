@@ -395,14 +395,29 @@ extern "C" int polus_gemm_tc(const polus_gemm_t* g, void* stream) {
     const int batch1 = g->batch1 < 1 ? 1 : g->batch1;
     const int sms = polus_num_sms();
 
-    // tile width: widest tile that still yields >= one wave of CTAs; narrow tiles for narrow N
-    int BN;
     const long long mt = cdiv(g->M, BM);
     const long long nb = (long long)batch0 * batch1;
+    const int kb_total = cdiv(g->K, BK);
+    // split_k == 0 with accumulate: pick the split that fills the machine (wgrad: few output tiles, long K)
+    int split = g->split_k;
+    if (split == 0) {
+        split = 1;
+        if (g->accumulate && g->act == POLUS_ACT_NONE && g->C2 == nullptr) {
+            const long long tiles = mt * cdiv(g->N, 128) * nb;
+            if (tiles < sms) {
+                split = (int)((sms + tiles - 1) / tiles);
+                const int max_split = kb_total / 4 > 1 ? kb_total / 4 : 1;  // >= 4 k-blocks per split
+                if (split > max_split) split = max_split;
+            }
+        }
+    }
+    if (split < 1) split = 1;
+    // tile width: widest tile that still yields >= one wave of CTAs; narrow tiles for narrow N
+    int BN;
     if (g->N <= 64) BN = 64;
     else if (g->N <= 128) BN = 128;
     else {
-        const long long tiles256 = mt * cdiv(g->N, 256) * nb * (g->split_k > 1 ? g->split_k : 1);
+        const long long tiles256 = mt * cdiv(g->N, 256) * nb * split;
         BN = tiles256 >= sms ? 256 : 128;
     }
 
@@ -413,8 +428,7 @@ extern "C" int polus_gemm_tc(const polus_gemm_t* g, void* stream) {
     p.batch0 = batch0;
     p.m_tiles = (int)mt;
     p.n_tiles = cdiv(g->N, BN);
-    p.kb_total = cdiv(g->K, BK);
-    int split = g->split_k < 1 ? 1 : g->split_k;
+    p.kb_total = kb_total;
     if (split > p.kb_total) split = p.kb_total;
     p.kb_per_split = cdiv(p.kb_total, split);
     p.split_k = cdiv(p.kb_total, p.kb_per_split);

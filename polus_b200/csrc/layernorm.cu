@@ -1,0 +1,532 @@
+// LayerNorm family (HBM-bound): fused residual + dropout + LayerNorm forward/backward, and the BERT
+// embedding block (gather x3 + sum + LayerNorm + dropout; backward with scatter-add).
+//
+// Replaces, per call, the ~7 Eigen kernels TF runs for HF TFBertSelfOutput/TFBertOutput
+// (`LayerNorm(dropout(dense(x)) + residual)`, eps 1e-12) and the ~8 it runs for TFBertEmbeddings;
+// reached from the reference through polus/models.py:205-213 and polus/data.py:526-545.
+//
+// Layout: one warp per row, each lane owns 16-byte chunks `lane + 32*i`; row statistics by warp
+// shuffles; no shared memory on the forward path.  Parameter gradients use a deterministic two-stage
+// reduction (per-CTA partials in a workspace, then a column-sum kernel) instead of global atomics.
+#include "common.cuh"
+#include <atomic>
+extern std::atomic<long long> g_launch_count;
+
+namespace {
+
+constexpr int kWarps = 8;            // warps per CTA
+constexpr int kBwdBlocks = 148 * 2;  // CTAs of the backward kernels (partials per CTA)
+
+struct DropCfg {
+    unsigned long long seed;
+    uint32_t site;
+    uint32_t thresh16;  // 0 => dropout off
+    float inv_keep;
+};
+
+inline DropCfg make_drop(float p, uint64_t seed, uint32_t site) {
+    DropCfg d;
+    d.seed = seed;
+    d.site = site;
+    d.thresh16 = p > 0.f ? (uint32_t)lrintf(p * 65536.0f) : 0u;
+    d.inv_keep = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
+    return d;
+}
+
+// ------------------------------------------------------------------------------ forward
+template <int MAXC>
+__global__ void __launch_bounds__(kWarps * 32)
+ln_res_fwd_kernel(bf16* __restrict__ x, const bf16* __restrict__ res, const float* __restrict__ gamma,
+                  const float* __restrict__ beta, int M, int H, float eps, DropCfg dc,
+                  const uint32_t* __restrict__ d_step, bf16* __restrict__ y, float* __restrict__ mean_out,
+                  float* __restrict__ rstd_out) {
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int chunks = H >> 3;
+    const uint32_t step = dc.thresh16 ? *d_step : 0u;
+    for (int row = blockIdx.x * kWarps + warp; row < M; row += gridDim.x * kWarps) {
+        float v[MAXC][8];
+        float sum = 0.f;
+        const long long base = (long long)row * H;
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i) {
+            const int c = lane + 32 * i;
+            if (c < chunks) {
+                float xv[8];
+                unpack8(*reinterpret_cast<const bf16x8*>(x + base + c * 8), xv);
+                if (dc.thresh16) {
+                    const uint32_t keep = dropout_keep8(dc.seed, dc.site, step, (unsigned long long)row * chunks + c, dc.thresh16);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) xv[j] = ((keep >> j) & 1u) ? xv[j] * dc.inv_keep : 0.f;
+                }
+                if (res != nullptr) {
+                    float rv[8];
+                    unpack8(*reinterpret_cast<const bf16x8*>(res + base + c * 8), rv);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) xv[j] += rv[j];
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    v[i][j] = xv[j];
+                    sum += xv[j];
+                }
+                *reinterpret_cast<bf16x8*>(x + base + c * 8) = pack8(xv);  // z, kept for backward
+            }
+        }
+        const float mean = warp_sum(sum) / (float)H;
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i) {
+            if (lane + 32 * i < chunks) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float d = v[i][j] - mean;
+                    sq += d * d;
+                }
+            }
+        }
+        const float rstd = rsqrtf(warp_sum(sq) / (float)H + eps);
+        if (lane == 0) {
+            mean_out[row] = mean;
+            rstd_out[row] = rstd;
+        }
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i) {
+            const int c = lane + 32 * i;
+            if (c < chunks) {
+                float o[8];
+                const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c * 8));
+                const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c * 8) + 1);
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c * 8));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c * 8) + 1);
+                const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * g[j] + b[j];
+                *reinterpret_cast<bf16x8*>(y + base + c * 8) = pack8(o);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ backward
+// dz = rstd * (g - mean(g) - xhat * mean(g*xhat)), g = dy*gamma.  Writes dres = dz and dx = dropout'(dz);
+// per-CTA partial sums of dgamma = dy*xhat and dbeta = dy into ws[blockIdx.x][2][H].
+template <int MAXC>
+__global__ void __launch_bounds__(kWarps * 32)
+ln_res_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, const float* __restrict__ mean_in,
+                  const float* __restrict__ rstd_in, const float* __restrict__ gamma, int M, int H, DropCfg dc,
+                  const uint32_t* __restrict__ d_step, bf16* __restrict__ dx, bf16* __restrict__ dres,
+                  float* __restrict__ ws) {
+    extern __shared__ float red[];  // [kWarps][2][H] only used at the end
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int chunks = H >> 3;
+    const uint32_t step = dc.thresh16 ? *d_step : 0u;
+    float dg[MAXC][8], db[MAXC][8], gam[MAXC][8];
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+        const int c = lane + 32 * i;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            dg[i][j] = 0.f;
+            db[i][j] = 0.f;
+            gam[i][j] = (c < chunks) ? __ldg(gamma + c * 8 + j) : 0.f;
+        }
+    }
+    for (int row = blockIdx.x * kWarps + warp; row < M; row += gridDim.x * kWarps) {
+        const long long base = (long long)row * H;
+        const float mean = mean_in[row], rstd = rstd_in[row];
+        float g[MAXC][8], xh[MAXC][8];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i) {
+            const int c = lane + 32 * i;
+            if (c < chunks) {
+                float dyv[8], zv[8];
+                unpack8(ld_stream8(dy + base + c * 8), dyv);
+                unpack8(ld_stream8(z + base + c * 8), zv);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    xh[i][j] = (zv[j] - mean) * rstd;
+                    g[i][j] = dyv[j] * gam[i][j];
+                    s1 += g[i][j];
+                    s2 += g[i][j] * xh[i][j];
+                    dg[i][j] += dyv[j] * xh[i][j];
+                    db[i][j] += dyv[j];
+                }
+            }
+        }
+        s1 = warp_sum(s1) / (float)H;
+        s2 = warp_sum(s2) / (float)H;
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i) {
+            const int c = lane + 32 * i;
+            if (c < chunks) {
+                float dz[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dz[j] = rstd * (g[i][j] - s1 - xh[i][j] * s2);
+                if (dres != nullptr && dres != dx) *reinterpret_cast<bf16x8*>(dres + base + c * 8) = pack8(dz);
+                if (dc.thresh16) {
+                    const uint32_t keep = dropout_keep8(dc.seed, dc.site, step, (unsigned long long)row * chunks + c, dc.thresh16);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dz[j] = ((keep >> j) & 1u) ? dz[j] * dc.inv_keep : 0.f;
+                }
+                *reinterpret_cast<bf16x8*>(dx + base + c * 8) = pack8(dz);
+            }
+        }
+    }
+    // CTA reduction of the parameter-gradient partials
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+        const int c = lane + 32 * i;
+        if (c < chunks) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                red[(warp * 2 + 0) * H + c * 8 + j] = dg[i][j];
+                red[(warp * 2 + 1) * H + c * 8 + j] = db[i][j];
+            }
+        }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 2 * H; idx += blockDim.x) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) s += red[w * 2 * H + idx];
+        ws[(long long)blockIdx.x * 2 * H + idx] = s;
+    }
+}
+
+// out[c] += sum_r partial[r][c]
+__global__ void colsum_partials_kernel(const float* __restrict__ partial, int rows, int cols,
+                                       float* __restrict__ out0, float* __restrict__ out1, int split) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    float s = 0.f;
+    for (int r = 0; r < rows; ++r) s += partial[(long long)r * cols + c];
+    if (c < split) {
+        if (out0) out0[c] += s;
+    } else {
+        if (out1) out1[c - split] += s;
+    }
+}
+
+// ------------------------------------------------------------------------------ embeddings
+template <int MAXC>
+__global__ void __launch_bounds__(kWarps * 32)
+embed_ln_fwd_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ tt, const float* __restrict__ word,
+                    const float* __restrict__ pos, const float* __restrict__ type, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, int M, int S, int H, int vocab, int n_types, float eps, DropCfg dc,
+                    const uint32_t* __restrict__ d_step, bf16* __restrict__ y, float* __restrict__ zout,
+                    float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int chunks = H >> 3;
+    const uint32_t step = dc.thresh16 ? *d_step : 0u;
+    for (int row = blockIdx.x * kWarps + warp; row < M; row += gridDim.x * kWarps) {
+        int id = ids[row];
+        id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+        int t = tt ? tt[row] : 0;
+        t = t < 0 ? 0 : (t >= n_types ? n_types - 1 : t);
+        const int s = row % S;
+        const float* wrow = word + (long long)id * H;
+        const float* prow = pos + (long long)s * H;
+        const float* trow = type + (long long)t * H;
+        float v[MAXC][8];
+        float sum = 0.f;
+        const long long base = (long long)row * H;
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i) {
+            const int c = lane + 32 * i;
+            if (c < chunks) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(wrow + c * 8) + h);
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(prow + c * 8) + h);
+                    const float4 d = __ldg(reinterpret_cast<const float4*>(trow + c * 8) + h);
+                    // TF adds word + type first?  HF: inputs_embeds + position_embeds + token_type_embeds
+                    const float4 r = make_float4((a.x + b.x) + d.x, (a.y + b.y) + d.y, (a.z + b.z) + d.z, (a.w + b.w) + d.w);
+                    v[i][4 * h + 0] = r.x;
+                    v[i][4 * h + 1] = r.y;
+                    v[i][4 * h + 2] = r.z;
+                    v[i][4 * h + 3] = r.w;
+                    reinterpret_cast<float4*>(zout + base + c * 8)[h] = r;
+                    sum += (r.x + r.y) + (r.z + r.w);
+                }
+            }
+        }
+        const float mean = warp_sum(sum) / (float)H;
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i)
+            if (lane + 32 * i < chunks) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float d = v[i][j] - mean;
+                    sq += d * d;
+                }
+            }
+        const float rstd = rsqrtf(warp_sum(sq) / (float)H + eps);
+        if (lane == 0) {
+            mean_out[row] = mean;
+            rstd_out[row] = rstd;
+        }
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i) {
+            const int c = lane + 32 * i;
+            if (c < chunks) {
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    o[j] = (v[i][j] - mean) * rstd * __ldg(gamma + c * 8 + j) + __ldg(beta + c * 8 + j);
+                if (dc.thresh16) {
+                    const uint32_t keep = dropout_keep8(dc.seed, dc.site, step, (unsigned long long)row * chunks + c, dc.thresh16);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[j] = ((keep >> j) & 1u) ? o[j] * dc.inv_keep : 0.f;
+                }
+                *reinterpret_cast<bf16x8*>(y + base + c * 8) = pack8(o);
+            }
+        }
+    }
+}
+
+// stage A of the embedding backward: dropout' + LayerNorm backward -> dz (fp32) + dgamma/dbeta partials
+template <int MAXC>
+__global__ void __launch_bounds__(kWarps * 32)
+embed_ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ z, const float* __restrict__ mean_in,
+                    const float* __restrict__ rstd_in, const float* __restrict__ gamma, int M, int H, DropCfg dc,
+                    const uint32_t* __restrict__ d_step, float* __restrict__ dz_out, float* __restrict__ ws) {
+    extern __shared__ float red[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int chunks = H >> 3;
+    const uint32_t step = dc.thresh16 ? *d_step : 0u;
+    float dg[MAXC][8], db[MAXC][8];
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dg[i][j] = db[i][j] = 0.f;
+    for (int row = blockIdx.x * kWarps + warp; row < M; row += gridDim.x * kWarps) {
+        const long long base = (long long)row * H;
+        const float mean = mean_in[row], rstd = rstd_in[row];
+        float g[MAXC][8], xh[MAXC][8];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i) {
+            const int c = lane + 32 * i;
+            if (c < chunks) {
+                float dyv[8];
+                unpack8(ld_stream8(dy + base + c * 8), dyv);
+                if (dc.thresh16) {
+                    const uint32_t keep = dropout_keep8(dc.seed, dc.site, step, (unsigned long long)row * chunks + c, dc.thresh16);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dyv[j] = ((keep >> j) & 1u) ? dyv[j] * dc.inv_keep : 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    xh[i][j] = (z[base + c * 8 + j] - mean) * rstd;
+                    g[i][j] = dyv[j] * __ldg(gamma + c * 8 + j);
+                    s1 += g[i][j];
+                    s2 += g[i][j] * xh[i][j];
+                    dg[i][j] += dyv[j] * xh[i][j];
+                    db[i][j] += dyv[j];
+                }
+            }
+        }
+        s1 = warp_sum(s1) / (float)H;
+        s2 = warp_sum(s2) / (float)H;
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i) {
+            const int c = lane + 32 * i;
+            if (c < chunks) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dz_out[base + c * 8 + j] = rstd * (g[i][j] - s1 - xh[i][j] * s2);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+        const int c = lane + 32 * i;
+        if (c < chunks) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                red[(warp * 2 + 0) * H + c * 8 + j] = dg[i][j];
+                red[(warp * 2 + 1) * H + c * 8 + j] = db[i][j];
+            }
+        }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 2 * H; idx += blockDim.x) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) s += red[w * 2 * H + idx];
+        ws[(long long)blockIdx.x * 2 * H + idx] = s;
+    }
+}
+
+// stage B: one CTA per position s.  gpos[s] is owned exclusively (no atomics); token-type sums are
+// reduced in registers (2 types) and word rows are scatter-added with fp32 atomics (what TF's
+// IndexedSlices -> unsorted_segment_sum does for the reference).
+__global__ void embed_scatter_kernel(const float* __restrict__ dz, const int32_t* __restrict__ ids,
+                                     const int32_t* __restrict__ tt, int B, int S, int H, int vocab, int n_types,
+                                     float* __restrict__ gword, float* __restrict__ gpos, float* __restrict__ gtype) {
+    const int s = blockIdx.x;
+    for (int col = threadIdx.x * 4; col < H; col += blockDim.x * 4) {
+        float4 accp = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 acct0 = accp, acct1 = accp;
+        for (int b = 0; b < B; ++b) {
+            const long long row = (long long)b * S + s;
+            const float4 v = *reinterpret_cast<const float4*>(dz + row * H + col);
+            accp.x += v.x; accp.y += v.y; accp.z += v.z; accp.w += v.w;
+            if (gword != nullptr) {
+                int id = ids[row];
+                id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+                float* w = gword + (long long)id * H + col;
+                atomicAdd(w + 0, v.x); atomicAdd(w + 1, v.y); atomicAdd(w + 2, v.z); atomicAdd(w + 3, v.w);
+            }
+            int t = tt ? tt[row] : 0;
+            t = t < 0 ? 0 : (t >= n_types ? n_types - 1 : t);
+            if (t == 0) { acct0.x += v.x; acct0.y += v.y; acct0.z += v.z; acct0.w += v.w; }
+            else if (t == 1) { acct1.x += v.x; acct1.y += v.y; acct1.z += v.z; acct1.w += v.w; }
+            else if (gtype != nullptr) {
+                float* g = gtype + (long long)t * H + col;
+                atomicAdd(g + 0, v.x); atomicAdd(g + 1, v.y); atomicAdd(g + 2, v.z); atomicAdd(g + 3, v.w);
+            }
+        }
+        if (gpos != nullptr) {
+            float4* gp = reinterpret_cast<float4*>(gpos + (long long)s * H + col);
+            float4 o = *gp;
+            o.x += accp.x; o.y += accp.y; o.z += accp.z; o.w += accp.w;
+            *gp = o;
+        }
+        if (gtype != nullptr) {
+            float* g0 = gtype + col;
+            atomicAdd(g0 + 0, acct0.x); atomicAdd(g0 + 1, acct0.y); atomicAdd(g0 + 2, acct0.z); atomicAdd(g0 + 3, acct0.w);
+            if (n_types > 1) {
+                float* g1 = gtype + H + col;
+                atomicAdd(g1 + 0, acct1.x); atomicAdd(g1 + 1, acct1.y); atomicAdd(g1 + 2, acct1.z); atomicAdd(g1 + 3, acct1.w);
+            }
+        }
+    }
+}
+
+int grid_for_rows(int M) {
+    int want = cdiv(M, kWarps);
+    int cap = polus_num_sms() * 8;
+    return want < cap ? want : cap;
+}
+
+}  // namespace
+
+#define DISPATCH_MAXC(H, CALL4, CALL16)        \
+    if ((H) <= 1024) { CALL4; } else { CALL16; }
+
+extern "C" size_t polus_ln_ws_floats(int H) { return (size_t)kBwdBlocks * 2 * (size_t)H; }
+
+extern "C" int polus_ln_res_fwd(polus_bf16_t* x, const polus_bf16_t* res, const float* gamma, const float* beta, int M,
+                                int H, float eps, float p_drop, uint64_t seed, uint32_t site, const uint32_t* d_step,
+                                polus_bf16_t* y, float* mean, float* rstd, void* stream) {
+    POLUS_REQUIRE(M >= 0 && H > 0 && H % 8 == 0 && H <= 4096, "polus_ln_res_fwd: H must be a multiple of 8 and <= 4096 (got %d)", H);
+    POLUS_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "polus_ln_res_fwd: bad dropout %f", p_drop);
+    POLUS_REQUIRE(p_drop == 0.f || d_step != nullptr, "polus_ln_res_fwd: dropout needs d_step");
+    if (M == 0) return 0;
+    DropCfg dc = make_drop(p_drop, seed, site);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = grid_for_rows(M);
+    DISPATCH_MAXC(H,
+        (ln_res_fwd_kernel<4><<<grid, kWarps * 32, 0, st>>>((bf16*)x, (const bf16*)res, gamma, beta, M, H, eps, dc, d_step, (bf16*)y, mean, rstd)),
+        (ln_res_fwd_kernel<16><<<grid, kWarps * 32, 0, st>>>((bf16*)x, (const bf16*)res, gamma, beta, M, H, eps, dc, d_step, (bf16*)y, mean, rstd)));
+    g_launch_count++;
+    POLUS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int polus_ln_res_bwd(const polus_bf16_t* dy, const polus_bf16_t* z, const float* mean, const float* rstd,
+                                const float* gamma, int M, int H, float p_drop, uint64_t seed, uint32_t site,
+                                const uint32_t* d_step, polus_bf16_t* dx, polus_bf16_t* dres, int accumulate_res,
+                                float* ggamma, float* gbeta, float* ws, void* stream) {
+    POLUS_REQUIRE(M >= 0 && H > 0 && H % 8 == 0 && H <= 4096, "polus_ln_res_bwd: H must be a multiple of 8 and <= 4096 (got %d)", H);
+    POLUS_REQUIRE(accumulate_res == 0, "polus_ln_res_bwd: accumulate_res is reserved (must be 0)");
+    POLUS_REQUIRE(ws != nullptr && dx != nullptr, "polus_ln_res_bwd: workspace and dx required");
+    POLUS_REQUIRE(!(p_drop > 0.f && dres == dx), "polus_ln_res_bwd: dres may alias dx only without dropout");
+    if (M == 0) return 0;
+    DropCfg dc = make_drop(p_drop, seed, site);
+    cudaStream_t st = (cudaStream_t)stream;
+    int grid = grid_for_rows(M);
+    if (grid > kBwdBlocks) grid = kBwdBlocks;
+    const size_t smem = (size_t)kWarps * 2 * H * sizeof(float);
+    if (H <= 1024) {
+        static bool set4 = false;
+        if (!set4) { POLUS_CHECK_CUDA(cudaFuncSetAttribute(ln_res_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 1024 * 4)); set4 = true; }
+        ln_res_bwd_kernel<4><<<grid, kWarps * 32, smem, st>>>((const bf16*)dy, (const bf16*)z, mean, rstd, gamma, M, H, dc, d_step, (bf16*)dx, (bf16*)dres, ws);
+    } else {
+        static bool set16 = false;
+        if (!set16) { POLUS_CHECK_CUDA(cudaFuncSetAttribute(ln_res_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 4096 * 4)); set16 = true; }
+        ln_res_bwd_kernel<16><<<grid, kWarps * 32, smem, st>>>((const bf16*)dy, (const bf16*)z, mean, rstd, gamma, M, H, dc, d_step, (bf16*)dx, (bf16*)dres, ws);
+    }
+    g_launch_count++;
+    POLUS_LAUNCH_CHECK();
+    colsum_partials_kernel<<<cdiv(2 * H, 256), 256, 0, st>>>(ws, grid, 2 * H, ggamma, gbeta, H);
+    g_launch_count++;
+    POLUS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" size_t polus_embed_ws_floats(int B, int S, int H) {
+    return (size_t)B * S * H + (size_t)kBwdBlocks * 2 * (size_t)H;
+}
+
+extern "C" int polus_embed_ln_fwd(const int32_t* ids, const int32_t* tt, const float* word, const float* pos,
+                                  const float* type, const float* gamma, const float* beta, int B, int S, int H,
+                                  int vocab, int n_types, float eps, float p_drop, uint64_t seed, uint32_t site,
+                                  const uint32_t* d_step, polus_bf16_t* y, float* z, float* mean, float* rstd, void* stream) {
+    POLUS_REQUIRE(H > 0 && H % 8 == 0 && H <= 4096, "polus_embed_ln_fwd: H must be a multiple of 8 and <= 4096 (got %d)", H);
+    POLUS_REQUIRE(p_drop == 0.f || d_step != nullptr, "polus_embed_ln_fwd: dropout needs d_step");
+    const int M = B * S;
+    if (M == 0) return 0;
+    DropCfg dc = make_drop(p_drop, seed, site);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = grid_for_rows(M);
+    DISPATCH_MAXC(H,
+        (embed_ln_fwd_kernel<4><<<grid, kWarps * 32, 0, st>>>(ids, tt, word, pos, type, gamma, beta, M, S, H, vocab, n_types, eps, dc, d_step, (bf16*)y, z, mean, rstd)),
+        (embed_ln_fwd_kernel<16><<<grid, kWarps * 32, 0, st>>>(ids, tt, word, pos, type, gamma, beta, M, S, H, vocab, n_types, eps, dc, d_step, (bf16*)y, z, mean, rstd)));
+    g_launch_count++;
+    POLUS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int polus_embed_ln_bwd(const polus_bf16_t* dy, const float* z, const float* mean, const float* rstd,
+                                  const float* gamma, const int32_t* ids, const int32_t* tt, int B, int S, int H,
+                                  int vocab, int n_types, float p_drop, uint64_t seed, uint32_t site, const uint32_t* d_step,
+                                  float* gword, float* gpos, float* gtype, float* ggamma, float* gbeta, float* ws,
+                                  void* stream) {
+    POLUS_REQUIRE(H > 0 && H % 8 == 0 && H <= 4096, "polus_embed_ln_bwd: H must be a multiple of 8 and <= 4096 (got %d)", H);
+    POLUS_REQUIRE(ws != nullptr, "polus_embed_ln_bwd: workspace required (polus_embed_ws_floats)");
+    const int M = B * S;
+    if (M == 0) return 0;
+    DropCfg dc = make_drop(p_drop, seed, site);
+    cudaStream_t st = (cudaStream_t)stream;
+    float* dz = ws;
+    float* partial = ws + (size_t)M * H;
+    int grid = grid_for_rows(M);
+    if (grid > kBwdBlocks) grid = kBwdBlocks;
+    const size_t smem = (size_t)kWarps * 2 * H * sizeof(float);
+    if (H <= 1024) {
+        static bool set4 = false;
+        if (!set4) { POLUS_CHECK_CUDA(cudaFuncSetAttribute(embed_ln_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 1024 * 4)); set4 = true; }
+        embed_ln_bwd_kernel<4><<<grid, kWarps * 32, smem, st>>>((const bf16*)dy, z, mean, rstd, gamma, M, H, dc, d_step, dz, partial);
+    } else {
+        static bool set16 = false;
+        if (!set16) { POLUS_CHECK_CUDA(cudaFuncSetAttribute(embed_ln_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 4096 * 4)); set16 = true; }
+        embed_ln_bwd_kernel<16><<<grid, kWarps * 32, smem, st>>>((const bf16*)dy, z, mean, rstd, gamma, M, H, dc, d_step, dz, partial);
+    }
+    g_launch_count++;
+    POLUS_LAUNCH_CHECK();
+    colsum_partials_kernel<<<cdiv(2 * H, 256), 256, 0, st>>>(partial, grid, 2 * H, ggamma, gbeta, H);
+    g_launch_count++;
+    POLUS_LAUNCH_CHECK();
+    embed_scatter_kernel<<<S, 192, 0, st>>>(dz, ids, tt, B, S, H, vocab, n_types, gword, gpos, gtype);
+    g_launch_count++;
+    POLUS_LAUNCH_CHECK();
+    return 0;
+}

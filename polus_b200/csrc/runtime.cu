@@ -5,11 +5,14 @@
 #include <cuda_profiler_api.h>
 #include <atomic>
 #include <stdarg.h>
+#include <unordered_map>
 
 std::atomic<long long> g_launch_count{0};
 
 static thread_local char g_err[1024] = "";
 static int g_num_sms = 0;
+static long long g_capture_start = 0;
+static std::unordered_map<void*, long long> g_graph_kernels;  // kernels recorded per captured graph
 
 void polus_set_error(const char* fmt, ...) {
     va_list ap;
@@ -155,7 +158,9 @@ int polus_stream_wait_event(void* stream, void* event) {
 }
 
 int polus_graph_begin(void* stream) {
-    POLUS_CHECK_CUDA(cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeThreadLocal));
+    // relaxed mode: the host may cudaMalloc activation buffers while the step is being traced
+    POLUS_CHECK_CUDA(cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeRelaxed));
+    g_capture_start = g_launch_count.load();
     return 0;
 }
 int polus_graph_end(void* stream, void** graph_exec) {
@@ -166,14 +171,20 @@ int polus_graph_end(void* stream, void** graph_exec) {
     cudaGraphDestroy(g);
     POLUS_CHECK_CUDA(e);
     *graph_exec = ge;
+    const long long recorded = g_launch_count.load() - g_capture_start;
+    g_graph_kernels[ge] = recorded;
+    g_launch_count -= recorded;  // recorded, not executed; each replay adds them back
     return 0;
 }
 int polus_graph_launch(void* graph_exec, void* stream) {
     POLUS_CHECK_CUDA(cudaGraphLaunch((cudaGraphExec_t)graph_exec, (cudaStream_t)stream));
+    auto it = g_graph_kernels.find(graph_exec);
+    if (it != g_graph_kernels.end()) g_launch_count += it->second;
     return 0;
 }
 int polus_graph_destroy(void* graph_exec) {
     POLUS_CHECK_CUDA(cudaGraphExecDestroy((cudaGraphExec_t)graph_exec));
+    g_graph_kernels.erase(graph_exec);
     return 0;
 }
 

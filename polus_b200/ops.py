@@ -1,0 +1,640 @@
+"""Differentiable device ops + the gradient tape.
+
+Plays the role tf.GradientTape / TF's kernel library play for the reference (polus/training.py:173-185):
+the trainer records the forward computation on a tape and asks for d(loss)/d(trainable_weights).  Every
+op below is one or a few launches of libpolus_b200.so kernels; nothing computes on the host.
+Parameter gradients are accumulated straight into the fp32 gradient arena (`Param.grad`), so shared
+variables and split-K GEMMs need no extra reduction pass.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib, device
+from .tensor import BF16, F32, I32, U8, Param, Tensor
+
+# ------------------------------------------------------------------------------------------------
+# tape
+# ------------------------------------------------------------------------------------------------
+_tape_stack = []
+_rng_state = {"seed": 0x5EED5EED, "site": 0, "step_ptr": None, "step_buf": None}
+
+
+def set_seed(seed):
+    """Seed of the device dropout streams (reference: polus/utils.py:6-9 set_random_seed)."""
+    _rng_state["seed"] = int(seed) & 0xFFFFFFFFFFFFFFFF
+    _rng_state["site"] = 0
+
+
+def reset_dropout_sites():
+    _rng_state["site"] = 0
+
+
+def _next_site():
+    _rng_state["site"] += 1
+    return _rng_state["site"]
+
+
+def step_counter():
+    """Device uint32 holding optimizer.iterations; dropout counters and the LR schedule read it."""
+    if _rng_state["step_ptr"] is None:
+        buf = device.Buffer(16, zero=True)
+        device.synchronize()
+        _rng_state["step_buf"] = buf
+        _rng_state["step_ptr"] = buf.ptr
+    return _rng_state["step_ptr"]
+
+
+def set_step(value):
+    device.upload(step_counter(), np.array([value, 0, 0, 0], np.uint32))
+
+
+class Node:
+    __slots__ = ("inputs", "output", "backward")
+
+    def __init__(self, inputs, output, backward):
+        self.inputs = inputs
+        self.output = output
+        self.backward = backward
+
+
+class GradientTape:
+    """Same usage as tf.GradientTape in polus/training.py:173-185 (incl. stop_recording)."""
+
+    def __init__(self):
+        self.nodes = []
+        self.paused = 0
+
+    def __enter__(self):
+        _tape_stack.append(self)
+        return self
+
+    def __exit__(self, *exc):
+        _tape_stack.pop()
+        return False
+
+    class _Pause:
+        def __init__(self, tape):
+            self.tape = tape
+
+        def __enter__(self):
+            self.tape.paused += 1
+
+        def __exit__(self, *exc):
+            self.tape.paused -= 1
+            return False
+
+    def stop_recording(self):
+        return GradientTape._Pause(self)
+
+    def gradient(self, loss, weights):
+        """Back-propagate from a scalar loss.  Returns the gradient tensors of `weights` (views of the
+        gradient arena for Params)."""
+        grads = {id(loss): ones_like(loss)}
+        for node in reversed(self.nodes):
+            g = grads.pop(id(node.output), None)
+            if g is None:
+                continue
+            in_grads = node.backward(g)
+            for t, gi in zip(node.inputs, in_grads):
+                if gi is None or t is None or isinstance(t, Param) or not t.requires_grad:
+                    continue
+                prev = grads.get(id(t))
+                grads[id(t)] = gi if prev is None else _accumulate(prev, gi)
+        self.nodes = []
+        out = []
+        for w in weights:
+            out.append(w.grad if isinstance(w, Param) else grads.get(id(w)))
+        return out
+
+
+def _recording(*inputs):
+    if not _tape_stack:
+        return None
+    tape = _tape_stack[-1]
+    if tape.paused:
+        return None
+    if any(t is not None and t.requires_grad for t in inputs):
+        return tape
+    return None
+
+
+def _record(tape, inputs, output, backward):
+    output.requires_grad = True
+    tape.nodes.append(Node(list(inputs), output, backward))
+    return output
+
+
+def _accumulate(a, b):
+    if a.dtype == BF16 and b.dtype == BF16:
+        out = Tensor(a.shape, BF16)
+        _lib.call("polus_add_bf16", a.ptr, b.ptr, out.ptr, a.size, device.stream())
+        return out
+    a32, b32 = cast(a, F32), cast(b, F32)
+    out = Tensor(a.shape, F32)
+    _lib.call("polus_binary_f32", 0, a32.ptr, b32.ptr, a.size, b.size, out.ptr, device.stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# basic helpers (not differentiable unless stated)
+# ------------------------------------------------------------------------------------------------
+def ones_like(t):
+    out = Tensor(t.shape, F32)
+    _lib.call("polus_fill_f32", out.ptr, 1.0, out.size, device.stream())
+    return out if t.dtype == F32 else cast(out, t.dtype)
+
+
+def zeros(shape, dtype=F32):
+    return Tensor(shape, dtype, zero=True)
+
+
+def cast(x, dtype):
+    """Differentiable dtype conversion."""
+    if x.dtype == dtype:
+        return x
+    out = Tensor(x.shape, dtype)
+    _lib.call("polus_cast", x.ptr, x.dtype, out.ptr, dtype, x.size, device.stream())
+    tape = _recording(x)
+    if tape is not None and dtype in (F32, BF16) and x.dtype in (F32, BF16):
+        src = x.dtype
+        _record(tape, [x], out, lambda g: [cast(g, src)])
+    return out
+
+
+def reshape(x, shape):
+    out = x.view(shape)
+    tape = _recording(x)
+    if tape is not None:
+        old = x.shape
+        _record(tape, [x], out, lambda g: [g.view(old)])
+    return out
+
+
+def argmax(x, axis=-1):
+    """tf.argmax(..., output_type=int32), ties -> lowest index (polus/models.py:148-150)."""
+    assert axis in (-1, x.ndim - 1)
+    x = cast(x, F32)
+    cols = x.shape[-1]
+    rows = x.size // cols
+    out = Tensor(x.shape[:-1], I32)
+    _lib.call("polus_argmax_f32", x.ptr, rows, cols, out.ptr, device.stream())
+    return out
+
+
+def one_hot(idx, depth):
+    rows = idx.size
+    out = Tensor(tuple(idx.shape) + (depth,), F32)
+    _lib.call("polus_one_hot_f32", idx.ptr, rows, depth, out.ptr, device.stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# GEMM plumbing
+# ------------------------------------------------------------------------------------------------
+def _operand(t_ptr, ld, mn_major, dtype, bs0=0, bs1=0):
+    return _lib.Operand(t_ptr, ld, bs0, bs1, 1 if mn_major else 0, dtype)
+
+
+def _gemm(M, N, K, A, B, c_ptr, ldc, c_dtype, bias=None, act=0, c2=None, alpha=1.0, accumulate=0, split_k=1,
+          batch0=1, batch1=1, cbs0=0, cbs1=0, force_small=False):
+    g = _lib.Gemm()
+    g.M, g.N, g.K, g.batch0, g.batch1 = M, N, K, batch0, batch1
+    g.A, g.B = A, B
+    g.C, g.ldc, g.cbs0, g.cbs1, g.c_dtype = c_ptr, ldc, cbs0, cbs1, c_dtype
+    g.C2, g.bias = c2, bias
+    g.alpha, g.act, g.accumulate, g.split_k = alpha, act, accumulate, split_k
+    if not force_small and A.dtype == BF16 and B.dtype == BF16 and _lib.call("polus_gemm_tc_supported", C.byref(g)) == 1:
+        _lib.call("polus_gemm_tc", C.byref(g), device.stream())
+        return "tc"
+    g.split_k = 1
+    _lib.call("polus_gemm_small", C.byref(g), device.stream())
+    return "small"
+
+
+def _act_code(act):
+    if callable(act):
+        act = getattr(act, "__name__", None)
+    if act not in _lib.ACT:
+        raise ValueError(f"unsupported activation {act!r}")
+    return _lib.ACT[act]
+
+
+def linear(x, W, b=None, activation=None, out_dtype=None):
+    """y = act(x @ W + b) with W in Keras layout [in, out] (tf.keras.layers.Dense).
+
+    bf16 operands with in/out multiples of 8 run on the tcgen05 GEMM; anything else (the K-tag
+    projection, the 10-way tutorial head) on the CUDA-core GEMM with fp32 weights."""
+    act = _act_code(activation)
+    K, N = W.shape
+    lead = x.shape[:-1]
+    M = x.size // K
+    assert x.shape[-1] == K, f"Dense expected last dim {K}, got {x.shape}"
+    use_tc = (K % 8 == 0 and N % 8 == 0 and M > 0)
+    tape = _recording(x, W, b)
+    if use_tc:
+        xb = cast(x, BF16)
+        y = Tensor(lead + (N,), BF16)
+        z = Tensor(lead + (N,), BF16) if (act != 0 and tape is not None) else None
+        _gemm(M, N, K, _operand(xb.ptr, K, False, BF16), _operand(W.shadow.ptr, N, True, BF16),
+              y.ptr, N, BF16, bias=b.ptr if b is not None else None, act=act, c2=z.ptr if z is not None else None)
+        if tape is not None:
+            def backward(g, xb=xb, z=z):
+                g = cast(g, BF16)
+                need_dz = act != 0
+                dz = Tensor(g.shape, BF16) if need_dz else g
+                ws = Tensor((int(_lib.call("polus_colsum_ws_floats", N)),), F32) if b is not None else None
+                if need_dz or b is not None:
+                    _lib.call("polus_act_bwd_colsum", g.ptr, z.ptr if z is not None else None, M, N, act,
+                              dz.ptr if need_dz else None, b.grad.ptr if b is not None else None,
+                              ws.ptr if ws is not None else None, device.stream())
+                # dW[K,N] += x^T dz : A = x (MN-major over K), B = dz (MN-major over N), reduce over M
+                _gemm(K, N, M, _operand(xb.ptr, K, True, BF16), _operand(dz.ptr, N, True, BF16),
+                      W.grad.ptr, N, F32, accumulate=1, split_k=0)
+                dx = None
+                if xb.requires_grad:
+                    dx = Tensor(lead + (K,), BF16)
+                    # dx[M,K] = dz[M,N] . W[K,N]^T : both K-major over N
+                    _gemm(M, K, N, _operand(dz.ptr, N, False, BF16), _operand(W.shadow.ptr, N, False, BF16),
+                          dx.ptr, K, BF16)
+                return [dx, None, None]
+            _record(tape, [xb, W, b], y, backward)
+        return y
+    # CUDA-core path (fp32 weights)
+    y = Tensor(lead + (N,), out_dtype if out_dtype is not None else F32)
+    assert y.dtype == F32
+    z = Tensor(lead + (N,), F32) if (act != 0 and tape is not None) else None
+    _gemm(M, N, K, _operand(x.ptr, K, False, x.dtype), _operand(W.ptr, N, True, F32), y.ptr, N, F32,
+          bias=b.ptr if b is not None else None, act=act, c2=z.ptr if z is not None else None, force_small=True)
+    if tape is not None:
+        def backward(g, z=z):
+            g = cast(g, F32)
+            if act != 0:
+                dz = Tensor(g.shape, F32)
+                _lib.call("polus_unary_f32", act, z.ptr, g.ptr, 1, g.size, dz.ptr, 1.0, device.stream())
+            else:
+                dz = g
+            if b is not None:
+                _lib.call("polus_reduce_sum_f32", dz.ptr, M, N, 0, 1.0, b.grad.ptr, 1, device.stream())
+            _gemm(K, N, M, _operand(x.ptr, K, True, x.dtype), _operand(dz.ptr, N, True, F32), W.grad.ptr, N, F32,
+                  accumulate=1, force_small=True)
+            dx = None
+            if x.requires_grad:
+                dx = Tensor(lead + (K,), x.dtype if x.dtype in (F32, BF16) else F32)
+                _gemm(M, K, N, _operand(dz.ptr, N, False, F32), _operand(W.ptr, N, False, F32), dx.ptr, K, dx.dtype,
+                      force_small=True)
+            return [dx, None, None]
+        _record(tape, [x, W, b], y, backward)
+    return y
+
+
+def matmul(a, b, transpose_b=False):
+    """fp32 2-D matmul for head/score code written against tf.matmul (polus/ir/training.py compute_scores)."""
+    a, b = cast(a, F32), cast(b, F32)
+    M, K = a.shape
+    N = b.shape[0] if transpose_b else b.shape[1]
+    y = Tensor((M, N), F32)
+    Bop = _operand(b.ptr, b.shape[1], not transpose_b, F32)
+    _gemm(M, N, K, _operand(a.ptr, K, False, F32), Bop, y.ptr, N, F32, force_small=True)
+    tape = _recording(a, b)
+    if tape is not None:
+        def backward(g):
+            g = cast(g, F32)
+            da = db = None
+            if a.requires_grad:
+                da = Tensor(a.shape, F32)
+                # da[M,K] = g[M,N] . Bm[N,K] where Bm = b^T (transpose_b) or b
+                _gemm(M, K, N, _operand(g.ptr, N, False, F32),
+                      _operand(b.ptr, b.shape[1], transpose_b, F32), da.ptr, K, F32, force_small=True)
+            if b.requires_grad:
+                db = Tensor(b.shape, F32)
+                if transpose_b:  # b [N,K]: db = g^T a
+                    _gemm(N, K, M, _operand(g.ptr, N, True, F32), _operand(a.ptr, K, True, F32), db.ptr, K, F32, force_small=True)
+                else:  # b [K,N]: db = a^T g
+                    _gemm(K, N, M, _operand(a.ptr, K, True, F32), _operand(g.ptr, N, True, F32), db.ptr, N, F32, force_small=True)
+            return [da, db]
+        _record(tape, [a, b], y, backward)
+    return y
+
+
+# ------------------------------------------------------------------------------------------------
+# encoder ops
+# ------------------------------------------------------------------------------------------------
+def embed_layernorm(ids, token_type_ids, word, pos, type_, gamma, beta, eps=1e-12, p_drop=0.0):
+    """HF TFBertEmbeddings (polus/data.py:526-545): LN(word[ids]+pos+type[tt]) -> dropout.  -> bf16 [B,S,H]."""
+    Bsz, S = ids.shape
+    V, H = word.shape
+    n_types = type_.shape[0]
+    assert S <= pos.shape[0], f"sequence length {S} exceeds the {pos.shape[0]} learned positions"
+    M = Bsz * S
+    y = Tensor((Bsz, S, H), BF16)
+    z = Tensor((M, H), F32)
+    mean, rstd = Tensor((M,), F32), Tensor((M,), F32)
+    site = _next_site() if p_drop > 0 else 0
+    seed = _rng_state["seed"]
+    _lib.call("polus_embed_ln_fwd", ids.ptr, token_type_ids.ptr if token_type_ids is not None else None, word.ptr,
+              pos.ptr, type_.ptr, gamma.ptr, beta.ptr, Bsz, S, H, V, n_types, eps, p_drop, seed, site, step_counter(),
+              y.ptr, z.ptr, mean.ptr, rstd.ptr, device.stream())
+    tape = _recording(word, pos, type_, gamma, beta)
+    if tape is not None:
+        def backward(g):
+            g = cast(g, BF16)
+            ws = Tensor((int(_lib.call("polus_embed_ws_floats", Bsz, S, H)),), F32)
+            _lib.call("polus_embed_ln_bwd", g.ptr, z.ptr, mean.ptr, rstd.ptr, gamma.ptr, ids.ptr,
+                      token_type_ids.ptr if token_type_ids is not None else None, Bsz, S, H, V, n_types, p_drop, seed,
+                      site, step_counter(), word.grad.ptr, pos.grad.ptr, type_.grad.ptr, gamma.grad.ptr, beta.grad.ptr,
+                      ws.ptr, device.stream())
+            return [None] * 5
+        _record(tape, [word, pos, type_, gamma, beta], y, backward)
+    return y
+
+
+def layernorm_residual(x, res, gamma, beta, eps=1e-12, p_drop=0.0):
+    """y = LN(dropout(x) + res)  (HF TFBertSelfOutput / TFBertOutput).  x is consumed (overwritten by z)."""
+    H = x.shape[-1]
+    M = x.size // H
+    x = cast(x, BF16)
+    if res is not None:
+        res = cast(res, BF16)
+    y = Tensor(x.shape, BF16)
+    mean, rstd = Tensor((M,), F32), Tensor((M,), F32)
+    site = _next_site() if p_drop > 0 else 0
+    seed = _rng_state["seed"]
+    _lib.call("polus_ln_res_fwd", x.ptr, res.ptr if res is not None else None, gamma.ptr, beta.ptr, M, H, eps, p_drop,
+              seed, site, step_counter(), y.ptr, mean.ptr, rstd.ptr, device.stream())
+    tape = _recording(x, res, gamma, beta)
+    if tape is not None:
+        z = x  # now holds dropout(x) + res
+
+        def backward(g):
+            g = cast(g, BF16)
+            dx = Tensor(x.shape, BF16)
+            if res is None:
+                dres = None
+            elif p_drop > 0:
+                dres = Tensor(x.shape, BF16)
+            else:
+                dres = dx  # identical values: write once
+            ws = Tensor((int(_lib.call("polus_ln_ws_floats", H)),), F32)
+            _lib.call("polus_ln_res_bwd", g.ptr, z.ptr, mean.ptr, rstd.ptr, gamma.ptr, M, H, p_drop, seed, site,
+                      step_counter(), dx.ptr, dres.ptr if dres is not None else None, 0, gamma.grad.ptr, beta.grad.ptr,
+                      ws.ptr, device.stream())
+            return [dx, dres, None, None]
+        _record(tape, [x, res, gamma, beta], y, backward)
+    return y
+
+
+def attention(qkv, mask, n_heads, p_drop=0.0):
+    """Multi-head self-attention core on the packed projection qkv [B,S,3H] (q|k|v column blocks):
+    softmax(QK^T/sqrt(dh) + (1-mask)*-10000) V  ->  ctx [B,S,H]   (HF TFBertSelfAttention; mask constant
+    from polus/models.py:175-195).  Three batched tcgen05 GEMM launches + one softmax launch; the head
+    split/merge transposes of the reference are folded into the TMA tensor maps."""
+    Bsz, S, H3 = qkv.shape
+    H = H3 // 3
+    dh = H // n_heads
+    assert dh % 8 == 0 and S % 8 == 0, "attention needs head_dim and sequence length multiples of 8"
+    qkv = cast(qkv, BF16)
+    nb = Bsz * n_heads
+    scale = 1.0 / math.sqrt(dh)
+    q_ptr, k_ptr, v_ptr = qkv.ptr, qkv.ptr + H * 2, qkv.ptr + 2 * H * 2
+    ld, bs0, bs1 = H3, dh, S * H3  # batch0 = head, batch1 = batch
+    scores = Tensor((nb, S, S), BF16)
+    _gemm(S, S, dh, _operand(q_ptr, ld, False, BF16, bs0, bs1), _operand(k_ptr, ld, False, BF16, bs0, bs1),
+          scores.ptr, S, BF16, batch0=n_heads, batch1=Bsz, cbs0=S * S, cbs1=S * S * n_heads)
+    tape = _recording(qkv)
+    P = scores  # softmax in place
+    Pd = Tensor((nb, S, S), BF16) if p_drop > 0 else P
+    site = _next_site() if p_drop > 0 else 0
+    seed = _rng_state["seed"]
+    _lib.call("polus_softmax_fwd", scores.ptr, mask.ptr if mask is not None else None, Bsz, n_heads, S, S, scale,
+              p_drop, seed, site, step_counter(), P.ptr, Pd.ptr, device.stream())
+    ctx = Tensor((Bsz, S, H), BF16)
+    _gemm(S, dh, S, _operand(Pd.ptr, S, False, BF16, S * S, S * S * n_heads), _operand(v_ptr, ld, True, BF16, bs0, bs1),
+          ctx.ptr, H, BF16, batch0=n_heads, batch1=Bsz, cbs0=dh, cbs1=S * H)
+    if tape is not None:
+        def backward(g):
+            g = cast(g, BF16)  # dctx [B,S,H]
+            dqkv = Tensor((Bsz, S, H3), BF16)
+            dq_ptr, dk_ptr, dv_ptr = dqkv.ptr, dqkv.ptr + H * 2, dqkv.ptr + 2 * H * 2
+            gO = lambda ptr: _operand(ptr, H, False, BF16, dh, S * H)   # dctx as [S, dh] K-major per head
+            # dPd[S,S'] = dctx[S,dh] . V[S',dh]^T
+            dP = Tensor((nb, S, S), BF16)
+            _gemm(S, S, dh, gO(g.ptr), _operand(v_ptr, ld, False, BF16, bs0, bs1), dP.ptr, S, BF16,
+                  batch0=n_heads, batch1=Bsz, cbs0=S * S, cbs1=S * S * n_heads)
+            # dS in place of dP; Pd (dropped probabilities) in place of P
+            _lib.call("polus_softmax_bwd", P.ptr, dP.ptr, Bsz, n_heads, S, S, scale, p_drop, seed, site,
+                      step_counter(), device.stream())
+            Pd_b = P
+            pop = lambda ptr, mn: _operand(ptr, S, mn, BF16, S * S, S * S * n_heads)
+            # dV[S',dh] = Pd^T[S',S] . dctx[S,dh]
+            _gemm(S, dh, S, pop(Pd_b.ptr, True), _operand(g.ptr, H, True, BF16, dh, S * H), dv_ptr, H3, BF16,
+                  batch0=n_heads, batch1=Bsz, cbs0=dh, cbs1=S * H3)
+            # dQ[S,dh] = dS[S,S'] . K[S',dh]
+            _gemm(S, dh, S, pop(dP.ptr, False), _operand(k_ptr, ld, True, BF16, bs0, bs1), dq_ptr, H3, BF16,
+                  batch0=n_heads, batch1=Bsz, cbs0=dh, cbs1=S * H3)
+            # dK[S',dh] = dS^T[S',S] . Q[S,dh]
+            _gemm(S, dh, S, pop(dP.ptr, True), _operand(q_ptr, ld, True, BF16, bs0, bs1), dk_ptr, H3, BF16,
+                  batch0=n_heads, batch1=Bsz, cbs0=dh, cbs1=S * H3)
+            return [dqkv]
+        _record(tape, [qkv], ctx, backward)
+    return ctx
+
+
+def dropout(x, p_drop):
+    """tf.keras.layers.Dropout in training mode (polus/ner/models.py:58)."""
+    if p_drop <= 0:
+        return x
+    x = cast(x, BF16)
+    assert x.size % 8 == 0
+    y = Tensor(x.shape, BF16)
+    site, seed = _next_site(), _rng_state["seed"]
+    _lib.call("polus_dropout", x.ptr, y.ptr, x.size, p_drop, seed, site, step_counter(), device.stream())
+    tape = _recording(x)
+    if tape is not None:
+        def backward(g):
+            g = cast(g, BF16)
+            dx = Tensor(x.shape, BF16)
+            _lib.call("polus_dropout", g.ptr, dx.ptr, g.size, p_drop, seed, site, step_counter(), device.stream())
+            return [dx]
+        _record(tape, [x], y, backward)
+    return y
+
+
+def gather_rows(x, first, step, n_rows):
+    """out[i] = x2d[first + i*step]  (e.g. h[:,0,:] pooling, polus/models.py:216)."""
+    cols = x.shape[-1]
+    esz = device.dtype_size(x.dtype)
+    out = Tensor((n_rows, cols), x.dtype)
+    _lib.call("polus_gather_rows", x.ptr, cols * esz, cols * esz, first, step, n_rows, out.ptr, device.stream())
+    tape = _recording(x)
+    if tape is not None:
+        def backward(g):
+            g = cast(g, BF16)
+            dx = Tensor(x.shape, BF16, zero=True)
+            _lib.call("polus_scatter_rows_add_bf16", g.ptr, cols, first, step, n_rows, dx.ptr, device.stream())
+            return [dx if x.dtype == BF16 else cast(dx, x.dtype)]
+        _record(tape, [x], out, backward)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# losses
+# ------------------------------------------------------------------------------------------------
+def crf_nll_loss(emissions, tags, transitions, lens=None, sample_weights=None):
+    """mean_b(w_b * -crf_log_likelihood)  (polus/layers.py:86-126 via tensorflow_addons)."""
+    emissions = cast(emissions, F32)
+    Bsz, T, K = emissions.shape
+    loss = Tensor((), F32)
+    nll = Tensor((Bsz,), F32)
+    gemis = Tensor(emissions.shape, F32)
+    tape = _recording(emissions, transitions)
+    is_param = isinstance(transitions, Param)
+    gtrans = transitions.grad if is_param else Tensor(transitions.shape, F32, zero=True)
+    _lib.call("polus_crf_nll", emissions.ptr, tags.ptr, lens.ptr if lens is not None else None, transitions.ptr,
+              sample_weights.ptr if sample_weights is not None else None, Bsz, T, K, nll.ptr, loss.ptr, gemis.ptr,
+              gtrans.ptr if tape is not None else None, device.stream())
+    if tape is not None:
+        def backward(g):
+            # loss is the root of the tape in polus (training.py:180-185): g == 1
+            return [gemis, None if is_param else gtrans]
+        _record(tape, [emissions, transitions], loss, backward)
+    return loss
+
+
+def crf_decode(emissions, transitions, lens=None):
+    emissions = cast(emissions, F32)
+    Bsz, T, K = emissions.shape
+    tags = Tensor((Bsz, T), I32)
+    score = Tensor((Bsz,), F32)
+    _lib.call("polus_crf_decode", emissions.ptr, lens.ptr if lens is not None else None, transitions.ptr, Bsz, T, K,
+              tags.ptr, score.ptr, device.stream())
+    return tags, score
+
+
+def cross_entropy(kind, logits, labels, class_weights=None, negative_weight=0.0):
+    logits = cast(logits, F32)
+    Cn = logits.shape[-1]
+    rows = logits.size // Cn
+    loss = Tensor((), F32)
+    glog = Tensor(logits.shape, F32)
+    _lib.call("polus_xent", kind, logits.ptr, labels.ptr, class_weights.ptr if class_weights is not None else None,
+              float(negative_weight), rows, Cn, loss.ptr, glog.ptr, device.stream())
+    tape = _recording(logits)
+    if tape is not None:
+        _record(tape, [logits], loss, lambda g: [glog])
+    return loss
+
+
+# ------------------------------------------------------------------------------------------------
+# fp32 element-wise / reductions (score functions and custom losses of polus.ir users)
+# ------------------------------------------------------------------------------------------------
+def _binary(op, a, b):
+    a = cast(a, F32)
+    if not isinstance(b, Tensor):
+        scalar = float(b)
+        b = Tensor((1,), F32)
+        _lib.call("polus_fill_f32", b.ptr, scalar, 1, device.stream())
+    b = cast(b, F32)
+    assert a.size % b.size == 0
+    out = Tensor(a.shape, F32)
+    _lib.call("polus_binary_f32", op, a.ptr, b.ptr, a.size, b.size, out.ptr, device.stream())
+    tape = _recording(a, b)
+    if tape is not None:
+        def backward(g):
+            ga = gb = None
+            if op == 0:
+                ga, gb_full = g, g
+            elif op == 1:
+                ga, gb_full = g, unary("neg", g)
+            elif op == 2:
+                ga, gb_full = _binary(2, g, b), _binary(2, g, a)
+            else:
+                ga = _binary(3, g, b)
+                gb_full = unary("neg", _binary(3, _binary(2, g, out), b))
+            if b.requires_grad:
+                if b.size == a.size:
+                    gb = gb_full
+                else:  # broadcast over leading rows
+                    gb = Tensor(b.shape, F32)
+                    _lib.call("polus_reduce_sum_f32", gb_full.ptr, a.size // b.size, b.size, 0, 1.0, gb.ptr, 0, device.stream())
+            return [ga if a.requires_grad else None, gb]
+        _record(tape, [a, b], out, backward)
+    return out
+
+
+def add(a, b):
+    return _binary(0, a, b)
+
+
+def sub(a, b):
+    return _binary(1, a, b)
+
+
+def mul(a, b):
+    return _binary(2, a, b)
+
+
+def div(a, b):
+    return _binary(3, a, b)
+
+
+def unary(name, x, alpha=1.0):
+    code = _lib.UNARY[name]
+    x = cast(x, F32)
+    out = Tensor(x.shape, F32)
+    _lib.call("polus_unary_f32", code, x.ptr, None, 0, x.size, out.ptr, alpha, device.stream())
+    tape = _recording(x)
+    if tape is not None:
+        def backward(g):
+            dx = Tensor(x.shape, F32)
+            _lib.call("polus_unary_f32", code, x.ptr, cast(g, F32).ptr, 1, x.size, dx.ptr, alpha, device.stream())
+            return [dx]
+        _record(tape, [x], out, backward)
+    return out
+
+
+def reduce_sum(x, axis=None, mean=False):
+    """Sum (or mean) over everything (axis=None) or over the last axis (axis=-1)."""
+    x = cast(x, F32)
+    if axis is None:
+        rows, cols = 1, x.size
+        out_shape = ()
+    else:
+        assert axis in (-1, x.ndim - 1)
+        cols = x.shape[-1]
+        rows = x.size // cols
+        out_shape = x.shape[:-1]
+    scale = 1.0 / cols if mean else 1.0
+    out = Tensor(out_shape, F32)
+    _lib.call("polus_reduce_sum_f32", x.ptr, rows, cols, 1, scale, out.ptr, 0, device.stream())
+    tape = _recording(x)
+    if tape is not None:
+        def backward(g):
+            # broadcast g back over the reduced axis: dx[r, c] = g[r] * scale
+            ones = Tensor((rows, cols), F32)
+            _lib.call("polus_fill_f32", ones.ptr, scale, ones.size, device.stream())
+            dx = Tensor(x.shape, F32)
+            # dx = ones * g (row broadcast): use binary with transposed roles via per-row scaling
+            gcol = cast(g, F32)
+            _broadcast_rows_mul(ones, gcol, rows, cols, dx)
+            return [dx]
+        _record(tape, [x], out, backward)
+    return out
+
+
+def _broadcast_rows_mul(mat, vec, rows, cols, out):
+    """out[r, c] = mat[r, c] * vec[r]  -- expressed as a K=1 outer product on the CUDA-core GEMM."""
+    if rows == 1:
+        _lib.call("polus_binary_f32", 2, mat.ptr, vec.ptr, mat.size, 1, out.ptr, device.stream())
+        return
+    onesrow = Tensor((cols,), F32)
+    _lib.call("polus_fill_f32", onesrow.ptr, 1.0, cols, device.stream())
+    tmp = Tensor((rows, cols), F32)
+    _gemm(rows, cols, 1, _operand(vec.ptr, 1, False, F32), _operand(onesrow.ptr, 1, False, F32), tmp.ptr, cols, F32,
+          force_small=True)
+    _lib.call("polus_binary_f32", 2, mat.ptr, tmp.ptr, mat.size, tmp.size, out.ptr, device.stream())
+
+
+def reduce_mean(x, axis=None):
+    return reduce_sum(x, axis=axis, mean=True)

@@ -1,0 +1,154 @@
+"""Optimizers with the tf.keras call surface polus uses (polus/training.py:88-96,191,208-211):
+`optimizer.learning_rate.read_value()/.assign()`, `optimizer.apply_gradients(zip(grads, weights))`,
+`optimizer.variables()`, `optimizer.iterations`.  One fused polus_adam launch covers each contiguous
+run of trainable variables in the parameter arena."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib, device, ops
+from .tensor import F32, Param, Tensor, arena
+
+
+class Variable:
+    """Host scalar with the tf.Variable methods polus touches (training.py:90-94)."""
+
+    def __init__(self, value, on_change=None):
+        self._v = float(value)
+        self._on_change = on_change
+
+    def read_value(self):
+        return self._v
+
+    def numpy(self):
+        return self._v
+
+    def assign(self, v):
+        self._v = float(v)
+        if self._on_change:
+            self._on_change()
+
+    def __float__(self):
+        return self._v
+
+    def __mul__(self, o):
+        return self._v * o
+
+    __rmul__ = __mul__
+
+    def __repr__(self):
+        return f"Variable({self._v})"
+
+
+class WarmUp:
+    """transformers.optimization_tf.WarmUp over PolynomialDecay(power=1) (polus/schedulers.py:5-23)."""
+
+    def __init__(self, initial_learning_rate, warmup_steps, decay_steps, end_learning_rate=1e-7):
+        self.initial_learning_rate = float(initial_learning_rate)
+        self.warmup_steps = int(warmup_steps)
+        self.decay_steps = int(decay_steps)
+        self.end_learning_rate = float(end_learning_rate)
+
+    def __call__(self, step):
+        if step < self.warmup_steps:
+            return self.initial_learning_rate * (step / self.warmup_steps)
+        d = min(step - self.warmup_steps, self.decay_steps)
+        return (self.initial_learning_rate - self.end_learning_rate) * (1.0 - d / self.decay_steps) + self.end_learning_rate
+
+    # lets BaseTrainer's hvd.size() scaling treat a schedule like a variable
+    def read_value(self):
+        return self.initial_learning_rate
+
+    def assign(self, v):
+        self.initial_learning_rate = float(v)
+
+
+class Adam:
+    """tf.keras.optimizers.Adam (epsilon 1e-7, outside the bias-corrected sqrt)."""
+
+    def __init__(self, learning_rate=0.001, beta_1=0.9, beta_2=0.999, epsilon=1e-7, weight_decay_rate=0.0, name="Adam",
+                 **kwargs):
+        self.learning_rate = learning_rate if isinstance(learning_rate, WarmUp) else Variable(learning_rate)
+        self.beta_1, self.beta_2, self.epsilon = float(beta_1), float(beta_2), float(epsilon)
+        self.weight_decay_rate = float(weight_decay_rate)
+        self.name = name
+        self.grad_scale = 1.0       # set to 1/size by the distributed tape (Horovod op=Average)
+        self._state = {}            # chunk id -> (m Buffer, v Buffer, decay Buffer|None)
+        self._ranges_key = None
+        self._ranges = None
+
+    @property
+    def lr(self):
+        return self.learning_rate
+
+    @property
+    def iterations(self):
+        return int(device.download(ops.step_counter(), (1,), np.uint32)[0])
+
+    def _chunk_state(self, ch):
+        st = self._state.get(id(ch))
+        if st is None:
+            m = device.Buffer(ch.capacity * 4, zero=True)
+            v = device.Buffer(ch.capacity * 4, zero=True)
+            dm = None
+            if self.weight_decay_rate > 0:
+                dm = device.Buffer(ch.capacity)
+                device.upload(dm.ptr, ch.host_decay)
+            device.synchronize()
+            st = self._state[id(ch)] = (m, v, dm, ch)
+        return st
+
+    def variables(self):
+        """Optimizer slots as (ptr, nbytes) spans -- what broadcast_init_vars ships (training.py:211)."""
+        out = []
+        for m, v, _, ch in self._state.values():
+            out.append(Tensor((ch.used,), F32, ptr=m.ptr, block=m))
+            out.append(Tensor((ch.used,), F32, ptr=v.ptr, block=v))
+        return out
+
+    def _cfg(self):
+        c = _lib.AdamCfg()
+        lr = self.learning_rate
+        if isinstance(lr, WarmUp):
+            c.lr, c.schedule = lr.initial_learning_rate, 1
+            c.warmup_steps, c.decay_steps, c.end_lr = lr.warmup_steps, lr.decay_steps, lr.end_learning_rate
+        else:
+            c.lr, c.schedule, c.warmup_steps, c.decay_steps, c.end_lr = float(lr), 0, 0, 1, 0.0
+        c.beta1, c.beta2, c.eps = self.beta_1, self.beta_2, self.epsilon
+        c.weight_decay, c.grad_scale = self.weight_decay_rate, self.grad_scale
+        return c
+
+    @staticmethod
+    def _contiguous_ranges(weights):
+        spans = sorted(((id(w.chunk), w.offset, (w.size + 63) & ~63, w.chunk) for w in weights if isinstance(w, Param)),
+                       key=lambda s: (s[0], s[1]))
+        out = []
+        for cid, off, n, ch in spans:
+            if out and out[-1][0] is ch and out[-1][1] + out[-1][2] == off:
+                out[-1][2] += n
+            elif out and out[-1][0] is ch and off < out[-1][1] + out[-1][2]:
+                continue  # duplicate variable
+            else:
+                out.append([ch, off, n])
+        return out
+
+    def apply_gradients(self, grads_and_vars):
+        weights = [w for g, w in grads_and_vars if g is not None]
+        key = tuple(id(w) for w in weights)
+        if key != self._ranges_key:
+            self._ranges_key, self._ranges = key, self._contiguous_ranges(weights)
+        cfg = self._cfg()
+        step_ptr = ops.step_counter()
+        n_ranges = len(self._ranges)
+        for i, (ch, off, n) in enumerate(self._ranges):
+            m, v, dm, _ = self._chunk_state(ch)
+            _lib.call("polus_adam", ch.p.ptr + off * 4, ch.g.ptr + off * 4, m.ptr + off * 4, v.ptr + off * 4,
+                      ch.pb.ptr + off * 2, (dm.ptr + off) if dm is not None else None, n, C.byref(cfg), step_ptr,
+                      1 if i == n_ranges - 1 else 0, device.stream())
+
+
+class AdamWeightDecay(Adam):
+    """transformers.AdamWeightDecay: decoupled decay, skipped for LayerNorm / bias variables."""
+
+    def __init__(self, learning_rate=0.001, weight_decay_rate=0.01, **kwargs):
+        super().__init__(learning_rate=learning_rate, weight_decay_rate=weight_decay_rate, **kwargs)

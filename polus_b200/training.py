@@ -1,0 +1,364 @@
+"""polus.training (reference polus/training.py:14-397): BaseTrainer / ClassifierTrainer.
+
+Same constructor, attributes, override points and loop as the reference; `train_step` is where the
+device work happens.  The reference wraps it in `@tf.function` (one static graph per input signature,
+retraced on new shapes, training.py:150-151,171); here the first call with a given signature runs the
+step once under CUDA stream capture -- forward, loss, backward, gradient allreduce, optimizer -- and
+every later call copies the batch into the graph's input buffers and replays it with one launch.
+The returned loss is a lazy handle: it syncs only when a callback formats or does arithmetic on it
+(SURVEY.md §3.2), so the host loop never stalls the GPU by itself.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import PolusContext, _lib, device, hvd as _hvd, logger, ops, tensor
+from .callbacks import CallbackCoordinator, Profiler
+from .tensor import BF16, F32, I32, Tensor
+
+
+class LazyLoss:
+    """Scalar loss of one step, living in a pinned host slot filled by an async D2H copy."""
+
+    __slots__ = ("_slot", "_event", "_value")
+
+    def __init__(self, slot_array, event):
+        self._slot, self._event, self._value = slot_array, event, None
+
+    def _get(self):
+        if self._value is None:
+            _lib.call("polus_event_sync", self._event)
+            self._value = float(self._slot[0])
+        return self._value
+
+    def numpy(self):
+        return np.float32(self._get())
+
+    def __float__(self):
+        return self._get()
+
+    def __format__(self, spec):
+        return format(self._get(), spec)
+
+    def __repr__(self):
+        return f"LazyLoss({self._get()})"
+
+    def __mul__(self, o):
+        return self._get() * o
+
+    __rmul__ = __mul__
+
+    def __add__(self, o):
+        return self._get() + o
+
+    __radd__ = __add__
+
+    def __sub__(self, o):
+        return self._get() - o
+
+    def __rsub__(self, o):
+        return o - self._get()
+
+    def __truediv__(self, o):
+        return self._get() / o
+
+    def __lt__(self, o):
+        return self._get() < float(o)
+
+    def __gt__(self, o):
+        return self._get() > float(o)
+
+    def __array__(self, dtype=None, copy=None):
+        return np.asarray(self._get(), dtype=dtype or np.float32)
+
+
+_LOSS_RING = 256
+
+
+def _flatten_inputs(inputs):
+    """(structure, leaves): leaves are numpy arrays / Tensors in a deterministic order."""
+    leaves = []
+
+    def walk(x):
+        if isinstance(x, dict):
+            return {k: walk(x[k]) for k in x}
+        if isinstance(x, (list, tuple)):
+            return type(x)(walk(v) for v in x)
+        if x is None:
+            return None
+        leaves.append(x)
+        return ("leaf", len(leaves) - 1)
+    return walk(list(inputs)), leaves
+
+
+def _rebuild(struct, leaves):
+    if isinstance(struct, dict):
+        return {k: _rebuild(v, leaves) for k, v in struct.items()}
+    if isinstance(struct, tuple) and len(struct) == 2 and struct[0] == "leaf":
+        return leaves[struct[1]]
+    if isinstance(struct, (list, tuple)):
+        return type(struct)(_rebuild(v, leaves) for v in struct)
+    return struct
+
+
+def _leaf_dtype(x):
+    if isinstance(x, Tensor):
+        return x.dtype
+    a = np.asarray(x)
+    if a.dtype.kind == "f":
+        return F32
+    if a.dtype == np.uint8 or a.dtype == np.bool_:
+        return tensor.U8
+    return I32
+
+
+class _CompiledStep:
+    """One captured CUDA graph + its static input buffers (one per input signature)."""
+
+    def __init__(self, trainer, struct, leaves):
+        self.struct = struct
+        self.inputs = []   # device tensors the graph reads
+        self.staging = []  # pinned host arrays
+        for x in leaves:
+            dt = _leaf_dtype(x)
+            shape = x.shape if isinstance(x, Tensor) else np.asarray(x).shape
+            self.inputs.append(Tensor(shape, dt))
+            self.staging.append(None if isinstance(x, Tensor) else device.PinnedArray(shape, tensor._NP[dt]))
+        self.h2d_bytes = sum(t.nbytes for t, s in zip(self.inputs, self.staging) if s is not None)
+        self.blocks = None
+        self.graph = None
+        self.loss = None
+        self.trainer = trainer
+
+    def feed(self, leaves):
+        st = device.stream()
+        for x, t, pin in zip(leaves, self.inputs, self.staging):
+            if isinstance(x, Tensor):
+                if x.ptr != t.ptr:
+                    _lib.call("polus_memcpy_d2d", t.ptr, x.ptr, t.nbytes, st)
+            else:
+                np.copyto(pin.array, np.asarray(x), casting="unsafe")
+                _lib.call("polus_memcpy_h2d", t.ptr, pin.ptr, t.nbytes, st)
+
+    def capture(self):
+        st = device.stream()
+        ops.reset_dropout_sites()
+        self.blocks = tensor.begin_trace()
+        try:
+            _lib.call("polus_graph_begin", st)
+            try:
+                self.loss = self.trainer._step_body(*_rebuild(self.struct, self.inputs))
+            finally:
+                g = C.c_void_p()
+                _lib.call("polus_graph_end", st, C.byref(g))
+            self.graph = g.value
+        finally:
+            tensor.end_trace()
+
+    def launch(self):
+        _lib.call("polus_graph_launch", self.graph, device.stream())
+
+
+class BaseTrainer:
+    """Abstraction of a gradient-descent training procedure (reference training.py:14-338)."""
+
+    def __init__(self, model, optimizer, loss, metrics=[], post_process_logits=None, post_process_grads=None):
+        if self.__class__.__name__ == "BaseTrainer":
+            raise Exception("This is an abstraction that cannot be instantiated")
+        super().__init__()
+        self.model = model
+        self.loss = loss
+        self.optimizer = optimizer
+        self.post_process_logits = post_process_logits
+        self.post_process_grads = post_process_grads
+        self.metrics = metrics
+        self.early_stop = False
+        self.train_config = {}
+        self.step_counter = 0
+        if not hasattr(self, "trainable_weights"):
+            logger.warning(f"Since no specific trainable_weights were defined during the {self.__class__.__name__} "
+                           f"instantiation, the trainer will optimizer all the variables found on the model instance")
+            self.trainable_weights = model.trainable_weights
+        self.use_horovod = PolusContext().is_horovod_enabled()
+        self.hvd = _hvd()
+        if self.use_horovod:
+            if hasattr(optimizer, "learning_rate"):
+                _new_lr = optimizer.learning_rate.read_value() * self.hvd.size()
+                optimizer.learning_rate.assign(_new_lr)
+                logger.info(f"The learning rate was adjusted to account for the multiGPU training, local lr is {_new_lr}")
+            else:
+                logger.info("It was not possible to change the learning rate to adjusted for the multiGPU training, "
+                            "please make the attention to multiply the learning rate by hvd.size()")
+            # Horovod op=Average (training.py:182): NCCL sums, the optimizer kernel divides
+            if hasattr(optimizer, "grad_scale"):
+                optimizer.grad_scale = 1.0 / self.hvd.size()
+        # POLUS_EAGER=1 runs every step op-by-op (debugging); default is capture + replay
+        self.use_graph = os.environ.get("POLUS_EAGER", "0") != "1"
+        self._compiled = {}
+        self._warm = set()
+        self._loss_ring = None
+        self._ring_pos = 0
+        self.last_h2d_bytes = 0
+
+    def __str__(self):
+        return 'Trainer'
+
+    def forward_without_grads(self, *inputs):
+        return inputs
+
+    def forward_with_grads(self, *inputs):
+        raise NotImplementedError("forward_with_grads function must be implemented in order to compute a loss value for optimization")
+
+    # -------------------------------------------------------------------------------- the step
+    def _step_body(self, *inputs):
+        """The computation polus/training.py:173-193 traces: forward, loss, backward, allreduce, update."""
+        with ops.GradientTape() as tape:
+            with tape.stop_recording():
+                inputs = self.forward_without_grads(*inputs)
+            inputs = self.forward_with_grads(*inputs)
+            loss_value = self.loss(*inputs)
+        if not self.trainable_weights:  # Keras-style lazy build: variables exist only after the first call
+            self.trainable_weights = self.model.trainable_weights
+        tape = self.hvd.DistributedGradientTape(tape)
+        grads = tape.gradient(loss_value, self.trainable_weights)
+        if self.post_process_grads is not None:
+            grads = self.post_process_grads(grads)
+        self.optimizer.apply_gradients(zip(grads, self.trainable_weights))
+        return loss_value
+
+    def _lazy_loss(self, loss_tensor):
+        if self._loss_ring is None:
+            self._loss_ring = device.PinnedArray((_LOSS_RING, 4), np.float32)
+            self._loss_events = []
+            for _ in range(_LOSS_RING):
+                ev = C.c_void_p()
+                _lib.call("polus_event_create", C.byref(ev))
+                self._loss_events.append(ev.value)
+        i = self._ring_pos
+        self._ring_pos = (i + 1) % _LOSS_RING
+        st = device.stream()
+        _lib.call("polus_memcpy_d2h", self._loss_ring.ptr + i * 16, loss_tensor.ptr, 4, st)
+        _lib.call("polus_event_record", self._loss_events[i], st)
+        return LazyLoss(self._loss_ring.array[i], self._loss_events[i])
+
+    def train_step(self, *inputs):
+        """One optimisation step on one batch; returns the (lazy) scalar loss of that batch."""
+        struct, leaves = _flatten_inputs(inputs)
+        key = (repr(struct), tuple((tuple(x.shape) if isinstance(x, Tensor) else np.asarray(x).shape, _leaf_dtype(x))
+                                   for x in leaves))
+        if not self.use_graph or key not in self._warm:
+            # First call per signature runs op by op: it builds lazily-created variables, optimizer
+            # slots and per-kernel attributes (all of which need host<->device syncs that a stream
+            # capture forbids).  The second call captures, later calls replay.
+            self._warm.add(key)
+            ops.reset_dropout_sites()
+            dev = [x if isinstance(x, Tensor) else Tensor.from_numpy(np.asarray(x), _leaf_dtype(x)) for x in leaves]
+            self.last_h2d_bytes = sum(t.nbytes for t, x in zip(dev, leaves) if not isinstance(x, Tensor))
+            return self._lazy_loss(self._step_body(*_rebuild(struct, dev)))
+        step = self._compiled.get(key)
+        if step is None:
+            logger.debug("train_step was traced (more than a few traces means the step is receiving inputs with "
+                         "different shapes or dtypes)")
+            step = _CompiledStep(self, struct, leaves)
+            step.feed(leaves)
+            step.capture()
+            self._compiled[key] = step
+        else:
+            step.feed(leaves)
+        step.launch()
+        self.last_h2d_bytes = step.h2d_bytes
+        return self._lazy_loss(step.loss)
+
+    def lr_finder(self, tf_dataset, use_lr_found=False):
+        pass
+
+    def changing_train_config(self, **config):
+        for k, v in config.items():
+            self.train_config[k] = v
+
+    def broadcast_init_vars(self):
+        self.hvd.broadcast_variables(self.trainable_weights, root_rank=0)
+        self.hvd.broadcast_variables(self.optimizer.variables(), root_rank=0)
+
+    # -------------------------------------------------------------------------------- the loop
+    def train(self, tf_dataset=None, epochs=None, callbacks=[], train_map_f=None, steps=None, **kwargs):
+        if tf_dataset is None:
+            if "tf_dataset" in self.train_config:
+                tf_dataset = self.train_config["tf_dataset"]
+            else:
+                raise ValueError("You need to pass a training dataset to the trainer.train method")
+        if epochs is None:
+            if "epochs" in self.train_config:
+                epochs = self.train_config["epochs"]
+            else:
+                raise ValueError("You need to pass the epochs variable to the trainer.train method")
+        if len(callbacks) == 0 and "callbacks" in self.train_config:
+            callbacks = self.train_config["callbacks"]
+        if train_map_f is None and "train_map_f" in self.train_config:
+            train_map_f = self.train_config["train_map_f"]
+        if steps is None and "steps" in self.train_config:
+            steps = self.train_config["steps"]
+
+        if steps is None:
+            if hasattr(tf_dataset, "cardinality"):
+                N_STEPS = tf_dataset.cardinality()
+            elif hasattr(tf_dataset, "__len__"):
+                N_STEPS = len(tf_dataset)
+            else:
+                N_STEPS = -2  # tf.data UNKNOWN_CARDINALITY
+        else:
+            N_STEPS = steps
+
+        if "custom_data_transform_f" in kwargs:
+            train_map_f = kwargs.pop("custom_data_transform_f")
+
+        if os.getenv("POLUS_PROFILER", 'False').lower() in ('true', '1', 't', 'y', 'yes'):
+            logger.info("POLUS_PROFILER env was set to True, so the Profiler callback was added to training")
+            profiler_step_range = list(map(int, os.getenv("POLUS_PROFILER_RANGE", '10:20').split(":")))
+            callbacks = list(callbacks) + [Profiler(steps_interval=profiler_step_range)]
+
+        if not isinstance(callbacks, CallbackCoordinator):
+            callbacks = CallbackCoordinator(callbacks, trainer=self, epochs=epochs, steps=N_STEPS)
+        self.callbacks = callbacks
+        self.callbacks.on_train_begin()
+
+        for epoch in range(epochs):
+            self.callbacks.on_epoch_begin(epoch)
+            _iter = iter(tf_dataset)
+            step = 0
+            while True:
+                self.callbacks.on_train_batch_begin(epoch, step)
+                data = next(_iter, None)
+                if data is None:
+                    break
+                if train_map_f is not None:
+                    data = train_map_f(data)
+                if step == 0 and self.use_horovod:
+                    self.broadcast_init_vars()
+                loss = self.train_step(*data)
+                self.callbacks.on_train_batch_end(epoch, step, loss)
+                self.step_counter += 1
+                step += 1
+                if self.early_stop:
+                    break
+            self.callbacks.on_epoch_end(epoch)
+            if self.early_stop:
+                break
+        self.callbacks.on_train_end()
+
+
+class ClassifierTrainer(BaseTrainer):
+    """Standard classifier trainer (reference training.py:341-397)."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+
+    def forward_with_grads(self, x, y):
+        if isinstance(x, dict):
+            logits = self.model(**x, training=True)
+        else:
+            logits = self.model(x, training=True)
+        if self.post_process_logits is not None:
+            logits = self.post_process_logits(logits)
+        return y, logits
