@@ -176,24 +176,25 @@ ln_res_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, const
             }
         }
     }
-    // CTA reduction of the parameter-gradient partials
+    // CTA reduction of the parameter-gradient partials (dgamma, then dbeta: red is [kWarps][H])
 #pragma unroll
-    for (int i = 0; i < MAXC; ++i) {
-        const int c = lane + 32 * i;
-        if (c < chunks) {
+    for (int which = 0; which < 2; ++which) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                red[(warp * 2 + 0) * H + c * 8 + j] = dg[i][j];
-                red[(warp * 2 + 1) * H + c * 8 + j] = db[i][j];
+        for (int i = 0; i < MAXC; ++i) {
+            const int c = lane + 32 * i;
+            if (c < chunks) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) red[warp * H + c * 8 + j] = which == 0 ? dg[i][j] : db[i][j];
             }
         }
-    }
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < 2 * H; idx += blockDim.x) {
-        float s = 0.f;
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < H; idx += blockDim.x) {
+            float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w) s += red[w * 2 * H + idx];
-        ws[(long long)blockIdx.x * 2 * H + idx] = s;
+            for (int w = 0; w < kWarps; ++w) s += red[w * H + idx];
+            ws[(long long)blockIdx.x * 2 * H + which * H + idx] = s;
+        }
+        __syncthreads();
     }
 }
 
@@ -345,22 +346,23 @@ embed_ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ z, co
         }
     }
 #pragma unroll
-    for (int i = 0; i < MAXC; ++i) {
-        const int c = lane + 32 * i;
-        if (c < chunks) {
+    for (int which = 0; which < 2; ++which) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                red[(warp * 2 + 0) * H + c * 8 + j] = dg[i][j];
-                red[(warp * 2 + 1) * H + c * 8 + j] = db[i][j];
+        for (int i = 0; i < MAXC; ++i) {
+            const int c = lane + 32 * i;
+            if (c < chunks) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) red[warp * H + c * 8 + j] = which == 0 ? dg[i][j] : db[i][j];
             }
         }
-    }
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < 2 * H; idx += blockDim.x) {
-        float s = 0.f;
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < H; idx += blockDim.x) {
+            float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w) s += red[w * 2 * H + idx];
-        ws[(long long)blockIdx.x * 2 * H + idx] = s;
+            for (int w = 0; w < kWarps; ++w) s += red[w * H + idx];
+            ws[(long long)blockIdx.x * 2 * H + which * H + idx] = s;
+        }
+        __syncthreads();
     }
 }
 
@@ -454,14 +456,14 @@ extern "C" int polus_ln_res_bwd(const polus_bf16_t* dy, const polus_bf16_t* z, c
     cudaStream_t st = (cudaStream_t)stream;
     int grid = grid_for_rows(M);
     if (grid > kBwdBlocks) grid = kBwdBlocks;
-    const size_t smem = (size_t)kWarps * 2 * H * sizeof(float);
+    const size_t smem = (size_t)kWarps * H * sizeof(float);
     if (H <= 1024) {
         static bool set4 = false;
-        if (!set4) { POLUS_CHECK_CUDA(cudaFuncSetAttribute(ln_res_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 1024 * 4)); set4 = true; }
+        if (!set4) { POLUS_CHECK_CUDA(cudaFuncSetAttribute(ln_res_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 1024 * 4)); set4 = true; }
         ln_res_bwd_kernel<4><<<grid, kWarps * 32, smem, st>>>((const bf16*)dy, (const bf16*)z, mean, rstd, gamma, M, H, dc, d_step, (bf16*)dx, (bf16*)dres, ws);
     } else {
         static bool set16 = false;
-        if (!set16) { POLUS_CHECK_CUDA(cudaFuncSetAttribute(ln_res_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 4096 * 4)); set16 = true; }
+        if (!set16) { POLUS_CHECK_CUDA(cudaFuncSetAttribute(ln_res_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4096 * 4)); set16 = true; }
         ln_res_bwd_kernel<16><<<grid, kWarps * 32, smem, st>>>((const bf16*)dy, (const bf16*)z, mean, rstd, gamma, M, H, dc, d_step, (bf16*)dx, (bf16*)dres, ws);
     }
     g_launch_count++;
@@ -510,14 +512,14 @@ extern "C" int polus_embed_ln_bwd(const polus_bf16_t* dy, const float* z, const 
     float* partial = ws + (size_t)M * H;
     int grid = grid_for_rows(M);
     if (grid > kBwdBlocks) grid = kBwdBlocks;
-    const size_t smem = (size_t)kWarps * 2 * H * sizeof(float);
+    const size_t smem = (size_t)kWarps * H * sizeof(float);
     if (H <= 1024) {
         static bool set4 = false;
-        if (!set4) { POLUS_CHECK_CUDA(cudaFuncSetAttribute(embed_ln_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 1024 * 4)); set4 = true; }
+        if (!set4) { POLUS_CHECK_CUDA(cudaFuncSetAttribute(embed_ln_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 1024 * 4)); set4 = true; }
         embed_ln_bwd_kernel<4><<<grid, kWarps * 32, smem, st>>>((const bf16*)dy, z, mean, rstd, gamma, M, H, dc, d_step, dz, partial);
     } else {
         static bool set16 = false;
-        if (!set16) { POLUS_CHECK_CUDA(cudaFuncSetAttribute(embed_ln_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 4096 * 4)); set16 = true; }
+        if (!set16) { POLUS_CHECK_CUDA(cudaFuncSetAttribute(embed_ln_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4096 * 4)); set16 = true; }
         embed_ln_bwd_kernel<16><<<grid, kWarps * 32, smem, st>>>((const bf16*)dy, z, mean, rstd, gamma, M, H, dc, d_step, dz, partial);
     }
     g_launch_count++;

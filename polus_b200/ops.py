@@ -193,6 +193,9 @@ def one_hot(idx, depth):
 # ------------------------------------------------------------------------------------------------
 # GEMM plumbing
 # ------------------------------------------------------------------------------------------------
+GEMM_PROFILE = None  # list collecting (kind, flops, start_event, stop_event) when bench.py profiles a step
+
+
 def _operand(t_ptr, ld, mn_major, dtype, bs0=0, bs1=0):
     return _lib.Operand(t_ptr, ld, bs0, bs1, 1 if mn_major else 0, dtype)
 
@@ -205,12 +208,23 @@ def _gemm(M, N, K, A, B, c_ptr, ldc, c_dtype, bias=None, act=0, c2=None, alpha=1
     g.C, g.ldc, g.cbs0, g.cbs1, g.c_dtype = c_ptr, ldc, cbs0, cbs1, c_dtype
     g.C2, g.bias = c2, bias
     g.alpha, g.act, g.accumulate, g.split_k = alpha, act, accumulate, split_k
-    if not force_small and A.dtype == BF16 and B.dtype == BF16 and _lib.call("polus_gemm_tc_supported", C.byref(g)) == 1:
+    use_tc = (not force_small and A.dtype == BF16 and B.dtype == BF16
+              and _lib.call("polus_gemm_tc_supported", C.byref(g)) == 1)
+    prof = GEMM_PROFILE
+    if prof is not None:  # bench.py: bracket every launch with CUDA events on the launching stream
+        e0, e1 = C.c_void_p(), C.c_void_p()
+        _lib.call("polus_event_create", C.byref(e0))
+        _lib.call("polus_event_create", C.byref(e1))
+        _lib.call("polus_event_record", e0, device.stream())
+    if use_tc:
         _lib.call("polus_gemm_tc", C.byref(g), device.stream())
-        return "tc"
-    g.split_k = 1
-    _lib.call("polus_gemm_small", C.byref(g), device.stream())
-    return "small"
+    else:
+        g.split_k = 1
+        _lib.call("polus_gemm_small", C.byref(g), device.stream())
+    if prof is not None:
+        _lib.call("polus_event_record", e1, device.stream())
+        prof.append(("tc" if use_tc else "small", 2.0 * M * N * K * batch0 * batch1, e0, e1))
+    return "tc" if use_tc else "small"
 
 
 def _act_code(act):

@@ -133,11 +133,14 @@ class _CompiledStep:
 
     def feed(self, leaves):
         st = device.stream()
-        for x, t, pin in zip(leaves, self.inputs, self.staging):
+        for i, (x, t, pin) in enumerate(zip(leaves, self.inputs, self.staging)):
             if isinstance(x, Tensor):
                 if x.ptr != t.ptr:
                     _lib.call("polus_memcpy_d2d", t.ptr, x.ptr, t.nbytes, st)
             else:
+                if pin is None:
+                    pin = self.staging[i] = device.PinnedArray(t.shape, tensor._NP[t.dtype])
+                    self.h2d_bytes += t.nbytes
                 np.copyto(pin.array, np.asarray(x), casting="unsafe")
                 _lib.call("polus_memcpy_h2d", t.ptr, pin.ptr, t.nbytes, st)
 
