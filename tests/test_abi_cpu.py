@@ -1,0 +1,62 @@
+"""CPU checks of the drop-in boundary: the shared library builds, loads and exports every symbol that
+include/polus_b200.h declares (no compute calls -- there is no GPU here), and the product package never
+imports the oracle."""
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "polus_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(polus_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    import ctypes
+    lib = ctypes.CDLL(os.path.join(ROOT, "polus_b200", "libpolus_b200.so"))
+    syms = header_symbols()
+    assert len(syms) > 60
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+
+
+def test_ctypes_binding_covers_the_header():
+    from polus_b200 import _lib
+    assert not _lib.missing_exports()
+    declared = set(header_symbols())
+    bound = set(_lib.EXPORTS)
+    assert declared == bound, (sorted(declared - bound), sorted(bound - declared))
+    assert _lib.call("polus_version") >= 100
+
+
+def test_error_convention_without_gpu():
+    """Entry points return a negative status + message instead of crashing (SURVEY §8b error convention)."""
+    import ctypes as C
+    from polus_b200 import _lib
+    n = C.c_int(-1)
+    rc = _lib.load().polus_device_count(C.byref(n))
+    if rc == 0 and n.value > 0:
+        return  # running on a GPU box: nothing to check here
+    rc = _lib.load().polus_init(0)
+    assert rc < 0
+    assert _lib.last_error() != ""
+
+
+def test_struct_layout_matches_header():
+    """ctypes mirrors of polus_gemm_t / polus_adam_cfg_t: sizes the C compiler would produce."""
+    import ctypes as C
+    from polus_b200 import _lib
+    assert C.sizeof(_lib.Operand) == 40
+    assert C.sizeof(_lib.Gemm) == 20 + 4 + 80 + 8 + 24 + 8 + 8 + 8 + 16  # incl. alignment padding
+    assert C.sizeof(_lib.AdamCfg) == 40
+
+
+def test_product_path_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "polus_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, os.path.join(dirpath, f)

@@ -1,0 +1,87 @@
+"""N>1 host path on CPU: two processes over gloo (world_size 2).  Covers rendezvous, hvd-shaped
+allgather_object, dataset sharding across ranks, learning-rate scaling and rank-0-only callbacks.
+Device collectives (NCCL) are exercised on the GPU box by bench.py --gpus N."""
+import os
+import socket
+import subprocess
+import sys
+import textwrap
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = textwrap.dedent("""
+    import json, os, sys
+    sys.path.insert(0, %r)
+    import polus_b200
+    from polus_b200 import PolusContext, comm, hvd
+    from polus_b200.data import DataLoader
+    from polus_b200.optimizers import Adam
+    from polus_b200.training import ClassifierTrainer
+    from polus_b200.callbacks import runs_if_root
+    assert PolusContext().is_horovod_enabled()
+    h = hvd()
+    assert h is comm and h.size() == 2 and h.rank() == int(os.environ["RANK"])
+    gathered = h.allgather_object({"rank": h.rank(), "payload": list(range(h.rank() + 1))})
+    def gen():
+        for i in range(11):
+            yield {"i": i}
+    mine = [int(s["i"]) for s in DataLoader(gen).to_tfDataset()]
+    class M:
+        name = "m"; trainable_weights = []
+    opt = Adam(1e-3)
+    tr = ClassifierTrainer(M(), opt, None)
+    class C:
+        @runs_if_root
+        def f(self): return "ran"
+    comm.barrier()
+    print(json.dumps({"rank": h.rank(), "gathered": gathered, "mine": mine, "lr": opt.learning_rate.read_value(),
+                      "grad_scale": opt.grad_scale, "root_only": C().f()}))
+""") % ROOT
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_two_rank_host_path_over_gloo():
+    import json
+    port = _free_port()
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port), POLUS_COMM_HOST_ONLY="1", POLUS_LOGGER_LEVEL="ERROR")
+        procs.append(subprocess.Popen([sys.executable, "-c", WORKER], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = []
+    for p in procs:
+        o, e = p.communicate(timeout=180)
+        assert p.returncode == 0, e[-2000:]
+        outs.append(json.loads(o.strip().splitlines()[-1]))
+    outs.sort(key=lambda d: d["rank"])
+    for d in outs:
+        assert d["gathered"] == [{"rank": 0, "payload": [0]}, {"rank": 1, "payload": [0, 1]}]
+        assert abs(d["lr"] - 2e-3) < 1e-12 and d["grad_scale"] == 0.5     # LR x size (training.py:90-94), op=Average
+    assert outs[0]["mine"] == [0, 2, 4, 6, 8, 10] and outs[1]["mine"] == [1, 3, 5, 7, 9]  # i mod N (data.py:94-96)
+    assert outs[0]["root_only"] == "ran" and outs[1]["root_only"] is None
+
+
+def test_file_rendezvous_fallback(tmp_path):
+    """Same gather without torch.distributed: POLUS_RENDEZVOUS_DIR shared directory."""
+    code = textwrap.dedent("""
+        import os, sys, json
+        sys.path.insert(0, %r)
+        from polus_b200 import comm
+        assert comm.init(use_device=False) is None
+        print(json.dumps(comm.allgather_object(("r", comm.rank()))))
+    """) % ROOT
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", POLUS_RENDEZVOUS_DIR=str(tmp_path))
+        procs.append(subprocess.Popen([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    for p in procs:
+        o, e = p.communicate(timeout=60)
+        assert p.returncode == 0, e[-2000:]
+        assert o.strip().splitlines()[-1] == '[["r", 0], ["r", 1]]'

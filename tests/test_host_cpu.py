@@ -1,0 +1,261 @@
+"""Host-side logic of the polus-shaped API (no GPU): utils/core/data/schedulers/labels/callbacks/bucket plan.
+Several cases mirror the reference's own unit tests (tests/test_utils.py, tests/test_core.py, tests/test_data.py)."""
+import json
+
+import numpy as np
+import pytest
+
+
+# ------------------------------------------------------------------ utils (reference tests/test_utils.py)
+def test_singleton_identity():
+    from polus_b200.utils import Singleton
+
+    class A(metaclass=Singleton):
+        pass
+
+    class B(metaclass=Singleton):
+        pass
+    assert A() is A() and B() is B() and A() is not B()
+
+
+def test_flatten_dict_cases():
+    from polus_b200.utils import flatten_dict
+    assert flatten_dict({"a": 1, "b": {"c": 2, "d": {"e": 3}}}) == {"a": 1, "c": 2, "e": 3}
+    assert flatten_dict({}) == {}
+    # duplicate key: the later occurrence overrides (reference tests/test_utils.py:26-55)
+    assert flatten_dict({"a": 1, "b": {"a": 2}}) == {"a": 2}
+    assert flatten_dict({"b": {"a": 2}, "a": 1}) == {"a": 1}
+
+
+def test_is_jsonable_and_tensor_roundtrip():
+    from polus_b200.utils import complex_json_deserializer, complex_json_serializer, is_jsonable, merge_dicts, unique
+    assert is_jsonable({"a": [1, 2, "x"]}) and not is_jsonable({"a": {1, 2}})
+    mask = np.ones((4, 4), np.float32)
+    mask[1, 3] = 0
+    data = {"model": {"mask_impossible_transitions": mask, "hidden": 128}, "name": "m"}
+    back = complex_json_deserializer(json.loads(json.dumps(complex_json_serializer(data))))
+    assert back["name"] == "m" and back["model"]["hidden"] == 128
+    assert np.array_equal(back["model"]["mask_impossible_transitions"], mask)
+    assert merge_dicts({"a": 1}, {"b": 2}, {"a": 3}) == {"a": 3, "b": 2}
+    assert unique([1, 2, 2, 3, 1]) == [1, 2, 3]
+    with pytest.raises(ValueError):
+        complex_json_serializer({"x": object()})
+
+
+def test_jit_flag_roundtrip(monkeypatch):
+    from polus_b200.core import get_jit_compile, set_jit_compile
+    monkeypatch.delenv("POLUS_JIT", raising=False)
+    assert get_jit_compile() is False  # default (reference tests/test_core.py)
+    set_jit_compile(True)
+    assert get_jit_compile() is True
+    set_jit_compile(False)
+    assert get_jit_compile() is False
+
+
+def test_execute_if():
+    from polus_b200.core import execute_if
+
+    class X:
+        flag = True
+
+        @execute_if("flag")
+        def f(self):
+            return 1
+    x = X()
+    assert x.f() == 1
+    x.flag = False
+    assert x.f() is None
+
+
+# ------------------------------------------------------------------ data (reference tests/test_data.py:28-80)
+def _gen(n=1000):
+    def source_generator():
+        for i in range(n):
+            yield {"id": i, "text": np.full(4, i, np.int32)}
+    return source_generator
+
+
+def test_dataloader_order_count_and_dataset_verbs():
+    from polus_b200.data import DataLoader
+    dl = DataLoader(_gen())
+    assert [s["id"] for s in dl] == list(range(1000))
+    assert dl.get_n_samples() == 1000
+    ds = dl.to_tfDataset()
+    assert dl.shapes["text"] == (4,) and dl.shapes["id"] == ()
+    assert [int(s["id"]) for s in ds] == list(range(1000))
+    b = list(ds.batch(128, drop_remainder=True))
+    assert len(b) == 7 and b[0]["text"].shape == (128, 4) and b[0]["id"][5] == 5
+    assert len(list(ds.batch(128))) == 8
+    mapped = ds.map(lambda d: (d["text"].astype(np.float32), d["id"])).batch(10)
+    x, y = next(iter(mapped))
+    assert x.shape == (10, 4) and x.dtype == np.float32 and list(y) == list(range(10))
+    shuffled = [int(s["id"]) for s in ds.shuffle(1000, seed=0)]
+    assert sorted(shuffled) == list(range(1000)) and shuffled != list(range(1000))
+    assert ds.batch(100).cardinality() == -2  # unknown: generator-backed, like tf.data
+
+
+def test_dynamic_shape_inference():
+    from polus_b200.core import find_dtype_and_shapes
+
+    def g():
+        for i in range(1, 20):
+            yield {"x": np.zeros((i, 3), np.float32)}
+    dt, sh = find_dtype_and_shapes(g(), k=10)
+    assert sh["x"] == (None, 3) and dt["x"] == np.float32
+    with pytest.raises(ValueError):
+        find_dtype_and_shapes(iter([1, 2, 3]), k=2)
+
+
+def test_shard_rule_is_i_mod_n_before_batching():
+    """polus/data.py:94-96: sample i -> rank i mod N, applied before the user batches."""
+    from polus_b200.data import Dataset
+    ds = Dataset.from_generator(lambda: iter(range(10)))
+    assert list(ds.shard(4, 1)) == [1, 5, 9]
+    assert [b.tolist() for b in ds.shard(2, 0).batch(2)] == [[0, 2], [4, 6], [8]]
+
+
+# ------------------------------------------------------------------ schedule / labels
+def test_warmup_scheduler_matches_oracle():
+    from oracle import numpy_ref as R
+    from polus_b200.schedulers import warmup_scheduler
+    s = warmup_scheduler(200, 3e-4, warmup_percentage=0.1, end_lr=123.0)  # end_lr ignored, like the reference
+    assert s.warmup_steps == 20 and s.decay_steps == 180 and s.end_learning_rate == 1e-7
+    for step in (0, 1, 19, 20, 21, 100, 199, 200, 5000):
+        assert abs(s(step) - R.warmup_schedule_lr(step, 200, 3e-4)) < 1e-15
+
+
+def _ref_get_bio(spans, entities):
+    """Loop-for-loop restatement of polus/ner/bio.py:13-114 (entity_fits_spans / update_tags / get_bio)."""
+    tags = ["O"] * len(spans)
+    for (es, ee, typ) in sorted(entities, key=lambda e: e[1] - e[0], reverse=True):
+        start_found = end_found = False
+        idx = []
+        for i, sp in enumerate(spans):
+            if not start_found:
+                if es == sp[0]:
+                    start_found = True
+                elif es < sp[0]:
+                    break
+            if start_found and not end_found:
+                idx.append(i)
+                if ee == sp[1]:
+                    end_found = True
+                    break
+                elif ee < sp[1]:
+                    break
+        if start_found and end_found and all(tags[i] == "O" for i in idx):
+            tags[idx[0]] = f"B-{typ}"
+            for i in idx[1:]:
+                tags[i] = f"I-{typ}"
+    return tags
+
+
+def test_bio_labels_bit_exact_vs_reference_algorithm():
+    from polus_b200.ner.bio import get_bio
+    from polus_b200.ner.utils import TAG2INT
+    assert TAG2INT == {"PAD": 0, "O": 1, "B-Chemical": 2, "I-Chemical": 3}
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        n = int(rng.integers(1, 15))
+        cuts = np.sort(rng.choice(np.arange(1, 80), size=2 * n, replace=False))
+        spans = [(int(cuts[2 * i]), int(cuts[2 * i + 1])) for i in range(n)]
+        ents = []
+        for _ in range(int(rng.integers(0, 6))):
+            a, b = sorted(rng.integers(0, n, 2))
+            s, e = spans[a][0], spans[b][1]
+            if rng.uniform() < 0.3:
+                s += 1  # misaligned: must be discarded
+            ents.append((int(s), int(e), "Chemical"))
+        assert get_bio(spans, ents) == _ref_get_bio(spans, ents)
+    assert get_bio([(0, 3), (4, 9), (10, 12)], [(4, 12, "Chemical"), (4, 9, "Chemical")]) == ["O", "B-Chemical", "I-Chemical"]
+
+
+# ------------------------------------------------------------------ callbacks + trainer loop (fake step, no device)
+def test_training_loop_order_and_callbacks(monkeypatch):
+    from polus_b200.callbacks import Callback, ConsoleLogCallback, EarlyStop, LossSmoothCallback, TimerCallback
+    from polus_b200.training import BaseTrainer, ClassifierTrainer
+
+    with pytest.raises(Exception):
+        BaseTrainer(None, None, None)
+
+    class M:
+        name = "fake"
+        trainable_weights = []
+
+    events = []
+
+    class Spy(Callback):
+        def on_train_begin(self): events.append("tb")
+        def on_epoch_begin(self, e): events.append(f"eb{e}")
+        def on_train_batch_begin(self, e, s): events.append(f"bb{e}.{s}")
+        def on_train_batch_end(self, e, s, l): events.append(f"be{e}.{s}")
+        def on_epoch_end(self, e): events.append(f"ee{e}")
+        def on_train_end(self): events.append("te")
+
+    tr = ClassifierTrainer(M(), optimizer=object(), loss=None)
+    losses = iter([4.0, 3.0, 2.0, 1.0, 0.5, 0.25])
+    monkeypatch.setattr(tr, "train_step", lambda *d: next(losses))
+    smooth = LossSmoothCallback(output=True)
+    with pytest.raises(ValueError):
+        tr.train(epochs=1)
+    tr.train([(1, 2), (3, 4), (5, 6)], epochs=2, callbacks=[smooth, TimerCallback(), Spy(), ConsoleLogCallback(), EarlyStop()])
+    assert events == ["tb", "eb0", "bb0.0", "be0.0", "bb0.1", "be0.1", "bb0.2", "be0.2", "bb0.3", "ee0",
+                      "eb1", "bb1.0", "be1.0", "bb1.1", "be1.1", "bb1.2", "be1.2", "bb1.3", "ee1", "te"]
+    assert tr.step_counter == 6
+    # bias-corrected EMA, beta 0.97 (callbacks.py:176-182)
+    mov, n = 0.0, 0
+    for l in [4.0, 3.0, 2.0, 1.0, 0.5, 0.25]:
+        n += 1
+        mov = 0.97 * mov + 0.03 * l
+    assert abs(smooth.smooth_loss - mov / (1 - 0.97 ** n)) < 1e-12
+
+
+def test_profiler_env_appends_callback_and_stops(monkeypatch):
+    from polus_b200 import callbacks
+    from polus_b200.training import ClassifierTrainer
+
+    class M:
+        name = "fake"
+        trainable_weights = []
+    calls = []
+    monkeypatch.setattr(callbacks._lib, "call", lambda name, *a: calls.append(name) or 0)
+    monkeypatch.setenv("POLUS_PROFILER", "true")
+    monkeypatch.setenv("POLUS_PROFILER_RANGE", "2:4")
+    tr = ClassifierTrainer(M(), optimizer=object(), loss=None)
+    monkeypatch.setattr(tr, "train_step", lambda *d: 1.0)
+    tr.train([(0, 0)] * 10, epochs=1, callbacks=[])
+    assert tr.step_counter == 4 and tr.early_stop  # window [2,4) then stop, like the reference
+    assert calls.count("polus_profiler_start") == 1 and calls.count("polus_profiler_stop") == 1
+
+
+def test_gradient_bucket_plan():
+    """Buckets are contiguous arena spans, ordered from the end of the arena (backward order)."""
+    from polus_b200 import comm
+    from polus_b200.tensor import Param
+
+    class Chunk:
+        pass
+    ch = Chunk()
+    ps, off = [], 0
+    for n in [1000, 64, 5000, 64, 300000, 64, 128]:
+        p = Param.__new__(Param)
+        p.shape, p.chunk, p.offset = (n,), ch, off
+        off += (n + 63) & ~63
+        ps.append(p)
+    buckets = comm.plan_buckets(ps, bucket_bytes=100000)
+    spans = [(b[1], b[2]) for b in buckets]
+    assert sum(n for _, n in spans) == off
+    assert spans[0][0] + spans[0][1] == off                       # first bucket ends the arena
+    for (o1, n1), (o2, n2) in zip(spans, spans[1:]):
+        assert o2 + n2 == o1                                       # contiguous, descending
+    assert all(n * 4 < 100000 + 4 * 300032 for _, n in spans)
+    assert [id(p) for b in buckets for p in b[3]] == [id(p) for p in reversed(ps)]
+
+
+def test_mock_horovod_surface():
+    from polus_b200.mock import horovod as hvd
+    assert hvd.init() == "mock" and hvd.size() == 1 and hvd.local_rank() == 0
+    t = object()
+    assert hvd.DistributedGradientTape(t) is t
+    assert hvd.broadcast_variables([1, 2], root_rank=0) is None
+    assert hvd.allgather_object({"a": 1}) == [{"a": 1}]
