@@ -176,16 +176,16 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel family: every tcgen05 GEMM launch of one op-by-op step, event-bracketed
     roof = None
+    prof = []
+    ops.GEMM_PROFILE = prof
+    trainer.use_graph = False
+    for i in range(2):  # every rank runs these steps (they contain the gradient allreduce); rank 0 reports
+        prof.clear()
+        float(trainer.train_step(*batches[i]))
+    ops.GEMM_PROFILE = None
+    trainer.use_graph = True
+    barrier()
     if rank == 0:
-        prof = []
-        ops.GEMM_PROFILE = prof
-        trainer.use_graph = False
-        for i in range(2):
-            prof.clear()
-            float(trainer.train_step(*batches[i]))
-        ops.GEMM_PROFILE = None
-        trainer.use_graph = True
-        device.device_sync()
         tot_ms, tot_flop, n = 0.0, 0.0, 0
         for kind, flop, e0, e1 in prof:
             if kind != "tc":

@@ -5,6 +5,12 @@
 // polus/models.py:205-213), the NER head Dense (polus/ner/models.py:36) and every gradient GEMM that
 // tf.GradientTape derives from them (polus/training.py:185).
 //
+// Two variants of one kernel template:
+//   CG = 2 (default for M >= 256): a CTA PAIR (cluster 2x1x1, two SMs of one TPC) owns a 256 x BN tile and
+//           issues tcgen05.mma.cta_group::2 (M = 256).  Each CTA stages its own 128 rows of A and HALF of the
+//           B tile; the tensor cores read both halves, so L2->SM traffic per FLOP drops by a third vs CG = 1
+//           (the 1-CTA kernel was L2-bandwidth bound: profiles/r01_gemm_probe_v1.log).
+//   CG = 1: one CTA owns a 128 x BN tile (small M, odd shapes).
 // Kernel shape (persistent, warp-specialised, one CTA per SM):
 //   warp 0      TMA producer       global -> smem ring (kStages x {A 128x64, B BNx64} bf16)
 //   warp 1      MMA issuer         one thread issues 4 x tcgen05.mma (K=16) per stage
@@ -17,6 +23,7 @@
 #include "ptx.cuh"
 #include <cuda.h>
 #include <atomic>
+#include <stdlib.h>
 
 extern std::atomic<long long> g_launch_count;
 
@@ -42,12 +49,14 @@ struct TcParams {
     int accumulate;
 };
 
-template <int BN>
+template <int BN, int CG>
 struct Cfg {
-    static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
-    static constexpr int B_STAGE_BYTES = BN * BK * 2;
+    static constexpr int BN_LOCAL = BN / CG;  // rows of the B tile this CTA stages
+    static constexpr int B_STAGE_BYTES = BN_LOCAL * BK * 2;
+    static constexpr int kStageBytes = A_STAGE_BYTES + B_STAGE_BYTES;
+    static constexpr int kStages = (192 * 1024) / kStageBytes > 10 ? 10 : (192 * 1024) / kStageBytes;
     static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
-    static constexpr int kSmemBytes = 1024 + kStages * (A_STAGE_BYTES + B_STAGE_BYTES) + 256;
+    static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 256;
 };
 
 __device__ __forceinline__ void store_chunk(const TcParams& p, float* v, long long row_off, int col0,
@@ -89,14 +98,19 @@ __device__ __forceinline__ void store_chunk(const TcParams& p, float* v, long lo
     }
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const TcParams p) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, CG>;
     constexpr int kStages = C::kStages;
+    constexpr int BN_LOCAL = C::BN_LOCAL;
     constexpr int B_STAGE_BYTES = C::B_STAGE_BYTES;
-    constexpr uint32_t kStageTx = A_STAGE_BYTES + B_STAGE_BYTES;
+    constexpr uint32_t kStageTx = (A_STAGE_BYTES + B_STAGE_BYTES) * CG;  // bytes landing on the leader's barrier
+    const uint32_t cta_rank = CG == 2 ? ptx::cluster_ctarank() : 0u;
+    const bool is_leader = cta_rank == 0;
+    const int tile0 = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tile_step = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -123,13 +137,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(&tfull_bar[s], 1);
-            ptx::mbar_init(&tempty_bar[s], 4);
+            ptx::mbar_init(&tempty_bar[s], 4 * CG);  // one arrive per epilogue warp of every CTA of the group
         }
         ptx::fence_barrier_init();
     }
-    if (warp == 2) ptx::tmem_alloc<C::kTmemCols>(tmem_slot);
+    if (warp == 2) {
+        if (CG == 2) ptx::tmem_alloc_2sm<C::kTmemCols>(tmem_slot);
+        else ptx::tmem_alloc<C::kTmemCols>(tmem_slot);
+    }
     ptx::tc_fence_before();
     __syncthreads();
+    if (CG == 2) ptx::cluster_sync();  // peer barriers initialised before any remote arrive / multicast commit
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -149,31 +167,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+            auto load = [&](void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+                if (CG == 2) ptx::tma_load_4d_2sm(dst, map, bar, c0, c1, c2, c3);
+                else ptx::tma_load_4d(dst, map, bar, c0, c1, c2, c3);
+            };
+            for (int t = tile0; t < p.num_tiles; t += tile_step) {
                 int mt, nt, sp, b0, b1;
                 decode(t, mt, nt, sp, b0, b1);
                 const int kb0 = sp * p.kb_per_split;
                 const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+                const int m0 = (mt * CG + (int)cta_rank) * BM;          // this CTA's 128 rows of A / C
+                const int n0 = nt * BN + (int)cta_rank * BN_LOCAL;      // this CTA's share of the B tile
                 for (int kb = kb0; kb < kb1; ++kb) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                    ptx::mbar_expect_tx(&full_bar[stage], kStageTx);
+                    if (is_leader) ptx::mbar_expect_tx(&full_bar[stage], kStageTx);
                     uint8_t* a = sA + stage * A_STAGE_BYTES;
                     uint8_t* b = sB + stage * B_STAGE_BYTES;
                     if (!A_MN) {
-                        ptx::tma_load_4d(a, &tmA, &full_bar[stage], kb * BK, mt * BM, b0, b1);
+                        load(a, &tmA, &full_bar[stage], kb * BK, m0, b0, b1);
                     } else {
 #pragma unroll
                         for (int g = 0; g < BM / 64; ++g)
-                            ptx::tma_load_4d(a + g * (BK * 128), &tmA, &full_bar[stage],
-                                             mt * BM + g * 64, kb * BK, b0, b1);
+                            load(a + g * (BK * 128), &tmA, &full_bar[stage], m0 + g * 64, kb * BK, b0, b1);
                     }
                     if (!B_MN) {
-                        ptx::tma_load_4d(b, &tmB, &full_bar[stage], kb * BK, nt * BN, b0, b1);
+                        load(b, &tmB, &full_bar[stage], kb * BK, n0, b0, b1);
                     } else {
 #pragma unroll
-                        for (int g = 0; g < BN / 64; ++g)
-                            ptx::tma_load_4d(b + g * (BK * 128), &tmB, &full_bar[stage],
-                                             nt * BN + g * 64, kb * BK, b0, b1);
+                        for (int g = 0; g < BN_LOCAL / 64; ++g)
+                            load(b + g * (BK * 128), &tmB, &full_bar[stage], n0 + g * 64, kb * BK, b0, b1);
                     }
                     if (++stage == kStages) {
                         stage = 0;
@@ -184,8 +206,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+        if (lane == 0 && is_leader) {
+            constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM * CG, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
             const uint64_t adesc_base = A_MN ? ptx::umma_desc_base(BK * 128, 1024) : ptx::umma_desc_base(16, 1024);
             const uint64_t bdesc_base = B_MN ? ptx::umma_desc_base(BK * 128, 1024) : ptx::umma_desc_base(16, 1024);
             constexpr uint32_t a_kstep = A_MN ? 2048 : 32;  // bytes per UMMA_K=16 step
@@ -194,7 +216,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+            for (int t = tile0; t < p.num_tiles; t += tile_step) {
                 int mt, nt, sp, b0, b1;
                 decode(t, mt, nt, sp, b0, b1);
                 const int kb0 = sp * p.kb_per_split;
@@ -209,17 +231,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t b_addr = ptx::smem_u32(sB + stage * B_STAGE_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
-                        ptx::umma_bf16(tmem_d, ptx::umma_desc(adesc_base, a_addr + k * a_kstep),
-                                       ptx::umma_desc(bdesc_base, b_addr + k * b_kstep), idesc,
-                                       (kb > kb0 || k > 0) ? 1u : 0u);
+                        const uint64_t ad = ptx::umma_desc(adesc_base, a_addr + k * a_kstep);
+                        const uint64_t bd = ptx::umma_desc(bdesc_base, b_addr + k * b_kstep);
+                        const uint32_t accum = (kb > kb0 || k > 0) ? 1u : 0u;
+                        if (CG == 2) ptx::umma_bf16_2sm(tmem_d, ad, bd, idesc, accum);
+                        else ptx::umma_bf16(tmem_d, ad, bd, idesc, accum);
                     }
-                    ptx::umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+                    // smem slot reusable (in both CTAs of the pair) once these MMAs retire
+                    if (CG == 2) ptx::umma_commit_2sm(&empty_bar[stage]);
+                    else ptx::umma_commit(&empty_bar[stage]);
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                ptx::umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+                // accumulator complete -> epilogue warps of both CTAs
+                if (CG == 2) ptx::umma_commit_2sm(&tfull_bar[acc]);
+                else ptx::umma_commit(&tfull_bar[acc]);
                 if (++acc == 2) {
                     acc = 0;
                     acc_phase ^= 1;
@@ -231,12 +259,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32)
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        for (int t = tile0; t < p.num_tiles; t += tile_step) {
             int mt, nt, sp, b0, b1;
             decode(t, mt, nt, sp, b0, b1);
             ptx::mbar_wait(&tfull_bar[acc], acc_phase);
             ptx::tc_fence_after();
-            const int row = mt * BM + quad * 32 + lane;
+            const int row = (mt * CG + (int)cta_rank) * BM + quad * 32 + lane;
             const long long row_off = (long long)b0 * p.cbs0 + (long long)b1 * p.cbs1 + (long long)row * p.ldc;
             const bool add_bias = (p.bias != nullptr) && (sp == 0);
 #pragma unroll 1
@@ -269,7 +297,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) {
+                if (CG == 2) ptx::mbar_arrive_remote(&tempty_bar[acc], 0);  // the leader's MMA thread waits on it
+                else ptx::mbar_arrive(&tempty_bar[acc]);
+            }
             if (++acc == 2) {
                 acc = 0;
                 acc_phase ^= 1;
@@ -279,9 +310,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     ptx::tc_fence_before();
     __syncthreads();
+    if (CG == 2) ptx::cluster_sync();  // the peer may still be reading our smem / arriving on our barriers
     if (warp == 2) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc<C::kTmemCols>(tmem_base);
+        if (CG == 2) ptx::tmem_dealloc_2sm<C::kTmemCols>(tmem_base);
+        else ptx::tmem_dealloc<C::kTmemCols>(tmem_base);
     }
 }
 
@@ -340,28 +373,42 @@ int make_map(CUtensorMap* map, const polus_operand_t& op, long long mn_len, long
     return 0;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int CG>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, cudaStream_t st) {
-    auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
+    auto kern = gemm_tc_kernel<BN, A_MN, B_MN, CG>;
+    using C = Cfg<BN, CG>;
     static bool attr_set = false;
     if (!attr_set) {
-        POLUS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes));
+        POLUS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
         attr_set = true;
     }
-    int grid = p.num_tiles < polus_num_sms() ? p.num_tiles : polus_num_sms();
-    kern<<<grid, kThreads, Cfg<BN>::kSmemBytes, st>>>(ta, tb, p);
+    int groups = polus_num_sms() / CG;
+    if (p.num_tiles < groups) groups = p.num_tiles;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(groups * CG);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = C::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    POLUS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
     g_launch_count++;
     POLUS_LAUNCH_CHECK();
     return 0;
 }
 
-template <int BN>
+template <int BN, int CG>
 int launch_major(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p,
                  cudaStream_t st) {
-    if (!a_mn && !b_mn) return launch<BN, false, false>(ta, tb, p, st);
-    if (!a_mn && b_mn) return launch<BN, false, true>(ta, tb, p, st);
-    if (a_mn && !b_mn) return launch<BN, true, false>(ta, tb, p, st);
-    return launch<BN, true, true>(ta, tb, p, st);
+    if (!a_mn && !b_mn) return launch<BN, false, false, CG>(ta, tb, p, st);
+    if (!a_mn && b_mn) return launch<BN, false, true, CG>(ta, tb, p, st);
+    if (a_mn && !b_mn) return launch<BN, true, false, CG>(ta, tb, p, st);
+    return launch<BN, true, true, CG>(ta, tb, p, st);
 }
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -395,7 +442,10 @@ extern "C" int polus_gemm_tc(const polus_gemm_t* g, void* stream) {
     const int batch1 = g->batch1 < 1 ? 1 : g->batch1;
     const int sms = polus_num_sms();
 
-    const long long mt = cdiv(g->M, BM);
+    // CTA pairs (cta_group::2, 256-row tiles) whenever there are at least two 128-row tiles to pair up
+    static const int cg_env = getenv("POLUS_GEMM_CG") ? atoi(getenv("POLUS_GEMM_CG")) : 0;
+    const int CG = (g->M > BM && g->N > 64 && cg_env != 1) ? 2 : 1;
+    const long long mt = cdiv(g->M, BM * CG);
     const long long nb = (long long)batch0 * batch1;
     const int kb_total = cdiv(g->K, BK);
     // split_k == 0 with accumulate: pick the split that fills the machine (wgrad: few output tiles, long K)
@@ -403,9 +453,9 @@ extern "C" int polus_gemm_tc(const polus_gemm_t* g, void* stream) {
     if (split == 0) {
         split = 1;
         if (g->accumulate && g->act == POLUS_ACT_NONE && g->C2 == nullptr) {
-            const long long tiles = mt * cdiv(g->N, 128) * nb;
-            if (tiles < sms) {
-                split = (int)((sms + tiles - 1) / tiles);
+            const long long ctas = mt * cdiv(g->N, 128) * nb * CG;
+            if (ctas < sms) {
+                split = (int)((sms + ctas - 1) / ctas);
                 const int max_split = kb_total / 4 > 1 ? kb_total / 4 : 1;  // >= 4 k-blocks per split
                 if (split > max_split) split = max_split;
             }
@@ -417,8 +467,8 @@ extern "C" int polus_gemm_tc(const polus_gemm_t* g, void* stream) {
     if (g->N <= 64) BN = 64;
     else if (g->N <= 128) BN = 128;
     else {
-        const long long tiles256 = mt * cdiv(g->N, 256) * nb * split;
-        BN = tiles256 >= sms ? 256 : 128;
+        const long long ctas256 = mt * cdiv(g->N, 256) * nb * split * CG;
+        BN = ctas256 >= sms ? 256 : 128;
     }
 
     TcParams p;
@@ -447,10 +497,14 @@ extern "C" int polus_gemm_tc(const polus_gemm_t* g, void* stream) {
     CUtensorMap ta, tb;
     int rc = make_map(&ta, g->A, g->M, g->K, batch0, batch1, BM);
     if (rc) return rc;
-    rc = make_map(&tb, g->B, g->N, g->K, batch0, batch1, BN);
+    rc = make_map(&tb, g->B, g->N, g->K, batch0, batch1, BN / CG);
     if (rc) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (BN == 64) return launch_major<64>(g->A.mn_major, g->B.mn_major, ta, tb, p, st);
-    if (BN == 128) return launch_major<128>(g->A.mn_major, g->B.mn_major, ta, tb, p, st);
-    return launch_major<256>(g->A.mn_major, g->B.mn_major, ta, tb, p, st);
+    if (CG == 2) {
+        if (BN == 128) return launch_major<128, 2>(g->A.mn_major, g->B.mn_major, ta, tb, p, st);
+        return launch_major<256, 2>(g->A.mn_major, g->B.mn_major, ta, tb, p, st);
+    }
+    if (BN == 64) return launch_major<64, 1>(g->A.mn_major, g->B.mn_major, ta, tb, p, st);
+    if (BN == 128) return launch_major<128, 1>(g->A.mn_major, g->B.mn_major, ta, tb, p, st);
+    return launch_major<256, 1>(g->A.mn_major, g->B.mn_major, ta, tb, p, st);
 }
