@@ -108,6 +108,15 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+_T0 = time.time()
+
+
+def dbg(msg):
+    if os.environ.get("BENCH_DEBUG"):
+        sys.stderr.write(f"[bench r{os.environ.get('RANK', '0')} +{time.time() - _T0:6.1f}s] {msg}\n")
+        sys.stderr.flush()
+
+
 def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -123,7 +132,9 @@ def run_ours(args):
     from polus_b200.utils import set_random_seed
 
     device.init(local_rank)
+    dbg("device ready")
     polus_b200.PolusContext()  # brings NCCL up when WORLD_SIZE > 1
+    dbg("context ready")
     set_random_seed(42)
     K = 4
     cfg = BertConfig()  # BERT-base: L12 H768 nh12 I3072 vocab 30522, dropout 0.1
@@ -137,9 +148,14 @@ def run_ours(args):
         if world > 1:
             comm.barrier()
 
+    dbg("model built")
     for i in range(max(args.warmup, 3)):
         loss = trainer.train_step(*batches[i % len(batches)])
+        if i < 3:
+            device.device_sync()
+            dbg(f"warmup step {i} done")
     float(loss)
+    dbg("warmup done")
     if trainer.use_horovod:
         trainer.broadcast_init_vars()
     dev_batches = []
@@ -168,7 +184,9 @@ def run_ours(args):
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ms_dev, launches, loss_dev = timed(dev_batches)
+    dbg("timed (resident) done")
     ms_e2e, _, loss_e2e = timed(batches)
+    dbg("timed (e2e) done")
     clocks = sampler.stop() if sampler else None
     if world > 1:
         all_ms = [json.loads(b.decode()) for b in comm._host_allgather(json.dumps([ms_dev, ms_e2e]).encode())]

@@ -6,19 +6,24 @@
 // tf.GradientTape derives from them (polus/training.py:185).
 //
 // Two variants of one kernel template:
-//   CG = 2 (default for M >= 256): a CTA PAIR (cluster 2x1x1, two SMs of one TPC) owns a 256 x BN tile and
+//   CG = 2 (default for M > 128): a CTA PAIR (cluster 2x1x1, two SMs of one TPC) owns a 256 x BN tile and
 //           issues tcgen05.mma.cta_group::2 (M = 256).  Each CTA stages its own 128 rows of A and HALF of the
-//           B tile; the tensor cores read both halves, so L2->SM traffic per FLOP drops by a third vs CG = 1
-//           (the 1-CTA kernel was L2-bandwidth bound: profiles/r01_gemm_probe_v1.log).
+//           B tile; the tensor cores read both halves.
 //   CG = 1: one CTA owns a 128 x BN tile (small M, odd shapes).
-// Kernel shape (persistent, warp-specialised, one CTA per SM):
-//   warp 0      TMA producer       global -> smem ring (kStages x {A 128x64, B BNx64} bf16)
+// Kernel shape (persistent, warp-specialised, one CTA per SM, 384 threads):
+//   warp 0      TMA producer       global -> smem ring (kStages x {A 128x64, B (BN/CG)x64} bf16)
 //   warp 1      MMA issuer         one thread issues 4 x tcgen05.mma (K=16) per stage
 //   warp 2      TMEM alloc/dealloc 2 x BN fp32 columns: accumulator double buffer
-//   warps 4-7   epilogue           tcgen05.ld -> alpha/bias/activation -> bf16|fp32 global stores
-// Three mbarrier pipelines: smem full/empty, TMEM full/empty; tiles = batch x M/128 x N/BN x split_k.
+//   warps 4-11  epilogue           warp e owns TMEM lanes 32*(e%4).. and column half e/4:
+//                                  tcgen05.ld -> alpha/bias/activation -> bf16 into a 128B-swizzled smem
+//                                  staging block -> TMA store (coalesced, OOB-clipped); fp32 outputs
+//                                  (split-K wgrad, atomics) are written straight from registers.
+// Three mbarrier pipelines: smem full/empty, TMEM full/empty; tiles = batch x M/(128*CG) x N/BN x split_k.
 // Either operand may be K-major (reduction dim contiguous) or MN-major (the other dim contiguous), so
 // forward (X.W), dgrad (dY.W^T) and wgrad (X^T.dY) all read row-major tensors with no transposes.
+//
+// Round-1 measurement that shaped the epilogue: with per-thread row stores (each lane writing 16 B into a
+// different row) a 128x256 tile took ~19 us to drain vs ~3 us of MMA for K=768 (profiles/r01_gemm_shapes_v2.log).
 #include "common.cuh"
 #include "ptx.cuh"
 #include <cuda.h>
@@ -31,8 +36,11 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;
+constexpr int kEpiWarps = 8;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
+constexpr int STG_BLOCK = 32 * 128;                       // one staging block: 32 rows x 64 bf16, swizzled
+constexpr int STG_BYTES = kEpiWarps * 2 /*bufs*/ * 2 /*C,C2*/ * STG_BLOCK;  // 64 KB
 
 struct TcParams {
     int M, N, K;
@@ -40,13 +48,13 @@ struct TcParams {
     int m_tiles, n_tiles, split_k, kb_total, kb_per_split;
     int num_tiles;
     void* C;
-    void* C2;
     long long ldc, cbs0, cbs1;
     const float* bias;
     float alpha;
     int act;
     int c_f32;
     int accumulate;
+    int has_c2;
 };
 
 template <int BN, int CG>
@@ -54,54 +62,61 @@ struct Cfg {
     static constexpr int BN_LOCAL = BN / CG;  // rows of the B tile this CTA stages
     static constexpr int B_STAGE_BYTES = BN_LOCAL * BK * 2;
     static constexpr int kStageBytes = A_STAGE_BYTES + B_STAGE_BYTES;
-    static constexpr int kStages = (192 * 1024) / kStageBytes > 10 ? 10 : (192 * 1024) / kStageBytes;
+    static constexpr int kBudget = 227 * 1024 - 1024 - STG_BYTES - 256;
+    static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
     static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
-    static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 256;
+    static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + STG_BYTES + 256;
+    static constexpr int kColBlocks = BN / 64;                       // 64-column blocks per tile
+    static constexpr int kEpiActive = kColBlocks >= 2 ? 8 : 4;        // epilogue warps that do work
+    static constexpr int kBlocksPerWarp = kColBlocks >= 2 ? kColBlocks / 2 : 1;
 };
 
-__device__ __forceinline__ void store_chunk(const TcParams& p, float* v, long long row_off, int col0,
-                                            int ncols_valid) {
-    // v[0..31]: alpha*acc (+bias) before activation for columns col0..col0+31 of one row
-    if (p.C2 != nullptr) {
-        bf16* z = reinterpret_cast<bf16*>(p.C2) + row_off + col0;
-        if (ncols_valid == 32) {
+template <int ACT>
+__device__ __forceinline__ void apply_act32(float* v) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) *reinterpret_cast<bf16x8*>(z + 8 * j) = pack8(v + 8 * j);
-        } else {
-            _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < ncols_valid) z[j] = __float2bfloat16(v[j]);
-        }
+    for (int j = 0; j < 32; ++j) v[j] = act_fwd(ACT, v[j]);
+}
+__device__ __forceinline__ void apply_act(int act, float* v) {
+    switch (act) {  // one warp-uniform branch per 32 values, bodies fully unrolled
+        case POLUS_ACT_GELU: apply_act32<POLUS_ACT_GELU>(v); break;
+        case POLUS_ACT_RELU: apply_act32<POLUS_ACT_RELU>(v); break;
+        case POLUS_ACT_SWISH: apply_act32<POLUS_ACT_SWISH>(v); break;
+        case POLUS_ACT_TANH: apply_act32<POLUS_ACT_TANH>(v); break;
+        case POLUS_ACT_MISH: apply_act32<POLUS_ACT_MISH>(v); break;
+        default: break;
     }
-    if (p.act != POLUS_ACT_NONE) {
+}
+
+// 32 fp32 -> 32 bf16 into row `lane` of a swizzled [32 rows][128 B] block; `half` selects the 64-byte half.
+__device__ __forceinline__ void stage_row(uint8_t* block, int lane, int half, const float* v) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = act_fwd(p.act, v[j]);
+    for (int j = 0; j < 4; ++j) {
+        const int chunk = (half * 4 + j) ^ (lane & 7);  // 128B swizzle: 16-byte chunk index XOR row%8
+        *reinterpret_cast<bf16x8*>(block + lane * 128 + chunk * 16) = pack8(v + 8 * j);
     }
-    if (p.c_f32) {
-        float* c = reinterpret_cast<float*>(p.C) + row_off + col0;
-        if (p.accumulate) {
-            _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < ncols_valid) atomicAdd(c + j, v[j]);
-        } else if (ncols_valid == 32) {
+}
+
+__device__ __forceinline__ void store_f32_chunk(const TcParams& p, const float* v, long long row_off, int col0, int nvalid) {
+    float* c = reinterpret_cast<float*>(p.C) + row_off + col0;
+    if (p.accumulate) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                *reinterpret_cast<float4*>(c + 4 * j) =
-                    make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        } else {
-            _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < ncols_valid) c[j] = v[j];
-        }
+        for (int j = 0; j < 32; ++j)
+            if (j < nvalid) atomicAdd(c + j, v[j]);
+    } else if (nvalid == 32) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(c + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     } else {
-        bf16* c = reinterpret_cast<bf16*>(p.C) + row_off + col0;
-        if (ncols_valid == 32) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) *reinterpret_cast<bf16x8*>(c + 8 * j) = pack8(v + 8 * j);
-        } else {
-            _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < ncols_valid) c[j] = __float2bfloat16(v[j]);
-        }
+        for (int j = 0; j < 32; ++j)
+            if (j < nvalid) c[j] = v[j];
     }
 }
 
 template <int BN, bool A_MN, bool B_MN, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const TcParams p) {
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, const TcParams p) {
     using C = Cfg<BN, CG>;
     constexpr int kStages = C::kStages;
     constexpr int BN_LOCAL = C::BN_LOCAL;
@@ -117,7 +132,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                                ~static_cast<uintptr_t>(1023));
     uint8_t* sA = smem;
     uint8_t* sB = smem + kStages * A_STAGE_BYTES;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * (A_STAGE_BYTES + B_STAGE_BYTES));
+    uint8_t* sStage = smem + kStages * (A_STAGE_BYTES + B_STAGE_BYTES);  // 1024-aligned (stage sizes are multiples of 4 KB)
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sStage + STG_BYTES);
     uint64_t* empty_bar = full_bar + kStages;
     uint64_t* tfull_bar = empty_bar + kStages;
     uint64_t* tempty_bar = tfull_bar + 2;
@@ -129,6 +145,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmA);
         ptx::prefetch_tensormap(&tmB);
+        if (!p.c_f32) ptx::prefetch_tensormap(&tmC);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -137,7 +154,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(&tfull_bar[s], 1);
-            ptx::mbar_init(&tempty_bar[s], 4 * CG);  // one arrive per epilogue warp of every CTA of the group
+            ptx::mbar_init(&tempty_bar[s], C::kEpiActive * CG);  // one arrive per working epilogue warp of the group
         }
         ptx::fence_barrier_init();
     }
@@ -176,8 +193,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 decode(t, mt, nt, sp, b0, b1);
                 const int kb0 = sp * p.kb_per_split;
                 const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-                const int m0 = (mt * CG + (int)cta_rank) * BM;          // this CTA's 128 rows of A / C
-                const int n0 = nt * BN + (int)cta_rank * BN_LOCAL;      // this CTA's share of the B tile
+                const int m0 = (mt * CG + (int)cta_rank) * BM;      // this CTA's 128 rows of A / C
+                const int n0 = nt * BN + (int)cta_rank * BN_LOCAL;  // this CTA's share of the B tile
                 for (int kb = kb0; kb < kb1; ++kb) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     if (is_leader) ptx::mbar_expect_tx(&full_bar[stage], kStageTx);
@@ -254,45 +271,86 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && (warp - 4) < C::kEpiActive) {
         // ------------------------------------------------------------ epilogue (TMEM lane = row)
-        const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32)
+        const int e = warp - 4;
+        const int quad = e & 3;   // TMEM lanes [32*quad, 32*quad+32)  (hardware: warp_id % 4)
+        const int half = e >> 2;  // which half of the tile's 64-column blocks
+        uint8_t* stg = sStage + e * (4 * STG_BLOCK);  // [buf][C | C2]
         int acc = 0;
         uint32_t acc_phase = 0;
+        int stores_in_flight = 0;
+        int nblk = 0;  // staged blocks so far: alternates the two staging buffers across tiles too
         for (int t = tile0; t < p.num_tiles; t += tile_step) {
             int mt, nt, sp, b0, b1;
             decode(t, mt, nt, sp, b0, b1);
             ptx::mbar_wait(&tfull_bar[acc], acc_phase);
             ptx::tc_fence_after();
-            const int row = (mt * CG + (int)cta_rank) * BM + quad * 32 + lane;
+            const int row0 = (mt * CG + (int)cta_rank) * BM + quad * 32;
+            const int row = row0 + lane;
             const long long row_off = (long long)b0 * p.cbs0 + (long long)b1 * p.cbs1 + (long long)row * p.ldc;
             const bool add_bias = (p.bias != nullptr) && (sp == 0);
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                const int col0 = nt * BN + c * 32;
-                if (col0 >= p.N) break;  // warp-uniform
-                float v[32];
-                ptx::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + c * 32, v);
-                ptx::tmem_ld_wait();
-                const int nvalid = min(32, p.N - col0);
-                if (row < p.M) {
+            for (int i = 0; i < C::kBlocksPerWarp; ++i) {
+                const int cb = half * C::kBlocksPerWarp + i;
+                const int colb = nt * BN + cb * 64;
+                if (colb >= p.N) break;  // warp-uniform
+                const int buf = nblk & 1;
+                uint8_t* blkC = stg + buf * (2 * STG_BLOCK);
+                uint8_t* blkC2 = blkC + STG_BLOCK;
+                if (!p.c_f32 && stores_in_flight >= 2) {
+                    // the TMA store that last read this staging buffer must be done reading it
+                    if (lane == 0) ptx::tma_store_wait_read<1>();
+                    __syncwarp();
+                    stores_in_flight = 1;
+                }
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
-                    if (add_bias) {
-                        if (nvalid == 32) {
+                for (int h = 0; h < 2; ++h) {
+                    const int col0 = colb + h * 32;
+                    if (col0 < p.N) {  // warp-uniform; columns >= N of a staged block are clipped by the TMA store
+                        float v[32];
+                        ptx::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + cb * 64 + h * 32, v);
+                        ptx::tmem_ld_wait();
+                        const int nvalid = min(32, p.N - col0);
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
-                                v[4 * j] += bv.x;
-                                v[4 * j + 1] += bv.y;
-                                v[4 * j + 2] += bv.z;
-                                v[4 * j + 3] += bv.w;
+                        for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+                        if (add_bias) {
+                            if (nvalid == 32) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
+                                    v[4 * j] += bv.x;
+                                    v[4 * j + 1] += bv.y;
+                                    v[4 * j + 2] += bv.z;
+                                    v[4 * j + 3] += bv.w;
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    if (j < nvalid) v[j] += __ldg(p.bias + col0 + j);
                             }
+                        }
+                        if (p.c_f32) {
+                            apply_act(p.act, v);
+                            if (row < p.M) store_f32_chunk(p, v, row_off, col0, nvalid);
                         } else {
-                            _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nvalid) v[j] += __ldg(p.bias + col0 + j);
+                            if (p.has_c2) stage_row(blkC2, lane, h, v);  // pre-activation copy (GELU backward)
+                            apply_act(p.act, v);
+                            stage_row(blkC, lane, h, v);
                         }
                     }
-                    store_chunk(p, v, row_off, col0, nvalid);
+                }
+                if (!p.c_f32) {
+                    ptx::fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA engine
+                    __syncwarp();
+                    if (lane == 0) {
+                        // rows >= M and columns >= N are clipped by the tensor map
+                        ptx::tma_store_4d(&tmC, blkC, colb, row0, b0, b1);
+                        if (p.has_c2) ptx::tma_store_4d(&tmC2, blkC2, colb, row0, b0, b1);
+                        ptx::tma_store_commit();
+                    }
+                    ++stores_in_flight;
+                    ++nblk;
                 }
             }
             ptx::tc_fence_before();
@@ -306,6 +364,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 acc_phase ^= 1;
             }
         }
+        if (!p.c_f32 && lane == 0) ptx::tma_store_wait_all();  // smem must outlive the bulk stores
     }
 
     ptx::tc_fence_before();
@@ -336,47 +395,45 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// 4-D view (dim0 contiguous, rows, batch0, batch1) of one operand; box = {64, box_rows, 1, 1}.
-int make_map(CUtensorMap* map, const polus_operand_t& op, long long mn_len, long long k_len, int batch0,
-             int batch1, int box_mn) {
+// 4-D bf16 view (dim0 contiguous, rows, batch0, batch1); box = {64, box_rows, 1, 1}, 128-byte swizzle.
+int encode_map(CUtensorMap* map, const void* ptr, long long inner, long long rows, long long ld, int batch0,
+               long long bs0, int batch1, long long bs1, int box_rows) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) {
         polus_set_error("cuTensorMapEncodeTiled entry point not found (driver too old?)");
         return POLUS_ERR_CUDA;
     }
-    cuuint64_t dims[4];
+    cuuint64_t dims[4] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)batch0, (cuuint64_t)batch1};
     cuuint64_t strides[3];
-    cuuint32_t box[4];
+    cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    const long long inner = op.mn_major ? mn_len : k_len;
-    const long long rows = op.mn_major ? k_len : mn_len;
-    dims[0] = (cuuint64_t)inner;
-    dims[1] = (cuuint64_t)rows;
-    dims[2] = (cuuint64_t)batch0;
-    dims[3] = (cuuint64_t)batch1;
-    strides[0] = (cuuint64_t)op.ld * 2;
-    strides[1] = (cuuint64_t)(batch0 > 1 ? op.bs0 * 2 : rows * op.ld * 2);
-    strides[2] = (cuuint64_t)(batch1 > 1 ? op.bs1 * 2 : strides[1] * (cuuint64_t)batch0);
-    box[0] = 64;
-    box[1] = op.mn_major ? BK : (cuuint32_t)box_mn;
-    box[2] = 1;
-    box[3] = 1;
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(op.ptr), dims, strides, box,
-                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    strides[0] = (cuuint64_t)ld * 2;
+    strides[1] = (cuuint64_t)(batch0 > 1 ? bs0 * 2 : rows * ld * 2);
+    strides[2] = (cuuint64_t)(batch1 > 1 ? bs1 * 2 : strides[1] * (cuuint64_t)batch0);
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         polus_set_error("cuTensorMapEncodeTiled failed (%d): ptr=%p inner=%lld rows=%lld ld=%lld b0=%d/%lld b1=%d/%lld",
-                        (int)r, op.ptr, inner, rows, (long long)op.ld, batch0, (long long)op.bs0, batch1,
-                        (long long)op.bs1);
+                        (int)r, ptr, inner, rows, ld, batch0, bs0, batch1, bs1);
         return POLUS_ERR_INVALID;
     }
     return 0;
 }
 
+int make_map(CUtensorMap* map, const polus_operand_t& op, long long mn_len, long long k_len, int batch0, int batch1,
+             int box_mn) {
+    const long long inner = op.mn_major ? mn_len : k_len;
+    const long long rows = op.mn_major ? k_len : mn_len;
+    return encode_map(map, op.ptr, inner, rows, op.ld, batch0, op.bs0, batch1, op.bs1, op.mn_major ? BK : box_mn);
+}
+
 template <int BN, bool A_MN, bool B_MN, int CG>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, cudaStream_t st) {
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tc2,
+           const TcParams& p, cudaStream_t st) {
     auto kern = gemm_tc_kernel<BN, A_MN, B_MN, CG>;
     using C = Cfg<BN, CG>;
+    static_assert(C::kStages >= 2, "pipeline needs at least two stages");
     static bool attr_set = false;
     if (!attr_set) {
         POLUS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
@@ -396,19 +453,19 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, cuda
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    POLUS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+    POLUS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tc2, p));
     g_launch_count++;
     POLUS_LAUNCH_CHECK();
     return 0;
 }
 
 template <int BN, int CG>
-int launch_major(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p,
-                 cudaStream_t st) {
-    if (!a_mn && !b_mn) return launch<BN, false, false, CG>(ta, tb, p, st);
-    if (!a_mn && b_mn) return launch<BN, false, true, CG>(ta, tb, p, st);
-    if (a_mn && !b_mn) return launch<BN, true, false, CG>(ta, tb, p, st);
-    return launch<BN, true, true, CG>(ta, tb, p, st);
+int launch_major(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                 const CUtensorMap& tc2, const TcParams& p, cudaStream_t st) {
+    if (!a_mn && !b_mn) return launch<BN, false, false, CG>(ta, tb, tc, tc2, p, st);
+    if (!a_mn && b_mn) return launch<BN, false, true, CG>(ta, tb, tc, tc2, p, st);
+    if (a_mn && !b_mn) return launch<BN, true, false, CG>(ta, tb, tc, tc2, p, st);
+    return launch<BN, true, true, CG>(ta, tb, tc, tc2, p, st);
 }
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -484,7 +541,6 @@ extern "C" int polus_gemm_tc(const polus_gemm_t* g, void* stream) {
     p.split_k = cdiv(p.kb_total, p.kb_per_split);
     p.num_tiles = (int)(mt * p.n_tiles * p.split_k * nb);
     p.C = g->C;
-    p.C2 = g->C2;
     p.ldc = g->ldc;
     p.cbs0 = g->cbs0;
     p.cbs1 = g->cbs1;
@@ -493,18 +549,32 @@ extern "C" int polus_gemm_tc(const polus_gemm_t* g, void* stream) {
     p.act = g->act;
     p.c_f32 = g->c_dtype == POLUS_F32;
     p.accumulate = g->accumulate;
+    p.has_c2 = g->C2 != nullptr;
 
-    CUtensorMap ta, tb;
+    CUtensorMap ta, tb, tc, tc2;
     int rc = make_map(&ta, g->A, g->M, g->K, batch0, batch1, BM);
     if (rc) return rc;
     rc = make_map(&tb, g->B, g->N, g->K, batch0, batch1, BN / CG);
     if (rc) return rc;
+    if (!p.c_f32) {  // bf16 outputs leave through TMA stores of 32-row x 64-column blocks
+        rc = encode_map(&tc, g->C, g->N, g->M, g->ldc, batch0, g->cbs0, batch1, g->cbs1, 32);
+        if (rc) return rc;
+        if (p.has_c2) {
+            rc = encode_map(&tc2, g->C2, g->N, g->M, g->ldc, batch0, g->cbs0, batch1, g->cbs1, 32);
+            if (rc) return rc;
+        } else {
+            tc2 = tc;
+        }
+    } else {
+        tc = ta;
+        tc2 = ta;
+    }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (CG == 2) {
-        if (BN == 128) return launch_major<128, 2>(g->A.mn_major, g->B.mn_major, ta, tb, p, st);
-        return launch_major<256, 2>(g->A.mn_major, g->B.mn_major, ta, tb, p, st);
+        if (BN == 128) return launch_major<128, 2>(g->A.mn_major, g->B.mn_major, ta, tb, tc, tc2, p, st);
+        return launch_major<256, 2>(g->A.mn_major, g->B.mn_major, ta, tb, tc, tc2, p, st);
     }
-    if (BN == 64) return launch_major<64, 1>(g->A.mn_major, g->B.mn_major, ta, tb, p, st);
-    if (BN == 128) return launch_major<128, 1>(g->A.mn_major, g->B.mn_major, ta, tb, p, st);
-    return launch_major<256, 1>(g->A.mn_major, g->B.mn_major, ta, tb, p, st);
+    if (BN == 64) return launch_major<64, 1>(g->A.mn_major, g->B.mn_major, ta, tb, tc, tc2, p, st);
+    if (BN == 128) return launch_major<128, 1>(g->A.mn_major, g->B.mn_major, ta, tb, tc, tc2, p, st);
+    return launch_major<256, 1>(g->A.mn_major, g->B.mn_major, ta, tb, tc, tc2, p, st);
 }
