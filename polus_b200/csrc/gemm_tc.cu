@@ -96,6 +96,15 @@ __device__ __forceinline__ void stage_row(uint8_t* block, int lane, int half, co
     }
 }
 
+// 32 fp32 (one 128-byte row) into row `lane` of a swizzled [32 rows][128 B] block
+__device__ __forceinline__ void stage_row_f32(uint8_t* block, int lane, const float* v) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int chunk = j ^ (lane & 7);
+        *reinterpret_cast<float4*>(block + lane * 128 + chunk * 16) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+}
+
 __device__ __forceinline__ void store_f32_chunk(const TcParams& p, const float* v, long long row_off, int col0, int nvalid) {
     float* c = reinterpret_cast<float*>(p.C) + row_off + col0;
     if (p.accumulate) {
@@ -145,7 +154,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmA);
         ptx::prefetch_tensormap(&tmB);
-        if (!p.c_f32) ptx::prefetch_tensormap(&tmC);
+        ptx::prefetch_tensormap(&tmC);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -298,7 +307,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int buf = nblk & 1;
                 uint8_t* blkC = stg + buf * (2 * STG_BLOCK);
                 uint8_t* blkC2 = blkC + STG_BLOCK;
-                if (!p.c_f32 && stores_in_flight >= 2) {
+                if (stores_in_flight >= 2) {
                     // the TMA store that last read this staging buffer must be done reading it
                     if (lane == 0) ptx::tma_store_wait_read<1>();
                     __syncwarp();
@@ -331,8 +340,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             }
                         }
                         if (p.c_f32) {
+                            // fp32 output: the two 32-column chunks of this block use the buffer's two 4 KB halves
                             apply_act(p.act, v);
-                            if (row < p.M) store_f32_chunk(p, v, row_off, col0, nvalid);
+                            stage_row_f32(h == 0 ? blkC : blkC2, lane, v);
                         } else {
                             if (p.has_c2) stage_row(blkC2, lane, h, v);  // pre-activation copy (GELU backward)
                             apply_act(p.act, v);
@@ -340,18 +350,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                 }
-                if (!p.c_f32) {
-                    ptx::fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA engine
-                    __syncwarp();
-                    if (lane == 0) {
-                        // rows >= M and columns >= N are clipped by the tensor map
+                ptx::fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA engine
+                __syncwarp();
+                if (lane == 0) {
+                    // rows >= M and columns >= N are clipped by the tensor map
+                    if (p.c_f32) {
+                        if (p.accumulate) {  // split-K / shared-variable gradients: fp32 add performed by the TMA unit at L2
+                            ptx::tma_reduce_add_4d(&tmC, blkC, colb, row0, b0, b1);
+                            if (colb + 32 < p.N) ptx::tma_reduce_add_4d(&tmC, blkC2, colb + 32, row0, b0, b1);
+                        } else {
+                            ptx::tma_store_4d(&tmC, blkC, colb, row0, b0, b1);
+                            if (colb + 32 < p.N) ptx::tma_store_4d(&tmC, blkC2, colb + 32, row0, b0, b1);
+                        }
+                    } else {
                         ptx::tma_store_4d(&tmC, blkC, colb, row0, b0, b1);
                         if (p.has_c2) ptx::tma_store_4d(&tmC2, blkC2, colb, row0, b0, b1);
-                        ptx::tma_store_commit();
                     }
-                    ++stores_in_flight;
-                    ++nblk;
+                    ptx::tma_store_commit();
                 }
+                ++stores_in_flight;
+                ++nblk;
             }
             ptx::tc_fence_before();
             __syncwarp();
@@ -364,7 +382,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 acc_phase ^= 1;
             }
         }
-        if (!p.c_f32 && lane == 0) ptx::tma_store_wait_all();  // smem must outlive the bulk stores
+        if (lane == 0) ptx::tma_store_wait_all();  // smem must outlive the bulk stores
     }
 
     ptx::tc_fence_before();
@@ -397,7 +415,7 @@ EncodeTiledFn get_encode_fn() {
 
 // 4-D bf16 view (dim0 contiguous, rows, batch0, batch1); box = {64, box_rows, 1, 1}, 128-byte swizzle.
 int encode_map(CUtensorMap* map, const void* ptr, long long inner, long long rows, long long ld, int batch0,
-               long long bs0, int batch1, long long bs1, int box_rows) {
+               long long bs0, int batch1, long long bs1, int box_rows, int esize = 2) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) {
         polus_set_error("cuTensorMapEncodeTiled entry point not found (driver too old?)");
@@ -405,12 +423,12 @@ int encode_map(CUtensorMap* map, const void* ptr, long long inner, long long row
     }
     cuuint64_t dims[4] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)batch0, (cuuint64_t)batch1};
     cuuint64_t strides[3];
-    cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, 1};
+    cuuint32_t box[4] = {(cuuint32_t)(128 / esize), (cuuint32_t)box_rows, 1, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    strides[0] = (cuuint64_t)ld * 2;
-    strides[1] = (cuuint64_t)(batch0 > 1 ? bs0 * 2 : rows * ld * 2);
-    strides[2] = (cuuint64_t)(batch1 > 1 ? bs1 * 2 : strides[1] * (cuuint64_t)batch0);
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+    strides[0] = (cuuint64_t)ld * esize;
+    strides[1] = (cuuint64_t)(batch0 > 1 ? bs0 * esize : rows * ld * esize);
+    strides[2] = (cuuint64_t)(batch1 > 1 ? bs1 * esize : strides[1] * (cuuint64_t)batch0);
+    CUresult r = enc(map, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -519,13 +537,15 @@ extern "C" int polus_gemm_tc(const polus_gemm_t* g, void* stream) {
         }
     }
     if (split < 1) split = 1;
-    // tile width: widest tile that still yields >= one wave of CTAs; narrow tiles for narrow N
+    // tile width: minimise (waves x tile width); ties and near-ties go to the wide tile (less L2 traffic per FLOP)
     int BN;
     if (g->N <= 64) BN = 64;
     else if (g->N <= 128) BN = 128;
     else {
-        const long long ctas256 = mt * cdiv(g->N, 256) * nb * split * CG;
-        BN = ctas256 >= sms ? 256 : 128;
+        const long long groups = sms / CG;
+        const long long t256 = mt * cdiv(g->N, 256) * nb * split, t128 = mt * cdiv(g->N, 128) * nb * split;
+        const long long cost256 = ((t256 + groups - 1) / groups) * 256, cost128 = ((t128 + groups - 1) / groups) * 128;
+        BN = (cost128 * 10 < cost256 * 9) ? 128 : 256;
     }
 
     TcParams p;
@@ -565,9 +585,10 @@ extern "C" int polus_gemm_tc(const polus_gemm_t* g, void* stream) {
         } else {
             tc2 = tc;
         }
-    } else {
-        tc = ta;
-        tc2 = ta;
+    } else {  // fp32 outputs: 32-row x 32-column blocks, stored or reduce-added by the TMA unit
+        rc = encode_map(&tc, g->C, g->N, g->M, g->ldc, batch0, g->cbs0, batch1, g->cbs1, 32, 4);
+        if (rc) return rc;
+        tc2 = tc;
     }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (CG == 2) {
