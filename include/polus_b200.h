@@ -115,6 +115,14 @@ int polus_gemm_tc(const polus_gemm_t* g, void* stream);
 /* CUDA-core GEMM for shapes a tcgen05 tile cannot take (N=4 tag projection, N=10 tutorial head)
  * and the on-device checker for polus_gemm_tc in tests.  Accepts F32 or BF16 operands. */
 int polus_gemm_small(const polus_gemm_t* g, void* stream);
+/* Narrow dense layer, N <= 32 (polus/ner/models.py:37 tag projection; tutorials/classifier_example.py:47):
+ * y = act(x.W + b) with W [K,N] fp32; x f32 or bf16; optional z = pre-activation.  One pass over x. */
+int polus_skinny_supported(int K, int N);
+int polus_skinny_fwd(const void* d_x, int x_dtype, const float* d_W, const float* d_b, int M, int K, int N,
+                     int act, float* d_y, float* d_z, void* stream);
+/* dx = dz.W^T (may be NULL), gW += x^T.dz, gb += colsum(dz) (may be NULL) */
+int polus_skinny_bwd(const void* d_x, int x_dtype, const float* d_W, const float* d_dz, int M, int K, int N,
+                     void* d_dx, int dx_dtype, float* d_gW, float* d_gb, void* stream);
 /* 1 if polus_gemm_tc accepts this problem (alignment / dtype rules), else 0 */
 int polus_gemm_tc_supported(const polus_gemm_t* g);
 

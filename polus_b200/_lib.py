@@ -81,6 +81,9 @@ _SIGS = {
     "polus_gemm_tc": [C.POINTER(Gemm), p],
     "polus_gemm_small": [C.POINTER(Gemm), p],
     "polus_gemm_tc_supported": [C.POINTER(Gemm)],
+    "polus_skinny_supported": [i32, i32],
+    "polus_skinny_fwd": [p, i32, p, p, i32, i32, i32, i32, p, p, p],
+    "polus_skinny_bwd": [p, i32, p, p, i32, i32, i32, p, i32, p, p, p],
     "polus_embed_ln_fwd": [p, p, p, p, p, p, p, i32, i32, i32, i32, i32, f32, f32, u64, u32, p, p, p, p, p, p],
     "polus_embed_ln_bwd": [p, p, p, p, p, p, p, i32, i32, i32, i32, i32, f32, u64, u32, p, p, p, p, p, p, p, p],
     "polus_embed_ws_floats": [i32, i32, i32],
@@ -123,7 +126,7 @@ _SIGS = {
 _RET = {"polus_launch_count": C.c_int64, "polus_ln_ws_floats": sz, "polus_colsum_ws_floats": sz,
         "polus_embed_ws_floats": sz}
 # functions whose int return is a value, not a status
-_VALUE_RET = {"polus_version", "polus_gemm_tc_supported", "polus_comm_size", "polus_comm_rank",
+_VALUE_RET = {"polus_version", "polus_gemm_tc_supported", "polus_skinny_supported", "polus_comm_size", "polus_comm_rank",
               "polus_launch_count", "polus_ln_ws_floats", "polus_colsum_ws_floats", "polus_embed_ws_floats"}
 
 EXPORTS = ["polus_last_error"] + list(_SIGS)

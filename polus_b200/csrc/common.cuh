@@ -125,10 +125,11 @@ __device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint32_t site, 
 }
 
 // erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, below fp32 resolution of the GELU output); ~12 instructions
-// instead of erff()'s ~40, which made the FFN-up GEMM epilogue ALU-bound.
+// and branch-free (erff() diverges per element), which matters in the FFN-up GEMM epilogue.
 __device__ __forceinline__ float fast_erf(float x) {
     const float u = fabsf(x);
-    const float t = __frcp_rn(fmaf(0.3275911f, u, 1.0f));
+    float t;  // MUFU.RCP (approximate, 1 ulp): the IEEE __frcp_rn is a multi-instruction subroutine
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, u, 1.0f)));
     float poly = fmaf(t, 1.061405429f, -1.453152027f);
     poly = fmaf(t, poly, 1.421413741f);
     poly = fmaf(t, poly, -0.284496736f);

@@ -17,110 +17,148 @@ extern std::atomic<long long> g_launch_count;
 
 namespace {
 
-__device__ __forceinline__ float lse2(float a, float b) {
-    const float m = fmaxf(a, b);
-    if (m == -INFINITY) return -INFINITY;
-    return m + logf(expf(a - m) + expf(b - m));
-}
-
-// gemis doubles as scratch for the alphas: forward pass writes alpha_t there, backward pass replaces
-// each entry by the gradient.
-__global__ void crf_nll_kernel(const float* __restrict__ emis, const int32_t* __restrict__ tags,
-                               const int32_t* __restrict__ lens, const float* __restrict__ trans,
-                               const float* __restrict__ weights, int B, int T, int K, float* __restrict__ nll_out,
-                               float* __restrict__ loss, float* __restrict__ gemis, float* __restrict__ gtrans) {
+// Scaled forward-backward (Rabiner scaling) instead of per-step log-sum-exp: the recurrences run in the linear
+// domain on E = exp(A - max A), each step renormalised, so a time step costs K FMAs + one exp + one reciprocal
+// per lane instead of 2K exp + K log.  Warp 0 runs the forward recursion (and the gold-path score), warp 1 the
+// backward recursion, concurrently; then all 64 threads turn alpha-hat/beta-hat into marginals = gradients.
+//   alpha-hat_t[j] = u_t[j] / c_t,  u_t[j] = (sum_i alpha-hat_{t-1}[i] E[i][j]) * exp(x_t[j] - m_t),  m_t = max_j x_t[j]
+//   logZ = sum_t (m_t + log c_t) + (len-1) * max A
+//   beta-tilde_t[i] = r_t[i] / d_t, r_t[i] = sum_j E[i][j] w_{t+1}[j],  w_t[j] = exp(x_t[j] - m_t) * beta-tilde_t[j]
+//   gamma_t[j]  = alpha-hat_t[j] beta-tilde_t[j] / g_t,                g_t = sum_j alpha-hat_t[j] beta-tilde_t[j]
+//   xi_t[i][j]  = alpha-hat_t[i] E[i][j] w_{t+1}[j] / (d_t g_t)        (pair marginal of t -> t+1)
+// Shared memory: E [K][K], A [K][K], G [K][K], ah [T][K], w [T][K], bt [T][K], d [T].
+__global__ void __launch_bounds__(64)
+crf_nll_kernel(const float* __restrict__ emis, const int32_t* __restrict__ tags, const int32_t* __restrict__ lens,
+               const float* __restrict__ trans, const float* __restrict__ weights, int B, int T, int K,
+               float* __restrict__ nll_out, float* __restrict__ loss, float* __restrict__ gemis,
+               float* __restrict__ gtrans) {
     extern __shared__ float sm[];
-    float* sA = sm;           // [K][K]
-    float* sG = sm + K * K;   // [K][K] gradient accumulator for this block's sequence
+    float* sE = sm;
+    float* sA = sE + K * K;
+    float* sG = sA + K * K;
+    float* sAh = sG + K * K;          // [T][K]
+    float* sW = sAh + (size_t)T * K;  // [T][K]
+    float* sBt = sW + (size_t)T * K;  // [T][K]
+    float* sD = sBt + (size_t)T * K;  // [T]
+    __shared__ float s_logZ, s_score;
     const int b = blockIdx.x;
-    const int lane = threadIdx.x;
-    for (int i = lane; i < K * K; i += 32) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float amax = -INFINITY;
+    for (int i = tid; i < K * K; i += 64) amax = fmaxf(amax, trans[i]);
+    amax = warp_max(amax);
+    __shared__ float s_amax[2];
+    if (lane == 0) s_amax[warp] = amax;
+    __syncthreads();
+    amax = fmaxf(s_amax[0], s_amax[1]);
+    for (int i = tid; i < K * K; i += 64) {
         sA[i] = trans[i];
+        sE[i] = expf(trans[i] - amax);
         sG[i] = 0.f;
     }
-    __syncwarp();
+    __syncthreads();
     int len = lens ? lens[b] : T;
     len = len < 0 ? 0 : (len > T ? T : len);
-    const float w = (weights ? weights[b] : 1.0f);
-    const float gscale = w / (float)B;
+    const float w_b = (weights ? weights[b] : 1.0f);
+    const float gscale = w_b / (float)B;
     const float* x = emis + (long long)b * T * K;
     const int32_t* y = tags + (long long)b * T;
     float* g = gemis + (long long)b * T * K;
     const bool act = lane < K;
 
     if (len == 0) {
-        for (int i = lane; i < T * K; i += 32) g[i] = 0.f;
-        if (lane == 0 && nll_out) nll_out[b] = 0.f;
+        for (int i = tid; i < T * K; i += 64) g[i] = 0.f;
+        if (tid == 0 && nll_out) nll_out[b] = 0.f;
         return;
     }
-    // ---- forward: alphas
-    float alpha = act ? x[lane] : -INFINITY;
-    if (act) g[lane] = alpha;
-    for (int t = 1; t < len; ++t) {
-        float m = -INFINITY;
-        for (int i = 0; i < K; ++i) {
-            const float ai = __shfl_sync(0xffffffffu, alpha, i);
-            if (act) m = fmaxf(m, ai + sA[i * K + lane]);
+    if (warp == 0) {
+        // ---------------- forward recursion + gold path score
+        float xv = act ? x[lane] : -INFINITY;
+        float m = warp_max(xv);
+        float u = act ? expf(xv - m) : 0.f;
+        float c = warp_sum(u);
+        float ah = u / c;
+        float logZ = m + logf(c);
+        if (act) sAh[lane] = ah;
+        for (int t = 1; t < len; ++t) {
+            xv = act ? x[t * K + lane] : -INFINITY;  // issued early: independent of the recurrence
+            float s = 0.f;
+            for (int i = 0; i < K; ++i) s = fmaf(__shfl_sync(0xffffffffu, ah, i), act ? sE[i * K + lane] : 0.f, s);
+            m = warp_max(xv);
+            u = act ? s * expf(xv - m) : 0.f;
+            c = warp_sum(u);
+            ah = u / c;
+            logZ += m + logf(c) + amax;
+            if (act) sAh[t * K + lane] = ah;
         }
-        float s = 0.f;
-        for (int i = 0; i < K; ++i) {
-            const float ai = __shfl_sync(0xffffffffu, alpha, i);
-            if (act) s += expf(ai + sA[i * K + lane] - m);
+        float sc = 0.f;
+        for (int t = lane; t < len; t += 32) {
+            const int yt = min(max(y[t], 0), K - 1);
+            sc += x[t * K + yt];
+            if (t + 1 < len) sc += sA[yt * K + min(max(y[t + 1], 0), K - 1)];
         }
-        alpha = act ? x[t * K + lane] + m + logf(s) : -INFINITY;
-        if (act) g[t * K + lane] = alpha;
+        sc = warp_sum(sc);
+        if (lane == 0) {
+            s_logZ = logZ;
+            s_score = sc;
+        }
+    } else {
+        // ---------------- backward recursion
+        float bt = act ? 1.0f : 0.f;  // beta-tilde_{len-1} (any positive constant: marginals renormalise)
+        for (int t = len - 1; t >= 0; --t) {
+            const float xv = act ? x[t * K + lane] : -INFINITY;
+            const float m = warp_max(xv);
+            const float wv = act ? expf(xv - m) * bt : 0.f;  // w_t[j]
+            if (act) {
+                sBt[t * K + lane] = bt;
+                sW[t * K + lane] = wv;
+            }
+            if (t > 0) {
+                float r = 0.f;  // r_{t-1}[i = lane]
+                for (int j = 0; j < K; ++j) r = fmaf(act ? sE[lane * K + j] : 0.f, __shfl_sync(0xffffffffu, wv, j), r);
+                const float d = warp_sum(r);
+                if (lane == 0) sD[t - 1] = d;
+                bt = r / d;
+            }
+        }
     }
-    float mz = warp_max(alpha);
-    float logZ = mz + logf(warp_sum(act ? expf(alpha - mz) : 0.f));
-    // ---- gold path score
-    float sc = 0.f;
-    for (int t = lane; t < len; t += 32) {
-        const int yt = min(max(y[t], 0), K - 1);
-        sc += x[t * K + yt];
-        if (t + 1 < len) sc += sA[yt * K + min(max(y[t + 1], 0), K - 1)];
-    }
-    sc = warp_sum(sc);
-    const float nll = logZ - sc;
-    if (lane == 0) {
+    __syncthreads();
+    const float nll = s_logZ - s_score;
+    if (tid == 0) {
         if (nll_out) nll_out[b] = nll;
         if (loss) atomicAdd(loss, nll * gscale);
     }
-    // ---- backward: betas, marginals, gradients
-    __syncwarp();
-    float beta = act ? 0.f : -INFINITY;  // beta_{len-1}
-    for (int t = len - 1; t >= 0; --t) {
-        const float a_t = act ? g[t * K + lane] : -INFINITY;
-        const int yt = min(max(y[t], 0), K - 1);
-        if (act) {
-            const float marg = expf(a_t + beta - logZ);
-            g[t * K + lane] = gscale * (marg - (lane == yt ? 1.0f : 0.f));
-        }
-        if (t > 0) {
-            // pairwise marginals for (t-1 -> t): exp(alpha_{t-1}[i] + A[i,j] + x_t[j] + beta_t[j] - logZ)
-            const float xb = act ? x[t * K + lane] + beta : -INFINITY;  // indexed by j = lane
-            float newbeta = -INFINITY;                                 // beta_{t-1}[i = lane]
-            for (int j = 0; j < K; ++j) {
-                const float xbj = __shfl_sync(0xffffffffu, xb, j);
-                if (act) newbeta = lse2(newbeta, sA[lane * K + j] + xbj);
-            }
-            const float a_prev = act ? g[(t - 1) * K + lane] : -INFINITY;  // alpha_{t-1}[i = lane]
-            for (int j = 0; j < K; ++j) {
-                const float xbj = __shfl_sync(0xffffffffu, xb, j);
-                if (act) sG[lane * K + j] += expf(a_prev + sA[lane * K + j] + xbj - logZ);
-            }
-            __syncwarp();
-            if (lane == 0) {
-                const int yp = min(max(y[t - 1], 0), K - 1);
-                sG[yp * K + yt] -= 1.0f;
-            }
-            __syncwarp();
-            beta = newbeta;
+    // ---------------- emission gradients: gscale * (gamma_t[j] - [y_t == j]); zero beyond len
+    for (int t = tid; t < T; t += 64) {
+        if (t < len) {
+            float gsum = 0.f;
+            for (int j = 0; j < K; ++j) gsum += sAh[t * K + j] * sBt[t * K + j];
+            const float inv = 1.0f / gsum;
+            const int yt = min(max(y[t], 0), K - 1);
+            for (int j = 0; j < K; ++j)
+                g[t * K + j] = gscale * (sAh[t * K + j] * sBt[t * K + j] * inv - (j == yt ? 1.0f : 0.f));
+            if (t + 1 < len) sD[t] = 1.0f / (sD[t] * gsum);  // -> 1 / (d_t g_t), the pair-marginal normaliser
+        } else {
+            for (int j = 0; j < K; ++j) g[t * K + j] = 0.f;
         }
     }
-    for (int i = len * K + lane; i < T * K; i += 32) g[i] = 0.f;
-    __syncwarp();
-    if (gtrans != nullptr)
-        for (int i = lane; i < K * K; i += 32) atomicAdd(gtrans + i, gscale * sG[i]);
+    __syncthreads();
+    // ---------------- transition gradients: sum_t xi_t[i][j] - counts of gold transitions
+    if (gtrans != nullptr) {
+        for (int pidx = tid; pidx < K * K; pidx += 64) {
+            const int i = pidx / K, j = pidx % K;
+            const float e = sE[pidx];
+            float acc = 0.f;
+            for (int t = 0; t + 1 < len; ++t) acc = fmaf(sAh[t * K + i] * sW[(t + 1) * K + j], sD[t], acc);
+            sG[pidx] = acc * e;
+        }
+        __syncthreads();
+        for (int t = tid; t + 1 < len; t += 64) {
+            const int yp = min(max(y[t], 0), K - 1), yn = min(max(y[t + 1], 0), K - 1);
+            atomicAdd(&sG[yp * K + yn], -1.0f);
+        }
+        __syncthreads();
+        for (int i = tid; i < K * K; i += 64) atomicAdd(gtrans + i, gscale * sG[i]);
+    }
 }
 
 __global__ void crf_decode_kernel(const float* __restrict__ emis, const int32_t* __restrict__ lens,
@@ -221,12 +259,15 @@ extern "C" int polus_crf_nll(const float* emis, const int32_t* tags, const int32
                              const float* weights, int B, int T, int K, float* nll, float* loss, float* gemis,
                              float* gtrans, void* stream) {
     POLUS_REQUIRE(K >= 1 && K <= 32, "polus_crf_nll: K must be in [1,32] (got %d)", K);
-    POLUS_REQUIRE(gemis != nullptr, "polus_crf_nll: gemis is required (it doubles as the alpha scratch)");
+    POLUS_REQUIRE(gemis != nullptr, "polus_crf_nll: gemis is required");
     POLUS_REQUIRE(T >= 1, "polus_crf_nll: T must be >= 1");
+    const size_t smem = ((size_t)3 * K * K + (size_t)3 * T * K + T) * sizeof(float);
+    POLUS_REQUIRE(smem <= 200 * 1024, "polus_crf_nll: T*K = %d too large for the shared-memory forward-backward tables", T * K);
     if (B == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (loss) POLUS_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
-    crf_nll_kernel<<<B, 32, 2 * K * K * sizeof(float), st>>>(emis, tags, lens, trans, weights, B, T, K, nll, loss, gemis, gtrans);
+    if (smem > 48 * 1024) POLUS_CHECK_CUDA(cudaFuncSetAttribute(crf_nll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    crf_nll_kernel<<<B, 64, smem, st>>>(emis, tags, lens, trans, weights, B, T, K, nll, loss, gemis, gtrans);
     g_launch_count++;
     POLUS_LAUNCH_CHECK();
     return 0;

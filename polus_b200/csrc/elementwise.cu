@@ -47,12 +47,29 @@ act_bwd_colsum_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, i
     }
 }
 
-__global__ void colsum_final_kernel(const float* __restrict__ partial, int slabs, int N, float* __restrict__ out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= N) return;
+// out[c] += sum_r partial[r][c]; columns < split go to out0, the rest to out1 (either may be NULL).
+// Block = 32 columns x 8 row groups: coalesced 128-byte row reads, shared-memory tree for the 8 groups.
+__global__ void __launch_bounds__(256)
+colsum_reduce_kernel(const float* __restrict__ partial, int rows, int cols, float* __restrict__ out0,
+                     float* __restrict__ out1, int split) {
+    __shared__ float red[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
     float s = 0.f;
-    for (int r = 0; r < slabs; ++r) s += partial[(long long)r * N + c];
-    out[c] += s;
+    if (c < cols)
+        for (int r = ty; r < rows; r += 8) s += partial[(long long)r * cols + c];
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && c < cols) {
+        float t = 0.f;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) t += red[g][tx];
+        if (c < split) {
+            if (out0) out0[c] += t;
+        } else if (out1) {
+            out1[c - split] += t;
+        }
+    }
 }
 
 __global__ void dropout_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long long n8,
@@ -241,6 +258,13 @@ inline int ew_grid(long long n, int threads = 256) {
 
 }  // namespace
 
+int polus_launch_colsum_reduce(const float* partial, int rows, int cols, float* out0, float* out1, int split, cudaStream_t st) {
+    colsum_reduce_kernel<<<cdiv(cols, 32), 256, 0, st>>>(partial, rows, cols, out0, out1, split);
+    g_launch_count++;
+    POLUS_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" size_t polus_colsum_ws_floats(int N) { return (size_t)kColsumSlabs * (size_t)N; }
 
 extern "C" int polus_act_bwd_colsum(const polus_bf16_t* dy, const polus_bf16_t* z, int M, int N, int act,
@@ -260,7 +284,7 @@ extern "C" int polus_act_bwd_colsum(const polus_bf16_t* dy, const polus_bf16_t* 
     g_launch_count++;
     POLUS_LAUNCH_CHECK();
     if (gbias != nullptr) {
-        colsum_final_kernel<<<cdiv(N, 256), 256, 0, st>>>(ws, slabs, N, gbias);
+        colsum_reduce_kernel<<<cdiv(N, 32), 256, 0, st>>>(ws, slabs, N, gbias, nullptr, N);
         g_launch_count++;
         POLUS_LAUNCH_CHECK();
     }

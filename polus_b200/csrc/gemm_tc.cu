@@ -537,15 +537,14 @@ extern "C" int polus_gemm_tc(const polus_gemm_t* g, void* stream) {
         }
     }
     if (split < 1) split = 1;
-    // tile width: minimise (waves x tile width); ties and near-ties go to the wide tile (less L2 traffic per FLOP)
+    // tile width: the widest tile that still yields at least one full wave of CTAs.  (A wave-quantisation
+    // heuristic that preferred 128-wide tiles for N = 768 measured slower: profiles/r01_gemm_shapes_v4.log.)
     int BN;
     if (g->N <= 64) BN = 64;
     else if (g->N <= 128) BN = 128;
     else {
-        const long long groups = sms / CG;
-        const long long t256 = mt * cdiv(g->N, 256) * nb * split, t128 = mt * cdiv(g->N, 128) * nb * split;
-        const long long cost256 = ((t256 + groups - 1) / groups) * 256, cost128 = ((t128 + groups - 1) / groups) * 128;
-        BN = (cost128 * 10 < cost256 * 9) ? 128 : 256;
+        const long long ctas256 = mt * cdiv(g->N, 256) * nb * split * CG;
+        BN = ctas256 >= sms ? 256 : 128;
     }
 
     TcParams p;

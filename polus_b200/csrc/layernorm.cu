@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include <atomic>
 extern std::atomic<long long> g_launch_count;
+int polus_launch_colsum_reduce(const float* partial, int rows, int cols, float* out0, float* out1, int split, cudaStream_t st);
 
 namespace {
 
@@ -195,20 +196,6 @@ ln_res_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, const
             ws[(long long)blockIdx.x * 2 * H + which * H + idx] = s;
         }
         __syncthreads();
-    }
-}
-
-// out[c] += sum_r partial[r][c]
-__global__ void colsum_partials_kernel(const float* __restrict__ partial, int rows, int cols,
-                                       float* __restrict__ out0, float* __restrict__ out1, int split) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= cols) return;
-    float s = 0.f;
-    for (int r = 0; r < rows; ++r) s += partial[(long long)r * cols + c];
-    if (c < split) {
-        if (out0) out0[c] += s;
-    } else {
-        if (out1) out1[c - split] += s;
     }
 }
 
@@ -468,9 +455,7 @@ extern "C" int polus_ln_res_bwd(const polus_bf16_t* dy, const polus_bf16_t* z, c
     }
     g_launch_count++;
     POLUS_LAUNCH_CHECK();
-    colsum_partials_kernel<<<cdiv(2 * H, 256), 256, 0, st>>>(ws, grid, 2 * H, ggamma, gbeta, H);
-    g_launch_count++;
-    POLUS_LAUNCH_CHECK();
+    { int rc_ = polus_launch_colsum_reduce(ws, grid, 2 * H, ggamma, gbeta, H, st); if (rc_) return rc_; }
     return 0;
 }
 
@@ -524,9 +509,7 @@ extern "C" int polus_embed_ln_bwd(const polus_bf16_t* dy, const float* z, const 
     }
     g_launch_count++;
     POLUS_LAUNCH_CHECK();
-    colsum_partials_kernel<<<cdiv(2 * H, 256), 256, 0, st>>>(partial, grid, 2 * H, ggamma, gbeta, H);
-    g_launch_count++;
-    POLUS_LAUNCH_CHECK();
+    { int rc_ = polus_launch_colsum_reduce(partial, grid, 2 * H, ggamma, gbeta, H, st); if (rc_) return rc_; }
     embed_scatter_kernel<<<S, 192, 0, st>>>(dz, ids, tt, B, S, H, vocab, n_types, gword, gpos, gtype);
     g_launch_count++;
     POLUS_LAUNCH_CHECK();

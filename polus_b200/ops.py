@@ -279,8 +279,13 @@ def linear(x, W, b=None, activation=None, out_dtype=None):
     y = Tensor(lead + (N,), out_dtype if out_dtype is not None else F32)
     assert y.dtype == F32
     z = Tensor(lead + (N,), F32) if (act != 0 and tape is not None) else None
-    _gemm(M, N, K, _operand(x.ptr, K, False, x.dtype), _operand(W.ptr, N, True, F32), y.ptr, N, F32,
-          bias=b.ptr if b is not None else None, act=act, c2=z.ptr if z is not None else None, force_small=True)
+    skinny = x.dtype in (F32, BF16) and _lib.call("polus_skinny_supported", K, N) == 1
+    if skinny:  # narrow outputs (K-tag projection, 10-way head): one pass over x
+        _lib.call("polus_skinny_fwd", x.ptr, x.dtype, W.ptr, b.ptr if b is not None else None, M, K, N, act, y.ptr,
+                  z.ptr if z is not None else None, device.stream())
+    else:
+        _gemm(M, N, K, _operand(x.ptr, K, False, x.dtype), _operand(W.ptr, N, True, F32), y.ptr, N, F32,
+              bias=b.ptr if b is not None else None, act=act, c2=z.ptr if z is not None else None, force_small=True)
     if tape is not None:
         def backward(g, z=z):
             g = cast(g, F32)
@@ -289,13 +294,19 @@ def linear(x, W, b=None, activation=None, out_dtype=None):
                 _lib.call("polus_unary_f32", act, z.ptr, g.ptr, 1, g.size, dz.ptr, 1.0, device.stream())
             else:
                 dz = g
+            dx = None
+            if x.requires_grad:
+                dx = Tensor(lead + (K,), x.dtype if x.dtype in (F32, BF16) else F32)
+            if skinny:
+                _lib.call("polus_skinny_bwd", x.ptr, x.dtype, W.ptr, dz.ptr, M, K, N, dx.ptr if dx is not None else None,
+                          dx.dtype if dx is not None else F32, W.grad.ptr, b.grad.ptr if b is not None else None,
+                          device.stream())
+                return [dx, None, None]
             if b is not None:
                 _lib.call("polus_reduce_sum_f32", dz.ptr, M, N, 0, 1.0, b.grad.ptr, 1, device.stream())
             _gemm(K, N, M, _operand(x.ptr, K, True, x.dtype), _operand(dz.ptr, N, True, F32), W.grad.ptr, N, F32,
                   accumulate=1, force_small=True)
-            dx = None
-            if x.requires_grad:
-                dx = Tensor(lead + (K,), x.dtype if x.dtype in (F32, BF16) else F32)
+            if dx is not None:
                 _gemm(M, K, N, _operand(dz.ptr, N, False, F32), _operand(W.ptr, N, False, F32), dx.ptr, K, dx.dtype,
                       force_small=True)
             return [dx, None, None]
