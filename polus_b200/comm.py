@@ -222,21 +222,11 @@ class _DistributedTape:
             events.append(ev)
 
         from . import ops
-        grads = {id(loss): ops.ones_like(loss)}
-        nodes = tape.nodes
-        for idx in range(len(nodes) - 1, -1, -1):
+
+        def before_node(idx):
             while pending and ready_at[pending[0]] > idx:
                 launch(pending.pop(0))
-            node = nodes[idx]
-            g = grads.pop(id(node.output), None)
-            if g is None:
-                continue
-            in_grads = node.backward(g)
-            for t, gi in zip(node.inputs, in_grads):
-                if gi is None or t is None or isinstance(t, Param) or not t.requires_grad:
-                    continue
-                prev = grads.get(id(t))
-                grads[id(t)] = gi if prev is None else ops._accumulate(prev, gi)
+        grads = ops.run_backward(tape.nodes, loss, before_node)
         while pending:
             launch(pending.pop(0))
         tape.nodes = []
@@ -246,7 +236,7 @@ class _DistributedTape:
         _lib.call("polus_event_record", done, comm_stream)
         _lib.call("polus_stream_wait_event", main, done)
         self.events = events + [done]
-        return [w.grad if isinstance(w, Param) else grads.get(id(w)) for w in weights]
+        return [w.grad if isinstance(w, Param) else ops._materialise(grads.get(id(w))) for w in weights]
 
 
 def DistributedGradientTape(tape, **kwargs):

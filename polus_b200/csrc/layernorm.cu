@@ -115,7 +115,7 @@ ln_res_fwd_kernel(bf16* __restrict__ x, const bf16* __restrict__ res, const floa
 // per-CTA partial sums of dgamma = dy*xhat and dbeta = dy into ws[blockIdx.x][2][H].
 template <int MAXC>
 __global__ void __launch_bounds__(kWarps * 32)
-ln_res_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, const float* __restrict__ mean_in,
+ln_res_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, const bf16* __restrict__ z, const float* __restrict__ mean_in,
                   const float* __restrict__ rstd_in, const float* __restrict__ gamma, int M, int H, DropCfg dc,
                   const uint32_t* __restrict__ d_step, bf16* __restrict__ dx, bf16* __restrict__ dres,
                   float* __restrict__ ws) {
@@ -146,6 +146,12 @@ ln_res_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, const
             if (c < chunks) {
                 float dyv[8], zv[8];
                 unpack8(ld_stream8(dy + base + c * 8), dyv);
+                if (dy2 != nullptr) {  // second contribution to d(y) (residual stream): summed here, no add kernel
+                    float d2[8];
+                    unpack8(ld_stream8(dy2 + base + c * 8), d2);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dyv[j] += d2[j];
+                }
                 unpack8(ld_stream8(z + base + c * 8), zv);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -430,12 +436,11 @@ extern "C" int polus_ln_res_fwd(polus_bf16_t* x, const polus_bf16_t* res, const 
     return 0;
 }
 
-extern "C" int polus_ln_res_bwd(const polus_bf16_t* dy, const polus_bf16_t* z, const float* mean, const float* rstd,
-                                const float* gamma, int M, int H, float p_drop, uint64_t seed, uint32_t site,
-                                const uint32_t* d_step, polus_bf16_t* dx, polus_bf16_t* dres, int accumulate_res,
+extern "C" int polus_ln_res_bwd(const polus_bf16_t* dy, const polus_bf16_t* dy2, const polus_bf16_t* z, const float* mean,
+                                const float* rstd, const float* gamma, int M, int H, float p_drop, uint64_t seed,
+                                uint32_t site, const uint32_t* d_step, polus_bf16_t* dx, polus_bf16_t* dres,
                                 float* ggamma, float* gbeta, float* ws, void* stream) {
     POLUS_REQUIRE(M >= 0 && H > 0 && H % 8 == 0 && H <= 4096, "polus_ln_res_bwd: H must be a multiple of 8 and <= 4096 (got %d)", H);
-    POLUS_REQUIRE(accumulate_res == 0, "polus_ln_res_bwd: accumulate_res is reserved (must be 0)");
     POLUS_REQUIRE(ws != nullptr && dx != nullptr, "polus_ln_res_bwd: workspace and dx required");
     POLUS_REQUIRE(!(p_drop > 0.f && dres == dx), "polus_ln_res_bwd: dres may alias dx only without dropout");
     if (M == 0) return 0;
@@ -447,11 +452,11 @@ extern "C" int polus_ln_res_bwd(const polus_bf16_t* dy, const polus_bf16_t* z, c
     if (H <= 1024) {
         static bool set4 = false;
         if (!set4) { POLUS_CHECK_CUDA(cudaFuncSetAttribute(ln_res_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 1024 * 4)); set4 = true; }
-        ln_res_bwd_kernel<4><<<grid, kWarps * 32, smem, st>>>((const bf16*)dy, (const bf16*)z, mean, rstd, gamma, M, H, dc, d_step, (bf16*)dx, (bf16*)dres, ws);
+        ln_res_bwd_kernel<4><<<grid, kWarps * 32, smem, st>>>((const bf16*)dy, (const bf16*)dy2, (const bf16*)z, mean, rstd, gamma, M, H, dc, d_step, (bf16*)dx, (bf16*)dres, ws);
     } else {
         static bool set16 = false;
         if (!set16) { POLUS_CHECK_CUDA(cudaFuncSetAttribute(ln_res_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4096 * 4)); set16 = true; }
-        ln_res_bwd_kernel<16><<<grid, kWarps * 32, smem, st>>>((const bf16*)dy, (const bf16*)z, mean, rstd, gamma, M, H, dc, d_step, (bf16*)dx, (bf16*)dres, ws);
+        ln_res_bwd_kernel<16><<<grid, kWarps * 32, smem, st>>>((const bf16*)dy, (const bf16*)dy2, (const bf16*)z, mean, rstd, gamma, M, H, dc, d_step, (bf16*)dx, (bf16*)dres, ws);
     }
     g_launch_count++;
     POLUS_LAUNCH_CHECK();

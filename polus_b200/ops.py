@@ -91,22 +91,48 @@ class GradientTape:
     def gradient(self, loss, weights):
         """Back-propagate from a scalar loss.  Returns the gradient tensors of `weights` (views of the
         gradient arena for Params)."""
-        grads = {id(loss): ones_like(loss)}
-        for node in reversed(self.nodes):
-            g = grads.pop(id(node.output), None)
-            if g is None:
-                continue
-            in_grads = node.backward(g)
-            for t, gi in zip(node.inputs, in_grads):
-                if gi is None or t is None or isinstance(t, Param) or not t.requires_grad:
-                    continue
-                prev = grads.get(id(t))
-                grads[id(t)] = gi if prev is None else _accumulate(prev, gi)
+        grads = run_backward(self.nodes, loss)
         self.nodes = []
-        out = []
-        for w in weights:
-            out.append(w.grad if isinstance(w, Param) else grads.get(id(w)))
-        return out
+        return [w.grad if isinstance(w, Param) else _materialise(grads.get(id(w))) for w in weights]
+
+
+def _materialise(g):
+    """A gradient slot holds one tensor or a list of not-yet-summed contributions."""
+    if isinstance(g, list):
+        acc = g[0]
+        for t in g[1:]:
+            acc = _accumulate(acc, t)
+        return acc
+    return g
+
+
+def run_backward(nodes, loss, before_node=None):
+    """Reverse sweep over the recorded nodes.  `before_node(idx)` lets the data-parallel tape launch bucket
+    allreduces as soon as backward has passed the variables of a bucket.  Contributions to the same tensor
+    are kept as a list and summed lazily: a node whose backward carries `pair_ok` (LayerNorm backward)
+    consumes two contributions directly, fusing the residual-stream addition into its own pass."""
+    grads = {id(loss): ones_like(loss)}
+    for idx in range(len(nodes) - 1, -1, -1):
+        if before_node is not None:
+            before_node(idx)
+        node = nodes[idx]
+        g = grads.pop(id(node.output), None)
+        if g is None:
+            continue
+        if isinstance(g, list) and not (len(g) == 2 and getattr(node.backward, "pair_ok", False)):
+            g = _materialise(g)
+        in_grads = node.backward(g)
+        for t, gi in zip(node.inputs, in_grads):
+            if gi is None or t is None or isinstance(t, Param) or not t.requires_grad:
+                continue
+            prev = grads.get(id(t))
+            if prev is None:
+                grads[id(t)] = gi
+            elif isinstance(prev, list):
+                prev.append(gi)
+            else:
+                grads[id(t)] = [prev, gi]
+    return grads
 
 
 def _recording(*inputs):
@@ -393,7 +419,11 @@ def layernorm_residual(x, res, gamma, beta, eps=1e-12, p_drop=0.0):
         z = x  # now holds dropout(x) + res
 
         def backward(g):
-            g = cast(g, BF16)
+            g2 = None
+            if isinstance(g, list):  # two contributions to d(y): summed inside the kernel
+                g, g2 = cast(g[0], BF16), cast(g[1], BF16)
+            else:
+                g = cast(g, BF16)
             dx = Tensor(x.shape, BF16)
             if res is None:
                 dres = None
@@ -402,10 +432,11 @@ def layernorm_residual(x, res, gamma, beta, eps=1e-12, p_drop=0.0):
             else:
                 dres = dx  # identical values: write once
             ws = Tensor((int(_lib.call("polus_ln_ws_floats", H)),), F32)
-            _lib.call("polus_ln_res_bwd", g.ptr, z.ptr, mean.ptr, rstd.ptr, gamma.ptr, M, H, p_drop, seed, site,
-                      step_counter(), dx.ptr, dres.ptr if dres is not None else None, 0, gamma.grad.ptr, beta.grad.ptr,
-                      ws.ptr, device.stream())
+            _lib.call("polus_ln_res_bwd", g.ptr, g2.ptr if g2 is not None else None, z.ptr, mean.ptr, rstd.ptr, gamma.ptr,
+                      M, H, p_drop, seed, site, step_counter(), dx.ptr, dres.ptr if dres is not None else None,
+                      gamma.grad.ptr, beta.grad.ptr, ws.ptr, device.stream())
             return [dx, dres, None, None]
+        backward.pair_ok = True
         _record(tape, [x, res, gamma, beta], y, backward)
     return y
 

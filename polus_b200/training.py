@@ -183,6 +183,7 @@ class BaseTrainer:
             logger.warning(f"Since no specific trainable_weights were defined during the {self.__class__.__name__} "
                            f"instantiation, the trainer will optimizer all the variables found on the model instance")
             self.trainable_weights = model.trainable_weights
+            self._auto_weights = True  # Keras models may create variables lazily: re-read after the first forward
         self.use_horovod = PolusContext().is_horovod_enabled()
         self.hvd = _hvd()
         if self.use_horovod:
@@ -221,8 +222,11 @@ class BaseTrainer:
                 inputs = self.forward_without_grads(*inputs)
             inputs = self.forward_with_grads(*inputs)
             loss_value = self.loss(*inputs)
-        if not self.trainable_weights:  # Keras-style lazy build: variables exist only after the first call
-            self.trainable_weights = self.model.trainable_weights
+        if getattr(self, "_auto_weights", False) and hasattr(self.model, "trainable_weights"):
+            # Keras-style lazy build: some variables exist only after the first call
+            current = self.model.trainable_weights
+            if len(current) != len(self.trainable_weights):
+                self.trainable_weights = current
         tape = self.hvd.DistributedGradientTape(tape)
         grads = tape.gradient(loss_value, self.trainable_weights)
         if self.post_process_grads is not None:
