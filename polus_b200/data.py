@@ -166,3 +166,56 @@ class DataLoader:
             logger.info("this dataset does not have the number of samples in cache so it will take some time to counting")
             self.n_samples = sum(1 for _ in self)
         return self.n_samples
+
+
+class IAccelerated_Map:
+    def __init__(self):
+        super().__init__()
+        self.__name__ = self.__class__.__name__
+        if self.__class__.__name__ == "IAccelerated_Map":
+            raise Exception("This is an interface that cannot be instantiated")
+
+    def build(self):
+        raise NotImplementedError("build method was not implemented")
+
+
+def access_embeddings(func):
+    """Call `func(**kwargs["embeddings"])` when the config nests the arguments under "embeddings" (data.py:510-521)."""
+    def function_wrapper(*args, **kwargs):
+        if isinstance(kwargs, dict) and "embeddings" in kwargs:
+            return func(**kwargs["embeddings"])
+        return func(*args, **kwargs)
+    return function_wrapper
+
+
+@access_embeddings
+def build_bert_embeddings(checkpoint, bert_layer_index=None, **kwargs):
+    """Frozen encoder used as `train_map_f` "GPU preprocessing" (reference data.py:523-545): returns
+    `embeddings(input_ids=..., attention_mask=..., token_type_ids=...)` -> {last_hidden_state, pooler_output},
+    computed without recording gradients.  With `bert_layer_index` the model is cut there first (split_bert_model)
+    and only the lower layers run.  `checkpoint` is resolved offline (BertConfig / dict / directory / BertModel)."""
+    from . import ops
+    from .models import BertModel, split_bert_model, split_bert_model_from_checkpoint
+    if isinstance(checkpoint, BertModel):
+        bert_model = checkpoint
+        if bert_layer_index is not None:
+            bert_model = split_bert_model(bert_model, bert_layer_index, return_post_bert_model=False)
+    elif bert_layer_index is not None:
+        bert_model = split_bert_model_from_checkpoint(checkpoint, bert_layer_index, return_post_bert_model=False)
+    else:
+        from .models import BertConfig
+        import json
+        import os
+        if isinstance(checkpoint, BertConfig):
+            bert_model = BertModel(checkpoint)
+        elif isinstance(checkpoint, dict):
+            bert_model = BertModel(BertConfig(**checkpoint))
+        else:
+            with open(os.path.join(checkpoint, "config.json")) as f:
+                bert_model = BertModel(BertConfig(**json.load(f)))
+
+    def embeddings(**kw):
+        with ops.no_grad():
+            return bert_model(**kw, training=False)
+    embeddings.model = bert_model
+    return embeddings

@@ -135,8 +135,23 @@ def run_backward(nodes, loss, before_node=None):
     return grads
 
 
+_no_grad_depth = [0]
+
+
+class no_grad:
+    """Forward computations whose intermediates must not be kept (frozen encoders: polus/data.py:523-545,
+    polus/ir/training.py:47-67 under tape.stop_recording)."""
+
+    def __enter__(self):
+        _no_grad_depth[0] += 1
+
+    def __exit__(self, *exc):
+        _no_grad_depth[0] -= 1
+        return False
+
+
 def _recording(*inputs):
-    if not _tape_stack:
+    if not _tape_stack or _no_grad_depth[0]:
         return None
     tape = _tape_stack[-1]
     if tape.paused:
@@ -694,3 +709,29 @@ def _broadcast_rows_mul(mat, vec, rows, cols, out):
 
 def reduce_mean(x, axis=None):
     return reduce_sum(x, axis=axis, mean=True)
+
+
+def slice_rows(x, first, n):
+    """Contiguous row slice x[first:first+n] of a 1-D / 2-D fp32 tensor (view; gradient scattered back)."""
+    x = cast(x, F32)
+    cols = 1 if x.ndim == 1 else x.shape[-1]
+    shape = (n,) if x.ndim == 1 else (n, cols)
+    out = Tensor(shape, F32, ptr=x.ptr + first * cols * 4, block=x.block)
+    tape = _recording(x)
+    if tape is not None:
+        def backward(g):
+            dx = Tensor(x.shape, F32, zero=True)
+            _lib.call("polus_memcpy_d2d", dx.ptr + first * cols * 4, cast(g, F32).ptr, n * cols * 4, device.stream())
+            return [dx]
+        _record(tape, [x], out, backward)
+    return out
+
+
+def gather_cols0(x):
+    """Column 0 of a 2-D fp32 tensor as a vector (score heads padded to 8 outputs)."""
+    x = cast(x, F32)
+    rows, cols = x.shape
+    sel = Tensor((cols, 1), F32, zero=True)
+    _lib.call("polus_fill_f32", sel.ptr, 1.0, 1, device.stream())
+    out = matmul(x, sel)
+    return reshape(out, (rows,))
