@@ -1,0 +1,569 @@
+// Fused multi-head self-attention for S <= 256, head_dim = 64 (BERT-base/large heads), forward and backward.
+// The S x S score / probability tensors never leave the SM: scores live in TMEM, probabilities go through shared
+// memory straight into the second tcgen05.mma.  Replaces, per layer, three batched GEMM launches + the softmax
+// kernel in forward and five launches in backward (the unfused path of ops.attention, kept for longer sequences),
+// i.e. the TF ops behind HF TFBertSelfAttention: matmul(q,k^T)/sqrt(dh) + (1-mask)*-10000 (polus/models.py:175-195)
+// -> softmax -> dropout -> matmul(p, v), and their gradients.
+//
+// Forward, one CTA per (batch, head, 128-query tile), 160 threads:
+//   warp 0 / lane 0 : TMA loads of Q [128x64], K [256x64], V [256x64] from the packed [B,S,3H] projection (4-D
+//                     tensor map (dh, s, slot, b), slot = {q,k,v} x head); tcgen05.mma  S = Q K^T (M128 N256 K64) into
+//                     TMEM cols 0..255; later O = P V (M128 N64 K256) into cols 256..319.
+//   warps 1-4       : thread = query row.  Two passes over the TMEM row: max, then e = exp(x - max) (sum kept in fp32),
+//                     dropout with the same Philox counters as the unfused softmax kernel, bf16 e -> 128B-swizzled smem
+//                     (K-major A operand).  After the second MMA: O * (1/sum) -> bf16 -> smem -> TMA store into
+//                     ctx [B,S,H].  Saves L = max + log(sum) per row for backward.
+//
+// Backward, one CTA per (batch, head): blocks (query tile i, key half j) of 128x128.
+//   TMEM: S_ij 0..127 | dP_ij 128..255 | dQ_0 256..319 | dK_j 320..383 | dV_j 384..447 | dQ_1 448..511.
+//   smem: Q, K, V, dO (32 KB each), Pd_ij and dS_ij (32 KB each; ONE copy of dS serves both dQ += dS K (K-major A)
+//   and dK += dS^T Q (MN-major A): the two canonical layouts coincide byte for byte).
+//   P is recomputed from the saved L; delta_row = sum_d dO*O.
+#include "common.cuh"
+#include "ptx.cuh"
+#include <cuda.h>
+#include <atomic>
+
+extern std::atomic<long long> g_launch_count;
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+namespace {
+
+constexpr int DH = 64;
+constexpr float kLog2e = 1.4426950408889634f;
+
+struct AttnParams {
+    int B, S, nh;
+    float scale;           // 1/sqrt(dh)
+    uint32_t thresh16;     // dropout threshold (0 = off)
+    float inv_keep;
+    unsigned long long seed;
+    uint32_t site;
+    const uint32_t* d_step;
+    const int32_t* mask;   // [B,S] or null
+    float* lse;            // [B,nh,S]
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// ================================================================================================ forward
+constexpr int FWD_THREADS = 160;
+constexpr int F_SQ = 0;                    // 16 KB  Q tile, later the O staging tile
+constexpr int F_SK = F_SQ + 16384;         // 32 KB
+constexpr int F_SV = F_SK + 32768;         // 32 KB
+constexpr int F_SP = F_SV + 32768;         // 64 KB  P: 4 k-blocks of [128 rows][128 B]
+constexpr int F_MISC = F_SP + 65536;       // mask floats [256] + barriers
+constexpr int F_SMEM = 1024 + F_MISC + 1024 + 64;
+
+__global__ void __launch_bounds__(FWD_THREADS, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO, const AttnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* sQ = smem + F_SQ;
+    uint8_t* sK = smem + F_SK;
+    uint8_t* sV = smem + F_SV;
+    uint8_t* sP = smem + F_SP;
+    float* sMask = reinterpret_cast<float*>(smem + F_MISC);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + F_MISC + 1024);  // 0 load, 1 S ready, 2 P ready, 3 O ready
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q_tiles = (p.S + 127) / 128;
+    const int qt = blockIdx.x % q_tiles;
+    const int h = (blockIdx.x / q_tiles) % p.nh;
+    const int b = blockIdx.x / (q_tiles * p.nh);
+    const int q0 = qt * 128;
+
+    if (threadIdx.x == 0) {
+        ptx::prefetch_tensormap(&tmQKV);
+        ptx::prefetch_tensormap(&tmO);
+        ptx::mbar_init(&bars[0], 1);
+        ptx::mbar_init(&bars[1], 1);
+        ptx::mbar_init(&bars[2], 128);
+        ptx::mbar_init(&bars[3], 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 0) ptx::tmem_alloc<512>(tmem_slot);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            ptx::mbar_expect_tx(&bars[0], 16384 + 32768 + 32768);
+            ptx::tma_load_4d(sQ, &tmQKV, &bars[0], 0, q0, h, b);
+            ptx::tma_load_4d(sK, &tmQKV, &bars[0], 0, 0, p.nh + h, b);
+            ptx::tma_load_4d(sK + 16384, &tmQKV, &bars[0], 0, 128, p.nh + h, b);
+            ptx::tma_load_4d(sV, &tmQKV, &bars[0], 0, 0, 2 * p.nh + h, b);
+            ptx::tma_load_4d(sV + 16384, &tmQKV, &bars[0], 0, 128, 2 * p.nh + h, b);
+            ptx::mbar_wait(&bars[0], 0);
+            ptx::tc_fence_after();
+            // S = Q K^T : A = Q (K-major), B = K (K-major), M128 N256, K = 64 in 4 steps
+            {
+                constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, 256, 0, 0);
+                const uint64_t base = ptx::umma_desc_base(16, 1024);
+                const uint32_t a = ptx::smem_u32(sQ), bb = ptx::smem_u32(sK);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    ptx::umma_bf16(tmem, ptx::umma_desc(base, a + k * 32), ptx::umma_desc(base, bb + k * 32), idesc, k > 0);
+                ptx::umma_commit(&bars[1]);
+            }
+            ptx::mbar_wait(&bars[2], 0);
+            ptx::tc_fence_after();
+            // O = P V : A = P (K-major, 4 k-blocks of 64 keys), B = V ([key][d], d contiguous => MN-major), M128 N64 K256
+            {
+                constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, 64, 0, 1);
+                const uint64_t abase = ptx::umma_desc_base(16, 1024);
+                const uint64_t bbase = ptx::umma_desc_base(64 * 128, 1024);
+                const uint32_t a = ptx::smem_u32(sP), bb = ptx::smem_u32(sV);
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                    ptx::umma_bf16(tmem + 256, ptx::umma_desc(abase, a + (k >> 2) * 16384 + (k & 3) * 32),
+                                   ptx::umma_desc(bbase, bb + k * 2048), idesc, k > 0);
+                ptx::umma_commit(&bars[3]);
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------- softmax / epilogue warps (thread = row)
+        const int t = threadIdx.x - 32;          // 0..127
+        const int quad = warp & 3;               // TMEM lane quadrant this warp may access
+        const int row = quad * 32 + lane;        // row inside the tile (== TMEM lane)
+        const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
+        // additive key mask, staged once: (1 - m) * -10000 for real keys, -inf for keys beyond S
+        for (int k = t; k < 256; k += 128) {
+            float mv = -INFINITY;
+            if (k < p.S) mv = p.mask ? (1.0f - (float)p.mask[(long long)b * p.S + k]) * -10000.0f : 0.f;
+            sMask[k] = mv;
+        }
+        named_bar_sync(1, 128);
+        ptx::mbar_wait(&bars[1], 0);
+        ptx::tc_fence_after();
+        const float sc = p.scale;
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+            float v[32];
+            ptx::tmem_ld32(lane_addr + c * 32, v);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaf(v[j], sc, sMask[c * 32 + j]));
+        }
+        const uint32_t step = p.thresh16 ? *p.d_step : 0u;
+        const long long grow = ((long long)(b * p.nh + h) * p.S + (q0 + row));  // row of the [B*nh*S, S] probability matrix
+        const int chunks_per_row = p.S >> 3;
+        float sum = 0.f;
+        const float mxl = mx * kLog2e;
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+            float v[32];
+            ptx::tmem_ld32(lane_addr + c * 32, v);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                v[j] = exp2f(fmaf(fmaf(v[j], sc, sMask[c * 32 + j]), kLog2e, -mxl));
+                sum += v[j];
+            }
+            if (p.thresh16) {
+#pragma unroll
+                for (int g8 = 0; g8 < 4; ++g8) {
+                    const int key0 = c * 32 + g8 * 8;
+                    if (key0 < p.S && q0 + row < p.S) {
+                        const uint32_t keep = dropout_keep8(p.seed, p.site, step, (unsigned long long)grow * chunks_per_row + (key0 >> 3), p.thresh16);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[g8 * 8 + j] = ((keep >> j) & 1u) ? v[g8 * 8 + j] * p.inv_keep : 0.f;
+                    }
+                }
+            }
+            // keys [32c, 32c+32) -> k-block c/2, 16-byte chunks (c&1)*4 .. +3 of row `row`
+            uint8_t* blk = sP + (c >> 1) * 16384 + row * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int chunk = ((c & 1) * 4 + j) ^ (row & 7);
+                *reinterpret_cast<bf16x8*>(blk + chunk * 16) = pack8(v + 8 * j);
+            }
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&bars[2]);
+        if (q0 + row < p.S) p.lse[grow] = mx + logf(sum);
+        const float inv = 1.0f / sum;
+        ptx::mbar_wait(&bars[3], 0);
+        ptx::tc_fence_after();
+        uint8_t* stg = sQ + quad * 4096;  // this warp's 32 rows of the O tile (Q is dead after the first MMA)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            float v[32];
+            ptx::tmem_ld32(lane_addr + 256 + hh * 32, v);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= inv;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int chunk = (hh * 4 + j) ^ (lane & 7);
+                *reinterpret_cast<bf16x8*>(stg + lane * 128 + chunk * 16) = pack8(v + 8 * j);
+            }
+        }
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            ptx::tma_store_4d(&tmO, stg, 0, q0 + quad * 32, h, b);  // rows >= S clipped
+            ptx::tma_store_commit();
+            ptx::tma_store_wait_all();
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<512>(tmem);
+    }
+}
+
+// ================================================================================================ backward
+constexpr int BWD_THREADS = 160;
+constexpr int B_SQ = 0;                   // 32 KB: Q rows 0..255
+constexpr int B_SK = B_SQ + 32768;
+constexpr int B_SV = B_SK + 32768;
+constexpr int B_SDO = B_SV + 32768;
+constexpr int B_SPD = B_SDO + 32768;      // 32 KB: Pd_ij  [2 key groups][128 q][64 keys]
+constexpr int B_SDS = B_SPD + 32768;      // 32 KB: dS_ij  same layout
+constexpr int B_MISC = B_SDS + 32768;     // mask [256] floats, barriers
+constexpr int B_SMEM = 1024 + B_MISC + 1024 + 128;
+
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                const __grid_constant__ CUtensorMap tmDQKV, const bf16* __restrict__ ctx, const bf16* __restrict__ dctx,
+                const AttnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* sQ = smem + B_SQ;
+    uint8_t* sK = smem + B_SK;
+    uint8_t* sV = smem + B_SV;
+    uint8_t* sDO = smem + B_SDO;
+    uint8_t* sPd = smem + B_SPD;
+    uint8_t* sDS = smem + B_SDS;
+    float* sMask = reinterpret_cast<float*>(smem + B_MISC);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_MISC + 1024);  // 0 load, 1 S/dP ready, 2 Pd/dS ready, 3 block MMAs done
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int h = blockIdx.x % p.nh;
+    const int b = blockIdx.x / p.nh;
+    const int H = p.nh * DH;
+    const int n_qt = (p.S + 127) / 128;   // query tiles (1 or 2)
+    const int n_kh = n_qt;                // key halves
+
+    if (threadIdx.x == 0) {
+        ptx::prefetch_tensormap(&tmQKV);
+        ptx::prefetch_tensormap(&tmDO);
+        ptx::prefetch_tensormap(&tmDQKV);
+        ptx::mbar_init(&bars[0], 1);
+        ptx::mbar_init(&bars[1], 1);
+        ptx::mbar_init(&bars[2], 128);
+        ptx::mbar_init(&bars[3], 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 0) ptx::tmem_alloc<512>(tmem_slot);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    constexpr uint32_t C_S = 0, C_DP = 128, C_DQ0 = 256, C_DK = 320, C_DV = 384, C_DQ1 = 448;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            ptx::mbar_expect_tx(&bars[0], 4 * 32768);
+            for (int r = 0; r < 2; ++r) {
+                ptx::tma_load_4d(sQ + r * 16384, &tmQKV, &bars[0], 0, r * 128, h, b);
+                ptx::tma_load_4d(sK + r * 16384, &tmQKV, &bars[0], 0, r * 128, p.nh + h, b);
+                ptx::tma_load_4d(sV + r * 16384, &tmQKV, &bars[0], 0, r * 128, 2 * p.nh + h, b);
+                ptx::tma_load_4d(sDO + r * 16384, &tmDO, &bars[0], 0, r * 128, h, b);
+            }
+            ptx::mbar_wait(&bars[0], 0);
+            ptx::tc_fence_after();
+            const uint64_t kbase = ptx::umma_desc_base(16, 1024);            // K-major, one 64-wide k-block
+            const uint64_t mn1 = ptx::umma_desc_base(128 * 128, 1024);       // MN-major, 64-wide groups 16 KB apart (128 k-rows)
+            const uint32_t aQ = ptx::smem_u32(sQ), aK = ptx::smem_u32(sK), aV = ptx::smem_u32(sV), aDO = ptx::smem_u32(sDO);
+            const uint32_t aPd = ptx::smem_u32(sPd), aDS = ptx::smem_u32(sDS);
+            uint32_t ph2 = 0;
+            int blk = 0;
+            for (int j = 0; j < n_kh; ++j) {
+                for (int i = 0; i < n_qt; ++i, ++blk) {
+                    if (blk > 0) {  // previous block's MMAs must have drained S/dP (TMEM) and Pd/dS (smem)
+                        ptx::mbar_wait(&bars[3], (blk - 1) & 1);
+                        ptx::tc_fence_after();
+                    }
+                    {   // S_ij = Q_i K_j^T ; dP_ij = dO_i V_j^T   (M128 N128 K64)
+                        constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, 128, 0, 0);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            ptx::umma_bf16(tmem + C_S, ptx::umma_desc(kbase, aQ + i * 16384 + k * 32),
+                                           ptx::umma_desc(kbase, aK + j * 16384 + k * 32), idesc, k > 0);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            ptx::umma_bf16(tmem + C_DP, ptx::umma_desc(kbase, aDO + i * 16384 + k * 32),
+                                           ptx::umma_desc(kbase, aV + j * 16384 + k * 32), idesc, k > 0);
+                        ptx::umma_commit(&bars[1]);
+                    }
+                    ptx::mbar_wait(&bars[2], ph2);
+                    ph2 ^= 1;
+                    ptx::tc_fence_after();
+                    {   // dV_j += Pd_ij^T dO_i ; dK_j += dS_ij^T Q_i   (A MN-major over keys, B MN-major over d; M128 N64 K128)
+                        constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, 64, 1, 1);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            ptx::umma_bf16(tmem + C_DV, ptx::umma_desc(mn1, aPd + k * 2048),
+                                           ptx::umma_desc(mn1, aDO + i * 16384 + k * 2048), idesc, (i > 0 || k > 0));
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            ptx::umma_bf16(tmem + C_DK, ptx::umma_desc(mn1, aDS + k * 2048),
+                                           ptx::umma_desc(mn1, aQ + i * 16384 + k * 2048), idesc, (i > 0 || k > 0));
+                    }
+                    {   // dQ_i += dS_ij K_j   (A K-major: 2 k-blocks of 64 keys; B = K_j rows as MN-major over d; M128 N64 K128)
+                        constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, 64, 0, 1);
+                        const uint32_t cdq = i == 0 ? C_DQ0 : C_DQ1;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            ptx::umma_bf16(tmem + cdq, ptx::umma_desc(kbase, aDS + (k >> 2) * 16384 + (k & 3) * 32),
+                                           ptx::umma_desc(mn1, aK + j * 16384 + k * 2048), idesc, (j > 0 || k > 0));
+                    }
+                    ptx::umma_commit(&bars[3]);
+                }
+                // dK_j / dV_j complete after the last query tile: the epilogue threads drain them (they wait on bars[3])
+            }
+        }
+    } else {
+        const int t = threadIdx.x - 32;
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
+        for (int k = t; k < 256; k += 128) {
+            float mv = -INFINITY;
+            if (k < p.S) mv = p.mask ? (1.0f - (float)p.mask[(long long)b * p.S + k]) * -10000.0f : 0.f;
+            sMask[k] = mv;
+        }
+        // delta_row = sum_d dO[row,d] * O[row,d], L_row, for this thread's row in each query tile
+        float delta[2] = {0.f, 0.f}, Lrow[2] = {0.f, 0.f};
+        for (int i = 0; i < n_qt; ++i) {
+            const int q = i * 128 + row;
+            if (q < p.S) {
+                const bf16* o = ctx + ((long long)b * p.S + q) * H + h * DH;
+                const bf16* d = dctx + ((long long)b * p.S + q) * H + h * DH;
+                float acc = 0.f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float ov[8], dv[8];
+                    unpack8(*reinterpret_cast<const bf16x8*>(o + c * 8), ov);
+                    unpack8(*reinterpret_cast<const bf16x8*>(d + c * 8), dv);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc = fmaf(ov[e], dv[e], acc);
+                }
+                delta[i] = acc;
+                Lrow[i] = p.lse[(long long)(b * p.nh + h) * p.S + q];
+            }
+        }
+        named_bar_sync(1, 128);
+        const uint32_t step = p.thresh16 ? *p.d_step : 0u;
+        const int chunks_per_row = p.S >> 3;
+        const float sc = p.scale;
+        uint32_t ph1 = 0;
+        int blk = 0;
+        for (int j = 0; j < n_kh; ++j) {
+            for (int i = 0; i < n_qt; ++i, ++blk) {
+                ptx::mbar_wait(&bars[1], ph1);
+                ph1 ^= 1;
+                ptx::tc_fence_after();
+                const int q = i * 128 + row;
+                const bool qvalid = q < p.S;
+                const long long grow = (long long)(b * p.nh + h) * p.S + q;
+                const float Ll = Lrow[i] * kLog2e, dl = delta[i];
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {  // 32 keys per chunk: keys j*128 + c*32 ..
+                    float s[32], dp[32];
+                    ptx::tmem_ld32(lane_addr + C_S + c * 32, s);
+                    ptx::tmem_ld32(lane_addr + C_DP + c * 32, dp);
+                    ptx::tmem_ld_wait();
+                    float pd[32];
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const float pr = qvalid ? exp2f(fmaf(fmaf(s[e], sc, sMask[j * 128 + c * 32 + e]), kLog2e, -Ll)) : 0.f;
+                        s[e] = pr;
+                        pd[e] = pr;
+                    }
+                    if (p.thresh16) {
+#pragma unroll
+                        for (int g8 = 0; g8 < 4; ++g8) {
+                            const int key0 = j * 128 + c * 32 + g8 * 8;
+                            if (key0 < p.S && qvalid) {
+                                const uint32_t keep = dropout_keep8(p.seed, p.site, step, (unsigned long long)grow * chunks_per_row + (key0 >> 3), p.thresh16);
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    const bool kp = (keep >> e) & 1u;
+                                    pd[g8 * 8 + e] = kp ? pd[g8 * 8 + e] * p.inv_keep : 0.f;
+                                    dp[g8 * 8 + e] = kp ? dp[g8 * 8 + e] * p.inv_keep : 0.f;
+                                }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) dp[e] = s[e] * (dp[e] - dl) * sc;  // dS
+                    // keys [32c, 32c+32) of this half -> key group c/2, 16-byte chunks (c&1)*4.. of row `row`
+                    uint8_t* bp = sPd + (c >> 1) * 16384 + row * 128;
+                    uint8_t* bs = sDS + (c >> 1) * 16384 + row * 128;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int chunk = ((c & 1) * 4 + e) ^ (row & 7);
+                        *reinterpret_cast<bf16x8*>(bp + chunk * 16) = pack8(pd + 8 * e);
+                        *reinterpret_cast<bf16x8*>(bs + chunk * 16) = pack8(dp + 8 * e);
+                    }
+                }
+                ptx::fence_proxy_async_smem();
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(&bars[2]);
+                // drain finished accumulators while nothing else needs these threads
+                const bool last_i = (i == n_qt - 1);
+                const bool last_j = (j == n_kh - 1);
+                if (last_i || last_j) {
+                    ptx::mbar_wait(&bars[3], blk & 1);  // this block's MMAs (incl. the accumulations) have retired
+                    ptx::tc_fence_after();
+                    uint8_t* stg = sPd + quad * 4096;   // Pd/dS are free again until the next arrive on bars[2]
+                    auto drain = [&](uint32_t col, int slot, int row0) {
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            float v[32];
+                            ptx::tmem_ld32(lane_addr + col + hh * 32, v);
+                            ptx::tmem_ld_wait();
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int chunk = (hh * 4 + e) ^ (lane & 7);
+                                *reinterpret_cast<bf16x8*>(stg + lane * 128 + chunk * 16) = pack8(v + 8 * e);
+                            }
+                        }
+                        ptx::fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            ptx::tma_store_4d(&tmDQKV, stg, 0, row0 + quad * 32, slot, b);
+                            ptx::tma_store_commit();
+                            ptx::tma_store_wait_all();
+                        }
+                        __syncwarp();
+                    };
+                    if (last_i) {
+                        drain(C_DK, p.nh + h, j * 128);
+                        drain(C_DV, 2 * p.nh + h, j * 128);
+                    }
+                    if (last_j) drain(i == 0 ? C_DQ0 : C_DQ1, h, i * 128);
+                    ptx::tc_fence_before();
+                    named_bar_sync(1, 128);  // all four warps finished reading TMEM / staging before the next block reuses them
+                }
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<512>(tmem);
+    }
+}
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(f);
+    }
+    return fn;
+}
+
+// (dh, s, slot, b) view of a [B, S, slots*dh] bf16 tensor; box = {64, box_rows, 1, 1}, 128B swizzle
+int head_map(CUtensorMap* m, const void* ptr, int B, int S, int slots, int box_rows) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) {
+        polus_set_error("cuTensorMapEncodeTiled entry point not found");
+        return POLUS_ERR_CUDA;
+    }
+    const cuuint64_t row = (cuuint64_t)slots * DH * 2;
+    cuuint64_t dims[4] = {DH, (cuuint64_t)S, (cuuint64_t)slots, (cuuint64_t)B};
+    cuuint64_t strides[3] = {row, DH * 2, row * (cuuint64_t)S};
+    cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        polus_set_error("attention: cuTensorMapEncodeTiled failed (%d)", (int)r);
+        return POLUS_ERR_INVALID;
+    }
+    return 0;
+}
+
+AttnParams make_params(int B, int S, int nh, float p_drop, uint64_t seed, uint32_t site, const uint32_t* d_step,
+                       const int32_t* mask, float* lse) {
+    AttnParams p;
+    p.B = B; p.S = S; p.nh = nh;
+    p.scale = 1.0f / sqrtf((float)DH);
+    p.thresh16 = p_drop > 0.f ? (uint32_t)lrintf(p_drop * 65536.0f) : 0u;
+    p.inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+    p.seed = seed; p.site = site; p.d_step = d_step; p.mask = mask; p.lse = lse;
+    return p;
+}
+
+}  // namespace
+
+extern "C" int polus_attention_supported(int S, int dh) { return (dh == DH && S >= 8 && S <= 256 && S % 8 == 0) ? 1 : 0; }
+
+extern "C" int polus_attention_fwd(const polus_bf16_t* qkv, const int32_t* mask, int B, int S, int nh, int dh, float p_drop,
+                                   uint64_t seed, uint32_t site, const uint32_t* d_step, polus_bf16_t* ctx, float* lse,
+                                   void* stream) {
+    POLUS_REQUIRE(polus_attention_supported(S, dh), "polus_attention_fwd: needs head_dim 64 and S <= 256, S %% 8 == 0 (got S=%d dh=%d)", S, dh);
+    POLUS_REQUIRE(p_drop == 0.f || d_step != nullptr, "polus_attention_fwd: dropout needs d_step");
+    if (B == 0) return 0;
+    CUtensorMap tq, to;
+    int rc = head_map(&tq, qkv, B, S, 3 * nh, 128);
+    if (rc) return rc;
+    rc = head_map(&to, ctx, B, S, nh, 32);
+    if (rc) return rc;
+    static bool set = false;
+    if (!set) {
+        POLUS_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
+        set = true;
+    }
+    AttnParams p = make_params(B, S, nh, p_drop, seed, site, d_step, mask, lse);
+    const int q_tiles = (S + 127) / 128;
+    attn_fwd_kernel<<<B * nh * q_tiles, FWD_THREADS, F_SMEM, (cudaStream_t)stream>>>(tq, to, p);
+    g_launch_count++;
+    POLUS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int polus_attention_bwd(const polus_bf16_t* qkv, const int32_t* mask, const polus_bf16_t* ctx,
+                                   const polus_bf16_t* dctx, const float* lse, int B, int S, int nh, int dh, float p_drop,
+                                   uint64_t seed, uint32_t site, const uint32_t* d_step, polus_bf16_t* dqkv, void* stream) {
+    POLUS_REQUIRE(polus_attention_supported(S, dh), "polus_attention_bwd: needs head_dim 64 and S <= 256, S %% 8 == 0 (got S=%d dh=%d)", S, dh);
+    if (B == 0) return 0;
+    CUtensorMap tq, tdo, tdq;
+    int rc = head_map(&tq, qkv, B, S, 3 * nh, 128);
+    if (rc) return rc;
+    rc = head_map(&tdo, dctx, B, S, nh, 128);
+    if (rc) return rc;
+    rc = head_map(&tdq, dqkv, B, S, 3 * nh, 32);
+    if (rc) return rc;
+    static bool set = false;
+    if (!set) {
+        POLUS_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
+        set = true;
+    }
+    AttnParams p = make_params(B, S, nh, p_drop, seed, site, d_step, mask, const_cast<float*>(lse));
+    attn_bwd_kernel<<<B * nh, BWD_THREADS, B_SMEM, (cudaStream_t)stream>>>(tq, tdo, tdq, (const bf16*)ctx, (const bf16*)dctx, p);
+    g_launch_count++;
+    POLUS_LAUNCH_CHECK();
+    return 0;
+}

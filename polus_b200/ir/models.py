@@ -46,11 +46,8 @@ def in_batch_scores(q, d_pos, *d_negs):
 
 def softmax_ranking_loss(pos_scores, neg_scores):
     """-log softmax over [in-batch documents]: cross entropy of row i against column i."""
-    import numpy as np
-    from ..tensor import I32, Tensor
     B = neg_scores.shape[0]
-    labels = Tensor.from_numpy(np.arange(B, dtype=np.int32), I32)
-    return ops.cross_entropy(0, neg_scores, labels)
+    return ops.cross_entropy(0, neg_scores, ops.constant_arange(B))
 
 
 class BertCrossEncoder(PolusModel):

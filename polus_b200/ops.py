@@ -466,6 +466,8 @@ def attention(qkv, mask, n_heads, p_drop=0.0):
     dh = H // n_heads
     assert dh % 8 == 0 and S % 8 == 0, "attention needs head_dim and sequence length multiples of 8"
     qkv = cast(qkv, BF16)
+    if FUSED_ATTENTION and _lib.call("polus_attention_supported", S, dh) == 1:
+        return _attention_fused(qkv, mask, n_heads, p_drop)
     nb = Bsz * n_heads
     scale = 1.0 / math.sqrt(dh)
     q_ptr, k_ptr, v_ptr = qkv.ptr, qkv.ptr + H * 2, qkv.ptr + 2 * H * 2
@@ -507,6 +509,33 @@ def attention(qkv, mask, n_heads, p_drop=0.0):
             # dK[S',dh] = dS^T[S',S] . Q[S,dh]
             _gemm(S, dh, S, pop(dP.ptr, True), _operand(q_ptr, ld, True, BF16, bs0, bs1), dk_ptr, H3, BF16,
                   batch0=n_heads, batch1=Bsz, cbs0=dh, cbs1=S * H3)
+            return [dqkv]
+        _record(tape, [qkv], ctx, backward)
+    return ctx
+
+
+FUSED_ATTENTION = __import__("os").environ.get("POLUS_FUSED_ATTN", "1") != "0"
+
+
+def _attention_fused(qkv, mask, n_heads, p_drop):
+    """One kernel per direction: scores and probabilities stay in TMEM / shared memory (csrc/attention.cu)."""
+    Bsz, S, H3 = qkv.shape
+    H = H3 // 3
+    dh = H // n_heads
+    ctx = Tensor((Bsz, S, H), BF16)
+    lse = Tensor((Bsz, n_heads, S), F32)
+    site = _next_site() if p_drop > 0 else 0
+    seed = _rng_state["seed"]
+    mptr = mask.ptr if mask is not None else None
+    _lib.call("polus_attention_fwd", qkv.ptr, mptr, Bsz, S, n_heads, dh, p_drop, seed, site, step_counter(), ctx.ptr,
+              lse.ptr, device.stream())
+    tape = _recording(qkv)
+    if tape is not None:
+        def backward(g):
+            g = cast(g, BF16)
+            dqkv = Tensor((Bsz, S, H3), BF16)
+            _lib.call("polus_attention_bwd", qkv.ptr, mptr, ctx.ptr, g.ptr, lse.ptr, Bsz, S, n_heads, dh, p_drop, seed, site,
+                      step_counter(), dqkv.ptr, device.stream())
             return [dqkv]
         _record(tape, [qkv], ctx, backward)
     return ctx
@@ -735,3 +764,15 @@ def gather_cols0(x):
     _lib.call("polus_fill_f32", sel.ptr, 1.0, 1, device.stream())
     out = matmul(x, sel)
     return reshape(out, (rows,))
+
+
+_const_cache = {}
+
+
+def constant_arange(n):
+    """int32 [0..n) on the device, created once per n (host uploads are not allowed while a step is being
+    captured, so constants are built on the first, op-by-op, call and reused afterwards)."""
+    t = _const_cache.get(("arange", n))
+    if t is None:
+        t = _const_cache[("arange", n)] = Tensor.from_numpy(np.arange(n, dtype=np.int32), I32)
+    return t

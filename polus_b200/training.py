@@ -150,11 +150,18 @@ class _CompiledStep:
         self.blocks = tensor.begin_trace()
         try:
             _lib.call("polus_graph_begin", st)
+            g = C.c_void_p()
             try:
                 self.loss = self.trainer._step_body(*_rebuild(self.struct, self.inputs))
-            finally:
-                g = C.c_void_p()
-                _lib.call("polus_graph_end", st, C.byref(g))
+            except Exception as e:
+                try:  # leave capture mode so the stream stays usable, then report the real cause
+                    _lib.call("polus_graph_end", st, C.byref(g))
+                except Exception:
+                    pass
+                raise RuntimeError("the training step could not be captured into a CUDA graph (an op in the model / loss "
+                                   "needs a host<->device sync, e.g. creating a tensor from numpy inside the step); "
+                                   "set POLUS_EAGER=1 to run op by op") from e
+            _lib.call("polus_graph_end", st, C.byref(g))
             self.graph = g.value
         finally:
             tensor.end_trace()
