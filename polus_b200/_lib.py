@@ -94,8 +94,9 @@ _SIGS = {
     "polus_softmax_fwd": [p, p, i32, i32, i32, i32, f32, f32, u64, u32, p, p, p, p],
     "polus_softmax_bwd": [p, p, i32, i32, i32, i32, f32, f32, u64, u32, p, p],
     "polus_attention_supported": [i32, i32],
-    "polus_attention_fwd": [p, p, i32, i32, i32, i32, f32, u64, u32, p, p, p, p],
-    "polus_attention_bwd": [p, p, p, p, p, i32, i32, i32, i32, f32, u64, u32, p, p, p],
+    "polus_attention_keepbits_words": [i32, i32, i32],
+    "polus_attention_fwd": [p, p, i32, i32, i32, i32, f32, u64, u32, p, p, p, p, p],
+    "polus_attention_bwd": [p, p, p, p, p, i32, i32, i32, i32, f32, u64, u32, p, p, p, p],
     "polus_act_bwd_colsum": [p, p, i32, i32, i32, p, p, p, p],
     "polus_colsum_ws_floats": [i32],
     "polus_dropout": [p, p, i64, f32, u64, u32, p, p],
@@ -127,9 +128,9 @@ _SIGS = {
     "polus_comm_destroy": [],
 }
 _RET = {"polus_launch_count": C.c_int64, "polus_ln_ws_floats": sz, "polus_colsum_ws_floats": sz,
-        "polus_embed_ws_floats": sz}
+        "polus_embed_ws_floats": sz, "polus_attention_keepbits_words": sz}
 # functions whose int return is a value, not a status
-_VALUE_RET = {"polus_version", "polus_gemm_tc_supported", "polus_skinny_supported", "polus_attention_supported", "polus_comm_size", "polus_comm_rank",
+_VALUE_RET = {"polus_version", "polus_gemm_tc_supported", "polus_skinny_supported", "polus_attention_supported", "polus_attention_keepbits_words", "polus_comm_size", "polus_comm_rank",
               "polus_launch_count", "polus_ln_ws_floats", "polus_colsum_ws_floats", "polus_embed_ws_floats"}
 
 EXPORTS = ["polus_last_error"] + list(_SIGS)

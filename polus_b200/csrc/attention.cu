@@ -44,6 +44,7 @@ struct AttnParams {
     const uint32_t* d_step;
     const int32_t* mask;   // [B,S] or null
     float* lse;            // [B,nh,S]
+    uint32_t* keepbits;    // [B*nh*S][S/32] dropout keep bits (forward writes, backward reads); null when p = 0
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -51,24 +52,25 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 }
 
 // ================================================================================================ forward
-constexpr int FWD_THREADS = 160;
-constexpr int F_SQ = 0;                    // 16 KB  Q tile, later the O staging tile
-constexpr int F_SK = F_SQ + 16384;         // 32 KB
-constexpr int F_SV = F_SK + 32768;         // 32 KB
-constexpr int F_SP = F_SV + 32768;         // 64 KB  P: 4 k-blocks of [128 rows][128 B]
-constexpr int F_MISC = F_SP + 65536;       // mask floats [256] + barriers
-constexpr int F_SMEM = 1024 + F_MISC + 1024 + 64;
+// 288 threads: warp 0 = TMA + MMA issue, warps 1-8 = softmax (thread = (query row, key half)); 2 CTAs per SM.
+constexpr int FWD_THREADS = 288;
+constexpr int F_SQ = 0;                    // 16 KB  Q tile                       } P (64 KB) overlays Q, K and the
+constexpr int F_SK = 16384;                // 32 KB  K                            } 16 KB pad once S = Q K^T retired;
+constexpr int F_SV = 65536;                // 32 KB  V                              O staging reuses the first 16 KB
+constexpr int F_MISC = F_SV + 32768;       // mask [256] f32 | red [2][128] f32 | barriers
+constexpr int F_SMEM = 1024 + F_MISC + 1024 + 1024 + 64;
 
-__global__ void __launch_bounds__(FWD_THREADS, 1)
+__global__ void __launch_bounds__(FWD_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO, const AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint8_t* sQ = smem + F_SQ;
     uint8_t* sK = smem + F_SK;
     uint8_t* sV = smem + F_SV;
-    uint8_t* sP = smem + F_SP;
+    uint8_t* sP = smem;  // overlay
     float* sMask = reinterpret_cast<float*>(smem + F_MISC);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + F_MISC + 1024);  // 0 load, 1 S ready, 2 P ready, 3 O ready
+    float* sRed = reinterpret_cast<float*>(smem + F_MISC + 1024);        // [2 halves][128 rows]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + F_MISC + 2048);  // 0 load, 1 S ready, 2 P ready, 3 O ready
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -83,11 +85,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         ptx::prefetch_tensormap(&tmO);
         ptx::mbar_init(&bars[0], 1);
         ptx::mbar_init(&bars[1], 1);
-        ptx::mbar_init(&bars[2], 128);
+        ptx::mbar_init(&bars[2], 256);
         ptx::mbar_init(&bars[3], 1);
         ptx::fence_barrier_init();
     }
-    if (warp == 0) ptx::tmem_alloc<512>(tmem_slot);
+    if (warp == 0) ptx::tmem_alloc<256>(tmem_slot);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -103,8 +105,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             ptx::tma_load_4d(sV + 16384, &tmQKV, &bars[0], 0, 128, 2 * p.nh + h, b);
             ptx::mbar_wait(&bars[0], 0);
             ptx::tc_fence_after();
-            // S = Q K^T : A = Q (K-major), B = K (K-major), M128 N256, K = 64 in 4 steps
-            {
+            {   // S = Q K^T : A = Q (K-major), B = K (K-major), M128 N256, K = 64 in 4 steps
                 constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, 256, 0, 0);
                 const uint64_t base = ptx::umma_desc_base(16, 1024);
                 const uint32_t a = ptx::smem_u32(sQ), bb = ptx::smem_u32(sK);
@@ -115,103 +116,115 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             }
             ptx::mbar_wait(&bars[2], 0);
             ptx::tc_fence_after();
-            // O = P V : A = P (K-major, 4 k-blocks of 64 keys), B = V ([key][d], d contiguous => MN-major), M128 N64 K256
-            {
+            {   // O = P V : A = P (K-major, 4 k-blocks of 64 keys), B = V ([key][d] => MN-major), M128 N64 K256 -> cols 0..63
                 constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, 64, 0, 1);
                 const uint64_t abase = ptx::umma_desc_base(16, 1024);
                 const uint64_t bbase = ptx::umma_desc_base(64 * 128, 1024);
                 const uint32_t a = ptx::smem_u32(sP), bb = ptx::smem_u32(sV);
 #pragma unroll
                 for (int k = 0; k < 16; ++k)
-                    ptx::umma_bf16(tmem + 256, ptx::umma_desc(abase, a + (k >> 2) * 16384 + (k & 3) * 32),
+                    ptx::umma_bf16(tmem, ptx::umma_desc(abase, a + (k >> 2) * 16384 + (k & 3) * 32),
                                    ptx::umma_desc(bbase, bb + k * 2048), idesc, k > 0);
                 ptx::umma_commit(&bars[3]);
             }
         }
     } else {
-        // ---------------------------------------------------------------- softmax / epilogue warps (thread = row)
-        const int t = threadIdx.x - 32;          // 0..127
+        // ---------------------------------------------------------------- softmax / epilogue: thread = (row, key half)
+        const int t = threadIdx.x - 32;          // 0..255
+        const int e = warp - 1;                  // 0..7
         const int quad = warp & 3;               // TMEM lane quadrant this warp may access
+        const int half = e >> 2;                 // keys [128*half, 128*half + 128)
         const int row = quad * 32 + lane;        // row inside the tile (== TMEM lane)
         const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
         // additive key mask, staged once: (1 - m) * -10000 for real keys, -inf for keys beyond S
-        for (int k = t; k < 256; k += 128) {
+        {
             float mv = -INFINITY;
-            if (k < p.S) mv = p.mask ? (1.0f - (float)p.mask[(long long)b * p.S + k]) * -10000.0f : 0.f;
-            sMask[k] = mv;
+            if (t < p.S) mv = p.mask ? (1.0f - (float)p.mask[(long long)b * p.S + t]) * -10000.0f : 0.f;
+            sMask[t] = mv;
         }
-        named_bar_sync(1, 128);
+        named_bar_sync(1, 256);
         ptx::mbar_wait(&bars[1], 0);
         ptx::tc_fence_after();
         const float sc = p.scale;
         float mx = -INFINITY;
 #pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
+        for (int c = 0; c < 4; ++c) {
             float v[32];
-            ptx::tmem_ld32(lane_addr + c * 32, v);
+            ptx::tmem_ld32(lane_addr + half * 128 + c * 32, v);
             ptx::tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaf(v[j], sc, sMask[c * 32 + j]));
+            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaf(v[j], sc, sMask[half * 128 + c * 32 + j]));
         }
+        sRed[half * 128 + row] = mx;
+        named_bar_sync(1, 256);
+        mx = fmaxf(mx, sRed[(half ^ 1) * 128 + row]);  // keys beyond S are -inf, real keys finite: mx is finite
+        named_bar_sync(1, 256);                        // sRed is reused for the sums below
         const uint32_t step = p.thresh16 ? *p.d_step : 0u;
+        const bool qvalid = q0 + row < p.S;
         const long long grow = ((long long)(b * p.nh + h) * p.S + (q0 + row));  // row of the [B*nh*S, S] probability matrix
         const int chunks_per_row = p.S >> 3;
         float sum = 0.f;
         const float mxl = mx * kLog2e;
 #pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
+        for (int c = 0; c < 4; ++c) {
             float v[32];
-            ptx::tmem_ld32(lane_addr + c * 32, v);
+            ptx::tmem_ld32(lane_addr + half * 128 + c * 32, v);
             ptx::tmem_ld_wait();
+            const int kc = half * 128 + c * 32;  // first key of this chunk
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                v[j] = exp2f(fmaf(fmaf(v[j], sc, sMask[c * 32 + j]), kLog2e, -mxl));
+                v[j] = exp2f(fmaf(fmaf(v[j], sc, sMask[kc + j]), kLog2e, -mxl));
                 sum += v[j];
             }
             if (p.thresh16) {
+                uint32_t bits = 0;
 #pragma unroll
                 for (int g8 = 0; g8 < 4; ++g8) {
-                    const int key0 = c * 32 + g8 * 8;
-                    if (key0 < p.S && q0 + row < p.S) {
-                        const uint32_t keep = dropout_keep8(p.seed, p.site, step, (unsigned long long)grow * chunks_per_row + (key0 >> 3), p.thresh16);
+                    const int key0 = kc + g8 * 8;
+                    uint32_t keep = 0xFFu;
+                    if (key0 < p.S && qvalid)
+                        keep = dropout_keep8(p.seed, p.site, step, (unsigned long long)grow * chunks_per_row + (key0 >> 3), p.thresh16);
+                    bits |= keep << (8 * g8);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) v[g8 * 8 + j] = ((keep >> j) & 1u) ? v[g8 * 8 + j] * p.inv_keep : 0.f;
-                    }
+                    for (int j = 0; j < 8; ++j) v[g8 * 8 + j] = ((keep >> j) & 1u) ? v[g8 * 8 + j] * p.inv_keep : 0.f;
                 }
+                if (qvalid && kc < p.S) p.keepbits[grow * (p.S >> 5) + (kc >> 5)] = bits;  // reused by the backward kernel
             }
-            // keys [32c, 32c+32) -> k-block c/2, 16-byte chunks (c&1)*4 .. +3 of row `row`
-            uint8_t* blk = sP + (c >> 1) * 16384 + row * 128;
+            // keys [kc, kc+32) -> k-block kc/64, 16-byte chunks ((kc/32)&1)*4 .. +3 of row `row`
+            uint8_t* blk = sP + (kc >> 6) * 16384 + row * 128;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int chunk = ((c & 1) * 4 + j) ^ (row & 7);
+                const int chunk = (((kc >> 5) & 1) * 4 + j) ^ (row & 7);
                 *reinterpret_cast<bf16x8*>(blk + chunk * 16) = pack8(v + 8 * j);
             }
         }
+        sRed[half * 128 + row] = sum;
         ptx::fence_proxy_async_smem();
         ptx::tc_fence_before();
         ptx::mbar_arrive(&bars[2]);
-        if (q0 + row < p.S) p.lse[grow] = mx + logf(sum);
+        named_bar_sync(1, 256);
+        sum += sRed[(half ^ 1) * 128 + row];
+        if (qvalid && half == 0) p.lse[grow] = mx + logf(sum);
         const float inv = 1.0f / sum;
         ptx::mbar_wait(&bars[3], 0);
         ptx::tc_fence_after();
-        uint8_t* stg = sQ + quad * 4096;  // this warp's 32 rows of the O tile (Q is dead after the first MMA)
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
+        {   // O columns [32*half, +32) of this row -> staging tile [128 rows][128 B] at the start of the P region
             float v[32];
-            ptx::tmem_ld32(lane_addr + 256 + hh * 32, v);
+            ptx::tmem_ld32(lane_addr + half * 32, v);
             ptx::tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] *= inv;
+            uint8_t* stg = smem + row * 128;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int chunk = (hh * 4 + j) ^ (lane & 7);
-                *reinterpret_cast<bf16x8*>(stg + lane * 128 + chunk * 16) = pack8(v + 8 * j);
+                const int chunk = (half * 4 + j) ^ (row & 7);
+                *reinterpret_cast<bf16x8*>(stg + chunk * 16) = pack8(v + 8 * j);
             }
         }
         ptx::fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-            ptx::tma_store_4d(&tmO, stg, 0, q0 + quad * 32, h, b);  // rows >= S clipped
+        named_bar_sync(1, 256);
+        if (half == 0 && lane == 0) {
+            ptx::tma_store_4d(&tmO, smem + quad * 4096, 0, q0 + quad * 32, h, b);  // rows >= S clipped
             ptx::tma_store_commit();
             ptx::tma_store_wait_all();
         }
@@ -220,17 +233,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     __syncthreads();
     if (warp == 0) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc<512>(tmem);
+        ptx::tmem_dealloc<256>(tmem);
     }
 }
 
 // ================================================================================================ backward
-constexpr int BWD_THREADS = 160;
+// 288 threads: warp 0 = TMA + MMA issue, warps 1-8: thread = (query row, 64-key half of the 128-key block).
+constexpr int BWD_THREADS = 288;
 constexpr int B_SQ = 0;                   // 32 KB: Q rows 0..255
 constexpr int B_SK = B_SQ + 32768;
 constexpr int B_SV = B_SK + 32768;
 constexpr int B_SDO = B_SV + 32768;
-constexpr int B_SPD = B_SDO + 32768;      // 32 KB: Pd_ij  [2 key groups][128 q][64 keys]
+constexpr int B_SPD = B_SDO + 32768;      // 32 KB: Pd_ij  [2 key groups][128 q][64 keys]; also the drain staging tile
 constexpr int B_SDS = B_SPD + 32768;      // 32 KB: dS_ij  same layout
 constexpr int B_MISC = B_SDS + 32768;     // mask [256] floats, barriers
 constexpr int B_SMEM = 1024 + B_MISC + 1024 + 128;
@@ -256,7 +270,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const int b = blockIdx.x / p.nh;
     const int H = p.nh * DH;
     const int n_qt = (p.S + 127) / 128;   // query tiles (1 or 2)
-    const int n_kh = n_qt;                // key halves
+    const int n_kh = n_qt;                // 128-key blocks
 
     if (threadIdx.x == 0) {
         ptx::prefetch_tensormap(&tmQKV);
@@ -264,7 +278,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         ptx::prefetch_tensormap(&tmDQKV);
         ptx::mbar_init(&bars[0], 1);
         ptx::mbar_init(&bars[1], 1);
-        ptx::mbar_init(&bars[2], 128);
+        ptx::mbar_init(&bars[2], 256);
         ptx::mbar_init(&bars[3], 1);
         ptx::fence_barrier_init();
     }
@@ -334,18 +348,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                     }
                     ptx::umma_commit(&bars[3]);
                 }
-                // dK_j / dV_j complete after the last query tile: the epilogue threads drain them (they wait on bars[3])
             }
         }
     } else {
-        const int t = threadIdx.x - 32;
+        const int t = threadIdx.x - 32;   // 0..255
+        const int e = warp - 1;
         const int quad = warp & 3;
+        const int half = e >> 2;          // keys [64*half, +64) of the current 128-key block
         const int row = quad * 32 + lane;
         const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
-        for (int k = t; k < 256; k += 128) {
+        {
             float mv = -INFINITY;
-            if (k < p.S) mv = p.mask ? (1.0f - (float)p.mask[(long long)b * p.S + k]) * -10000.0f : 0.f;
-            sMask[k] = mv;
+            if (t < p.S) mv = p.mask ? (1.0f - (float)p.mask[(long long)b * p.S + t]) * -10000.0f : 0.f;
+            sMask[t] = mv;
         }
         // delta_row = sum_d dO[row,d] * O[row,d], L_row, for this thread's row in each query tile
         float delta[2] = {0.f, 0.f}, Lrow[2] = {0.f, 0.f};
@@ -361,15 +376,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                     unpack8(*reinterpret_cast<const bf16x8*>(o + c * 8), ov);
                     unpack8(*reinterpret_cast<const bf16x8*>(d + c * 8), dv);
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) acc = fmaf(ov[e], dv[e], acc);
+                    for (int x = 0; x < 8; ++x) acc = fmaf(ov[x], dv[x], acc);
                 }
                 delta[i] = acc;
                 Lrow[i] = p.lse[(long long)(b * p.nh + h) * p.S + q];
             }
         }
-        named_bar_sync(1, 128);
-        const uint32_t step = p.thresh16 ? *p.d_step : 0u;
-        const int chunks_per_row = p.S >> 3;
+        named_bar_sync(1, 256);
         const float sc = p.scale;
         uint32_t ph1 = 0;
         int blk = 0;
@@ -383,43 +396,40 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                 const long long grow = (long long)(b * p.nh + h) * p.S + q;
                 const float Ll = Lrow[i] * kLog2e, dl = delta[i];
 #pragma unroll 1
-                for (int c = 0; c < 4; ++c) {  // 32 keys per chunk: keys j*128 + c*32 ..
+                for (int c = 0; c < 2; ++c) {  // 32 keys per chunk
+                    const int kl = half * 64 + c * 32;   // key offset inside the 128-key block
+                    const int kc = j * 128 + kl;         // absolute first key
                     float s[32], dp[32];
-                    ptx::tmem_ld32(lane_addr + C_S + c * 32, s);
-                    ptx::tmem_ld32(lane_addr + C_DP + c * 32, dp);
+                    ptx::tmem_ld32(lane_addr + C_S + kl, s);
+                    ptx::tmem_ld32(lane_addr + C_DP + kl, dp);
                     ptx::tmem_ld_wait();
                     float pd[32];
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        const float pr = qvalid ? exp2f(fmaf(fmaf(s[e], sc, sMask[j * 128 + c * 32 + e]), kLog2e, -Ll)) : 0.f;
-                        s[e] = pr;
-                        pd[e] = pr;
+                    for (int x = 0; x < 32; ++x) {
+                        const float pr = qvalid ? exp2f(fmaf(fmaf(s[x], sc, sMask[kc + x]), kLog2e, -Ll)) : 0.f;
+                        s[x] = pr;
+                        pd[x] = pr;
                     }
                     if (p.thresh16) {
+                        uint32_t bits = 0xFFFFFFFFu;  // keep bits written by the forward kernel (same Philox stream)
+                        if (qvalid && kc < p.S) bits = p.keepbits[grow * (p.S >> 5) + (kc >> 5)];
 #pragma unroll
-                        for (int g8 = 0; g8 < 4; ++g8) {
-                            const int key0 = j * 128 + c * 32 + g8 * 8;
-                            if (key0 < p.S && qvalid) {
-                                const uint32_t keep = dropout_keep8(p.seed, p.site, step, (unsigned long long)grow * chunks_per_row + (key0 >> 3), p.thresh16);
-#pragma unroll
-                                for (int e = 0; e < 8; ++e) {
-                                    const bool kp = (keep >> e) & 1u;
-                                    pd[g8 * 8 + e] = kp ? pd[g8 * 8 + e] * p.inv_keep : 0.f;
-                                    dp[g8 * 8 + e] = kp ? dp[g8 * 8 + e] * p.inv_keep : 0.f;
-                                }
-                            }
+                        for (int x = 0; x < 32; ++x) {
+                            const bool kp = (bits >> x) & 1u;
+                            pd[x] = kp ? pd[x] * p.inv_keep : 0.f;
+                            dp[x] = kp ? dp[x] * p.inv_keep : 0.f;
                         }
                     }
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) dp[e] = s[e] * (dp[e] - dl) * sc;  // dS
-                    // keys [32c, 32c+32) of this half -> key group c/2, 16-byte chunks (c&1)*4.. of row `row`
-                    uint8_t* bp = sPd + (c >> 1) * 16384 + row * 128;
-                    uint8_t* bs = sDS + (c >> 1) * 16384 + row * 128;
+                    for (int x = 0; x < 32; ++x) dp[x] = s[x] * (dp[x] - dl) * sc;  // dS
+                    // 64 keys of this half = key group `half`; this chunk fills 16-byte chunks c*4 .. c*4+3 of row `row`
+                    uint8_t* bp = sPd + half * 16384 + row * 128;
+                    uint8_t* bs = sDS + half * 16384 + row * 128;
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int chunk = ((c & 1) * 4 + e) ^ (row & 7);
-                        *reinterpret_cast<bf16x8*>(bp + chunk * 16) = pack8(pd + 8 * e);
-                        *reinterpret_cast<bf16x8*>(bs + chunk * 16) = pack8(dp + 8 * e);
+                    for (int x = 0; x < 4; ++x) {
+                        const int chunk = (c * 4 + x) ^ (row & 7);
+                        *reinterpret_cast<bf16x8*>(bp + chunk * 16) = pack8(pd + 8 * x);
+                        *reinterpret_cast<bf16x8*>(bs + chunk * 16) = pack8(dp + 8 * x);
                     }
                 }
                 ptx::fence_proxy_async_smem();
@@ -431,27 +441,24 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                 if (last_i || last_j) {
                     ptx::mbar_wait(&bars[3], blk & 1);  // this block's MMAs (incl. the accumulations) have retired
                     ptx::tc_fence_after();
-                    uint8_t* stg = sPd + quad * 4096;   // Pd/dS are free again until the next arrive on bars[2]
                     auto drain = [&](uint32_t col, int slot, int row0) {
+                        float v[32];
+                        ptx::tmem_ld32(lane_addr + col + half * 32, v);
+                        ptx::tmem_ld_wait();
+                        uint8_t* stg = sPd + row * 128;  // [128 rows][128 B]; Pd/dS are free until the next arrive on bars[2]
 #pragma unroll
-                        for (int hh = 0; hh < 2; ++hh) {
-                            float v[32];
-                            ptx::tmem_ld32(lane_addr + col + hh * 32, v);
-                            ptx::tmem_ld_wait();
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const int chunk = (hh * 4 + e) ^ (lane & 7);
-                                *reinterpret_cast<bf16x8*>(stg + lane * 128 + chunk * 16) = pack8(v + 8 * e);
-                            }
+                        for (int x = 0; x < 4; ++x) {
+                            const int chunk = (half * 4 + x) ^ (row & 7);
+                            *reinterpret_cast<bf16x8*>(stg + chunk * 16) = pack8(v + 8 * x);
                         }
                         ptx::fence_proxy_async_smem();
-                        __syncwarp();
-                        if (lane == 0) {
-                            ptx::tma_store_4d(&tmDQKV, stg, 0, row0 + quad * 32, slot, b);
+                        named_bar_sync(1, 256);
+                        if (half == 0 && lane == 0) {
+                            ptx::tma_store_4d(&tmDQKV, sPd + quad * 4096, 0, row0 + quad * 32, slot, b);
                             ptx::tma_store_commit();
                             ptx::tma_store_wait_all();
                         }
-                        __syncwarp();
+                        named_bar_sync(1, 256);  // staging tile free again
                     };
                     if (last_i) {
                         drain(C_DK, p.nh + h, j * 128);
@@ -459,7 +466,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                     }
                     if (last_j) drain(i == 0 ? C_DQ0 : C_DQ1, h, i * 128);
                     ptx::tc_fence_before();
-                    named_bar_sync(1, 128);  // all four warps finished reading TMEM / staging before the next block reuses them
                 }
             }
         }
@@ -506,25 +512,26 @@ int head_map(CUtensorMap* m, const void* ptr, int B, int S, int slots, int box_r
 }
 
 AttnParams make_params(int B, int S, int nh, float p_drop, uint64_t seed, uint32_t site, const uint32_t* d_step,
-                       const int32_t* mask, float* lse) {
+                       const int32_t* mask, float* lse, uint32_t* keepbits) {
     AttnParams p;
     p.B = B; p.S = S; p.nh = nh;
     p.scale = 1.0f / sqrtf((float)DH);
     p.thresh16 = p_drop > 0.f ? (uint32_t)lrintf(p_drop * 65536.0f) : 0u;
     p.inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
-    p.seed = seed; p.site = site; p.d_step = d_step; p.mask = mask; p.lse = lse;
+    p.seed = seed; p.site = site; p.d_step = d_step; p.mask = mask; p.lse = lse; p.keepbits = keepbits;
     return p;
 }
 
 }  // namespace
 
-extern "C" int polus_attention_supported(int S, int dh) { return (dh == DH && S >= 8 && S <= 256 && S % 8 == 0) ? 1 : 0; }
+extern "C" int polus_attention_supported(int S, int dh) { return (dh == DH && S >= 32 && S <= 256 && S % 32 == 0) ? 1 : 0; }
+extern "C" size_t polus_attention_keepbits_words(int B, int S, int nh) { return (size_t)B * nh * S * (S / 32); }
 
 extern "C" int polus_attention_fwd(const polus_bf16_t* qkv, const int32_t* mask, int B, int S, int nh, int dh, float p_drop,
                                    uint64_t seed, uint32_t site, const uint32_t* d_step, polus_bf16_t* ctx, float* lse,
-                                   void* stream) {
-    POLUS_REQUIRE(polus_attention_supported(S, dh), "polus_attention_fwd: needs head_dim 64 and S <= 256, S %% 8 == 0 (got S=%d dh=%d)", S, dh);
-    POLUS_REQUIRE(p_drop == 0.f || d_step != nullptr, "polus_attention_fwd: dropout needs d_step");
+                                   uint32_t* keepbits, void* stream) {
+    POLUS_REQUIRE(polus_attention_supported(S, dh), "polus_attention_fwd: needs head_dim 64 and S <= 256, S %% 32 == 0 (got S=%d dh=%d)", S, dh);
+    POLUS_REQUIRE(p_drop == 0.f || (d_step != nullptr && keepbits != nullptr), "polus_attention_fwd: dropout needs d_step and keepbits");
     if (B == 0) return 0;
     CUtensorMap tq, to;
     int rc = head_map(&tq, qkv, B, S, 3 * nh, 128);
@@ -536,7 +543,7 @@ extern "C" int polus_attention_fwd(const polus_bf16_t* qkv, const int32_t* mask,
         POLUS_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
         set = true;
     }
-    AttnParams p = make_params(B, S, nh, p_drop, seed, site, d_step, mask, lse);
+    AttnParams p = make_params(B, S, nh, p_drop, seed, site, d_step, mask, lse, keepbits);
     const int q_tiles = (S + 127) / 128;
     attn_fwd_kernel<<<B * nh * q_tiles, FWD_THREADS, F_SMEM, (cudaStream_t)stream>>>(tq, to, p);
     g_launch_count++;
@@ -546,8 +553,10 @@ extern "C" int polus_attention_fwd(const polus_bf16_t* qkv, const int32_t* mask,
 
 extern "C" int polus_attention_bwd(const polus_bf16_t* qkv, const int32_t* mask, const polus_bf16_t* ctx,
                                    const polus_bf16_t* dctx, const float* lse, int B, int S, int nh, int dh, float p_drop,
-                                   uint64_t seed, uint32_t site, const uint32_t* d_step, polus_bf16_t* dqkv, void* stream) {
-    POLUS_REQUIRE(polus_attention_supported(S, dh), "polus_attention_bwd: needs head_dim 64 and S <= 256, S %% 8 == 0 (got S=%d dh=%d)", S, dh);
+                                   uint64_t seed, uint32_t site, const uint32_t* d_step, const uint32_t* keepbits,
+                                   polus_bf16_t* dqkv, void* stream) {
+    POLUS_REQUIRE(polus_attention_supported(S, dh), "polus_attention_bwd: needs head_dim 64 and S <= 256, S %% 32 == 0 (got S=%d dh=%d)", S, dh);
+    POLUS_REQUIRE(p_drop == 0.f || keepbits != nullptr, "polus_attention_bwd: dropout needs the forward's keepbits");
     if (B == 0) return 0;
     CUtensorMap tq, tdo, tdq;
     int rc = head_map(&tq, qkv, B, S, 3 * nh, 128);
@@ -561,7 +570,7 @@ extern "C" int polus_attention_bwd(const polus_bf16_t* qkv, const int32_t* mask,
         POLUS_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
         set = true;
     }
-    AttnParams p = make_params(B, S, nh, p_drop, seed, site, d_step, mask, const_cast<float*>(lse));
+    AttnParams p = make_params(B, S, nh, p_drop, seed, site, d_step, mask, const_cast<float*>(lse), const_cast<uint32_t*>(keepbits));
     attn_bwd_kernel<<<B * nh, BWD_THREADS, B_SMEM, (cudaStream_t)stream>>>(tq, tdo, tdq, (const bf16*)ctx, (const bf16*)dctx, p);
     g_launch_count++;
     POLUS_LAUNCH_CHECK();

@@ -527,15 +527,17 @@ def _attention_fused(qkv, mask, n_heads, p_drop):
     site = _next_site() if p_drop > 0 else 0
     seed = _rng_state["seed"]
     mptr = mask.ptr if mask is not None else None
+    keep = Tensor((int(_lib.call("polus_attention_keepbits_words", Bsz, S, n_heads)),), I32) if p_drop > 0 else None
+    kptr = keep.ptr if keep is not None else None
     _lib.call("polus_attention_fwd", qkv.ptr, mptr, Bsz, S, n_heads, dh, p_drop, seed, site, step_counter(), ctx.ptr,
-              lse.ptr, device.stream())
+              lse.ptr, kptr, device.stream())
     tape = _recording(qkv)
     if tape is not None:
         def backward(g):
             g = cast(g, BF16)
             dqkv = Tensor((Bsz, S, H3), BF16)
             _lib.call("polus_attention_bwd", qkv.ptr, mptr, ctx.ptr, g.ptr, lse.ptr, Bsz, S, n_heads, dh, p_drop, seed, site,
-                      step_counter(), dqkv.ptr, device.stream())
+                      step_counter(), kptr, dqkv.ptr, device.stream())
             return [dqkv]
         _record(tape, [qkv], ctx, backward)
     return ctx
