@@ -152,11 +152,13 @@ int polus_ln_res_fwd(polus_bf16_t* d_x_inout, const polus_bf16_t* d_res, const f
                      float* d_rstd, void* stream);
 /* d(y) = d_dy (+ d_dy2 when not NULL: a second contribution from the residual stream, summed in-kernel).
  * Writes d_dx (through dropout) and d_dres (may be NULL; may alias d_dx when p_drop == 0); dgamma/dbeta are
- * accumulated.  d_ws: workspace of polus_ln_ws_floats(H) floats. */
+ * accumulated; d_gbias_x (may be NULL) also receives the column sums of d_dx, i.e. the bias gradient of the Dense
+ * layer that produced x, saving that layer a separate reduction pass.  d_ws is unused (kept for ABI stability). */
 int polus_ln_res_bwd(const polus_bf16_t* d_dy, const polus_bf16_t* d_dy2, const polus_bf16_t* d_z,
                      const float* d_mean, const float* d_rstd, const float* d_gamma, int M, int H, float p_drop,
                      uint64_t seed, uint32_t site, const uint32_t* d_step, polus_bf16_t* d_dx,
-                     polus_bf16_t* d_dres, float* d_ggamma, float* d_gbeta, float* d_ws, void* stream);
+                     polus_bf16_t* d_dres, float* d_ggamma, float* d_gbeta, float* d_gbias_x, float* d_ws,
+                     void* stream);
 size_t polus_ln_ws_floats(int H);
 
 /* HF TFBertSelfAttention softmax: P = softmax(scores*scale + (1-mask)*-10000) (polus/models.py:

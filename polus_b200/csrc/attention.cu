@@ -226,7 +226,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         if (half == 0 && lane == 0) {
             ptx::tma_store_4d(&tmO, smem + quad * 4096, 0, q0 + quad * 32, h, b);  // rows >= S clipped
             ptx::tma_store_commit();
-            ptx::tma_store_wait_all();
+            ptx::tma_store_wait_read<0>();
         }
     }
     ptx::tc_fence_before();
@@ -359,7 +359,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
         {
             float mv = -INFINITY;
-            if (t < p.S) mv = p.mask ? (1.0f - (float)p.mask[(long long)b * p.S + t]) * -10000.0f : 0.f;
+            if (t < p.S) mv = p.mask ? (1.0f - (float)p.mask[(long long)b * p.S + t]) * (-10000.0f * kLog2e) : 0.f;
             sMask[t] = mv;
         }
         // delta_row = sum_d dO[row,d] * O[row,d], L_row, for this thread's row in each query tile
@@ -394,7 +394,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                 const int q = i * 128 + row;
                 const bool qvalid = q < p.S;
                 const long long grow = (long long)(b * p.nh + h) * p.S + q;
-                const float Ll = Lrow[i] * kLog2e, dl = delta[i];
+                const float Ll = qvalid ? Lrow[i] * kLog2e : INFINITY;  // rows beyond S: p = exp2(-inf) = 0
+                const float dl = delta[i];
+                const float scl = sc * kLog2e;
 #pragma unroll 1
                 for (int c = 0; c < 2; ++c) {  // 32 keys per chunk
                     const int kl = half * 64 + c * 32;   // key offset inside the 128-key block
@@ -403,25 +405,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                     ptx::tmem_ld32(lane_addr + C_S + kl, s);
                     ptx::tmem_ld32(lane_addr + C_DP + kl, dp);
                     ptx::tmem_ld_wait();
+                    uint32_t bits = 0xFFFFFFFFu;  // keep bits written by the forward kernel (same Philox stream)
+                    if (p.thresh16 && qvalid && kc < p.S) bits = p.keepbits[grow * (p.S >> 5) + (kc >> 5)];
                     float pd[32];
 #pragma unroll
                     for (int x = 0; x < 32; ++x) {
-                        const float pr = qvalid ? exp2f(fmaf(fmaf(s[x], sc, sMask[kc + x]), kLog2e, -Ll)) : 0.f;
-                        s[x] = pr;
-                        pd[x] = pr;
+                        const float pr = exp2f(fmaf(s[x], scl, sMask[kc + x]) - Ll);   // sMask holds mask * log2(e)
+                        const float m = ((bits >> x) & 1u) ? p.inv_keep : 0.f;         // dropout multiplier
+                        pd[x] = pr * m;                                                // dropped probability (for dV)
+                        dp[x] = (pr * sc) * fmaf(dp[x], m, -dl);                       // dS = P (dP - delta) / sqrt(dh)
                     }
-                    if (p.thresh16) {
-                        uint32_t bits = 0xFFFFFFFFu;  // keep bits written by the forward kernel (same Philox stream)
-                        if (qvalid && kc < p.S) bits = p.keepbits[grow * (p.S >> 5) + (kc >> 5)];
-#pragma unroll
-                        for (int x = 0; x < 32; ++x) {
-                            const bool kp = (bits >> x) & 1u;
-                            pd[x] = kp ? pd[x] * p.inv_keep : 0.f;
-                            dp[x] = kp ? dp[x] * p.inv_keep : 0.f;
-                        }
-                    }
-#pragma unroll
-                    for (int x = 0; x < 32; ++x) dp[x] = s[x] * (dp[x] - dl) * sc;  // dS
                     // 64 keys of this half = key group `half`; this chunk fills 16-byte chunks c*4 .. c*4+3 of row `row`
                     uint8_t* bp = sPd + half * 16384 + row * 128;
                     uint8_t* bs = sDS + half * 16384 + row * 128;
@@ -456,7 +449,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                         if (half == 0 && lane == 0) {
                             ptx::tma_store_4d(&tmDQKV, sPd + quad * 4096, 0, row0 + quad * 32, slot, b);
                             ptx::tma_store_commit();
-                            ptx::tma_store_wait_all();
+                            ptx::tma_store_wait_read<0>();
                         }
                         named_bar_sync(1, 256);  // staging tile free again
                     };

@@ -155,9 +155,18 @@ __device__ __forceinline__ float act_fwd(int act, float x) {
 __device__ __forceinline__ float act_grad(int act, float x) {
     switch (act) {
         case POLUS_ACT_GELU: {
-            float cdf = 0.5f * (1.0f + fast_erf(x * 0.70710678118654752f));
-            float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-            return cdf + x * pdf;
+            // Phi(x) + x phi(x); erf's exp(-u^2) with u = x/sqrt(2) IS exp(-x^2/2): one exponential for both terms
+            const float u = fabsf(x) * 0.70710678118654752f;
+            float t;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, u, 1.0f)));
+            float poly = fmaf(t, 1.061405429f, -1.453152027f);
+            poly = fmaf(t, poly, 1.421413741f);
+            poly = fmaf(t, poly, -0.284496736f);
+            poly = fmaf(t, poly, 0.254829592f);
+            const float ex = __expf(-u * u);
+            const float erf_abs = 1.0f - poly * t * ex;
+            const float cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
+            return fmaf(x, 0.3989422804014327f * ex, cdf);
         }
         case POLUS_ACT_RELU: return x > 0.0f ? 1.0f : 0.0f;
         case POLUS_ACT_SWISH: {

@@ -43,7 +43,9 @@ act_bwd_colsum_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, i
         float s = 0.f;
 #pragma unroll
         for (int w = 0; w < 8; ++w) s += red[w][c];
-        partial[(long long)blockIdx.y * N + blockIdx.x * 256 + c] = s;
+        // `partial` is the bias-gradient vector itself: one fp32 reduction per column per slab (<= 128 per address);
+        // replaces a workspace + second kernel (74 extra launches per step, profiles/r01_launch_summary_v3_fused_attn.txt)
+        atomicAdd(partial + blockIdx.x * 256 + c, s);
     }
 }
 
@@ -271,7 +273,6 @@ extern "C" int polus_act_bwd_colsum(const polus_bf16_t* dy, const polus_bf16_t* 
                                     polus_bf16_t* dz, float* gbias, float* ws, void* stream) {
     POLUS_REQUIRE(N > 0 && N % 8 == 0, "polus_act_bwd_colsum: N must be a multiple of 8 (got %d)", N);
     POLUS_REQUIRE(act == POLUS_ACT_NONE || z != nullptr, "polus_act_bwd_colsum: activation backward needs z");
-    POLUS_REQUIRE(gbias == nullptr || ws != nullptr, "polus_act_bwd_colsum: bias gradient needs a workspace");
     if (M == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     int slabs = cdiv(M, 64);
@@ -279,15 +280,10 @@ extern "C" int polus_act_bwd_colsum(const polus_bf16_t* dy, const polus_bf16_t* 
     const int rows_per_slab = cdiv(M, slabs);
     slabs = cdiv(M, rows_per_slab);
     dim3 grid(cdiv(N, 256), slabs);
-    act_bwd_colsum_kernel<<<grid, 256, 0, st>>>((const bf16*)dy, (const bf16*)z, M, N, act, (bf16*)dz,
-                                               gbias ? ws : nullptr, rows_per_slab);
+    (void)ws;
+    act_bwd_colsum_kernel<<<grid, 256, 0, st>>>((const bf16*)dy, (const bf16*)z, M, N, act, (bf16*)dz, gbias, rows_per_slab);
     g_launch_count++;
     POLUS_LAUNCH_CHECK();
-    if (gbias != nullptr) {
-        colsum_reduce_kernel<<<cdiv(N, 32), 256, 0, st>>>(ws, slabs, N, gbias, nullptr, N);
-        g_launch_count++;
-        POLUS_LAUNCH_CHECK();
-    }
     return 0;
 }
 

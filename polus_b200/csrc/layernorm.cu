@@ -111,30 +111,26 @@ ln_res_fwd_kernel(bf16* __restrict__ x, const bf16* __restrict__ res, const floa
 }
 
 // ------------------------------------------------------------------------------ backward
-// dz = rstd * (g - mean(g) - xhat * mean(g*xhat)), g = dy*gamma.  Writes dres = dz and dx = dropout'(dz);
-// per-CTA partial sums of dgamma = dy*xhat and dbeta = dy into ws[blockIdx.x][2][H].
+// dz = rstd * (g - mean(g) - xhat * mean(g*xhat)), g = dy*gamma.  Writes dres = dz and dx = dropout'(dz).
+// Per-warp register partials of dgamma = sum dy*xhat, dbeta = sum dy and (optionally) dbias = sum dx -- the bias
+// gradient of the Dense layer that produced x -- are reduced per CTA in shared memory and added to the
+// gradient arena with one fp32 atomic per column per CTA.
 template <int MAXC>
 __global__ void __launch_bounds__(kWarps * 32)
 ln_res_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, const bf16* __restrict__ z, const float* __restrict__ mean_in,
                   const float* __restrict__ rstd_in, const float* __restrict__ gamma, int M, int H, DropCfg dc,
                   const uint32_t* __restrict__ d_step, bf16* __restrict__ dx, bf16* __restrict__ dres,
-                  float* __restrict__ ws) {
-    extern __shared__ float red[];  // [kWarps][2][H] only used at the end
+                  float* __restrict__ ggamma, float* __restrict__ gbeta, float* __restrict__ gbias) {
+    extern __shared__ float red[];  // [kWarps][H]
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int chunks = H >> 3;
     const uint32_t step = dc.thresh16 ? *d_step : 0u;
-    float dg[MAXC][8], db[MAXC][8], gam[MAXC][8];
+    float dg[MAXC][8], db[MAXC][8], dxs[MAXC][8];
 #pragma unroll
-    for (int i = 0; i < MAXC; ++i) {
-        const int c = lane + 32 * i;
+    for (int i = 0; i < MAXC; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            dg[i][j] = 0.f;
-            db[i][j] = 0.f;
-            gam[i][j] = (c < chunks) ? __ldg(gamma + c * 8 + j) : 0.f;
-        }
-    }
+        for (int j = 0; j < 8; ++j) dg[i][j] = db[i][j] = dxs[i][j] = 0.f;
     for (int row = blockIdx.x * kWarps + warp; row < M; row += gridDim.x * kWarps) {
         const long long base = (long long)row * H;
         const float mean = mean_in[row], rstd = rstd_in[row];
@@ -153,10 +149,13 @@ ln_res_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, con
                     for (int j = 0; j < 8; ++j) dyv[j] += d2[j];
                 }
                 unpack8(ld_stream8(z + base + c * 8), zv);
+                const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c * 8));
+                const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c * 8) + 1);
+                const float gam[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     xh[i][j] = (zv[j] - mean) * rstd;
-                    g[i][j] = dyv[j] * gam[i][j];
+                    g[i][j] = dyv[j] * gam[j];
                     s1 += g[i][j];
                     s2 += g[i][j] * xh[i][j];
                     dg[i][j] += dyv[j] * xh[i][j];
@@ -180,18 +179,22 @@ ln_res_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, con
                     for (int j = 0; j < 8; ++j) dz[j] = ((keep >> j) & 1u) ? dz[j] * dc.inv_keep : 0.f;
                 }
                 *reinterpret_cast<bf16x8*>(dx + base + c * 8) = pack8(dz);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dxs[i][j] += dz[j];
             }
         }
     }
-    // CTA reduction of the parameter-gradient partials (dgamma, then dbeta: red is [kWarps][H])
+    // CTA reduction of the parameter-gradient partials, one quantity at a time (red is [kWarps][H])
 #pragma unroll
-    for (int which = 0; which < 2; ++which) {
+    for (int which = 0; which < 3; ++which) {
+        float* out = which == 0 ? ggamma : (which == 1 ? gbeta : gbias);
+        if (out == nullptr) continue;  // uniform
 #pragma unroll
         for (int i = 0; i < MAXC; ++i) {
             const int c = lane + 32 * i;
             if (c < chunks) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) red[warp * H + c * 8 + j] = which == 0 ? dg[i][j] : db[i][j];
+                for (int j = 0; j < 8; ++j) red[warp * H + c * 8 + j] = which == 0 ? dg[i][j] : (which == 1 ? db[i][j] : dxs[i][j]);
             }
         }
         __syncthreads();
@@ -199,7 +202,7 @@ ln_res_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, con
             float s = 0.f;
 #pragma unroll
             for (int w = 0; w < kWarps; ++w) s += red[w * H + idx];
-            ws[(long long)blockIdx.x * 2 * H + which * H + idx] = s;
+            atomicAdd(out + idx, s);
         }
         __syncthreads();
     }
@@ -289,7 +292,8 @@ template <int MAXC>
 __global__ void __launch_bounds__(kWarps * 32)
 embed_ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ z, const float* __restrict__ mean_in,
                     const float* __restrict__ rstd_in, const float* __restrict__ gamma, int M, int H, DropCfg dc,
-                    const uint32_t* __restrict__ d_step, float* __restrict__ dz_out, float* __restrict__ ws) {
+                    const uint32_t* __restrict__ d_step, float* __restrict__ dz_out, float* __restrict__ ggamma,
+                    float* __restrict__ gbeta) {
     extern __shared__ float red[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -340,6 +344,8 @@ embed_ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ z, co
     }
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
+        float* out = which == 0 ? ggamma : gbeta;
+        if (out == nullptr) continue;
 #pragma unroll
         for (int i = 0; i < MAXC; ++i) {
             const int c = lane + 32 * i;
@@ -353,7 +359,7 @@ embed_ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ z, co
             float s = 0.f;
 #pragma unroll
             for (int w = 0; w < kWarps; ++w) s += red[w * H + idx];
-            ws[(long long)blockIdx.x * 2 * H + which * H + idx] = s;
+            atomicAdd(out + idx, s);
         }
         __syncthreads();
     }
@@ -439,9 +445,10 @@ extern "C" int polus_ln_res_fwd(polus_bf16_t* x, const polus_bf16_t* res, const 
 extern "C" int polus_ln_res_bwd(const polus_bf16_t* dy, const polus_bf16_t* dy2, const polus_bf16_t* z, const float* mean,
                                 const float* rstd, const float* gamma, int M, int H, float p_drop, uint64_t seed,
                                 uint32_t site, const uint32_t* d_step, polus_bf16_t* dx, polus_bf16_t* dres,
-                                float* ggamma, float* gbeta, float* ws, void* stream) {
+                                float* ggamma, float* gbeta, float* gbias_x, float* ws, void* stream) {
     POLUS_REQUIRE(M >= 0 && H > 0 && H % 8 == 0 && H <= 4096, "polus_ln_res_bwd: H must be a multiple of 8 and <= 4096 (got %d)", H);
-    POLUS_REQUIRE(ws != nullptr && dx != nullptr, "polus_ln_res_bwd: workspace and dx required");
+    (void)ws;
+    POLUS_REQUIRE(dx != nullptr, "polus_ln_res_bwd: dx required");
     POLUS_REQUIRE(!(p_drop > 0.f && dres == dx), "polus_ln_res_bwd: dres may alias dx only without dropout");
     if (M == 0) return 0;
     DropCfg dc = make_drop(p_drop, seed, site);
@@ -452,15 +459,14 @@ extern "C" int polus_ln_res_bwd(const polus_bf16_t* dy, const polus_bf16_t* dy2,
     if (H <= 1024) {
         static bool set4 = false;
         if (!set4) { POLUS_CHECK_CUDA(cudaFuncSetAttribute(ln_res_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 1024 * 4)); set4 = true; }
-        ln_res_bwd_kernel<4><<<grid, kWarps * 32, smem, st>>>((const bf16*)dy, (const bf16*)dy2, (const bf16*)z, mean, rstd, gamma, M, H, dc, d_step, (bf16*)dx, (bf16*)dres, ws);
+        ln_res_bwd_kernel<4><<<grid, kWarps * 32, smem, st>>>((const bf16*)dy, (const bf16*)dy2, (const bf16*)z, mean, rstd, gamma, M, H, dc, d_step, (bf16*)dx, (bf16*)dres, ggamma, gbeta, gbias_x);
     } else {
         static bool set16 = false;
         if (!set16) { POLUS_CHECK_CUDA(cudaFuncSetAttribute(ln_res_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4096 * 4)); set16 = true; }
-        ln_res_bwd_kernel<16><<<grid, kWarps * 32, smem, st>>>((const bf16*)dy, (const bf16*)dy2, (const bf16*)z, mean, rstd, gamma, M, H, dc, d_step, (bf16*)dx, (bf16*)dres, ws);
+        ln_res_bwd_kernel<16><<<grid, kWarps * 32, smem, st>>>((const bf16*)dy, (const bf16*)dy2, (const bf16*)z, mean, rstd, gamma, M, H, dc, d_step, (bf16*)dx, (bf16*)dres, ggamma, gbeta, gbias_x);
     }
     g_launch_count++;
     POLUS_LAUNCH_CHECK();
-    { int rc_ = polus_launch_colsum_reduce(ws, grid, 2 * H, ggamma, gbeta, H, st); if (rc_) return rc_; }
     return 0;
 }
 
@@ -499,22 +505,20 @@ extern "C" int polus_embed_ln_bwd(const polus_bf16_t* dy, const float* z, const 
     DropCfg dc = make_drop(p_drop, seed, site);
     cudaStream_t st = (cudaStream_t)stream;
     float* dz = ws;
-    float* partial = ws + (size_t)M * H;
     int grid = grid_for_rows(M);
     if (grid > kBwdBlocks) grid = kBwdBlocks;
     const size_t smem = (size_t)kWarps * H * sizeof(float);
     if (H <= 1024) {
         static bool set4 = false;
         if (!set4) { POLUS_CHECK_CUDA(cudaFuncSetAttribute(embed_ln_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 1024 * 4)); set4 = true; }
-        embed_ln_bwd_kernel<4><<<grid, kWarps * 32, smem, st>>>((const bf16*)dy, z, mean, rstd, gamma, M, H, dc, d_step, dz, partial);
+        embed_ln_bwd_kernel<4><<<grid, kWarps * 32, smem, st>>>((const bf16*)dy, z, mean, rstd, gamma, M, H, dc, d_step, dz, ggamma, gbeta);
     } else {
         static bool set16 = false;
         if (!set16) { POLUS_CHECK_CUDA(cudaFuncSetAttribute(embed_ln_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4096 * 4)); set16 = true; }
-        embed_ln_bwd_kernel<16><<<grid, kWarps * 32, smem, st>>>((const bf16*)dy, z, mean, rstd, gamma, M, H, dc, d_step, dz, partial);
+        embed_ln_bwd_kernel<16><<<grid, kWarps * 32, smem, st>>>((const bf16*)dy, z, mean, rstd, gamma, M, H, dc, d_step, dz, ggamma, gbeta);
     }
     g_launch_count++;
     POLUS_LAUNCH_CHECK();
-    { int rc_ = polus_launch_colsum_reduce(partial, grid, 2 * H, ggamma, gbeta, H, st); if (rc_) return rc_; }
     embed_scatter_kernel<<<S, 192, 0, st>>>(dz, ids, tt, B, S, H, vocab, n_types, gword, gpos, gtype);
     g_launch_count++;
     POLUS_LAUNCH_CHECK();

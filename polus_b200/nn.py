@@ -306,11 +306,12 @@ class BertLayer(Layer):
         ph = c.hidden_dropout_prob if training else 0.0
         qkv = ops.linear(x, self.Wqkv, self.bqkv)
         ctx = ops.attention(qkv, attention_mask, c.num_attention_heads, pa)
-        ao = ops.linear(ctx, self.Wo, self.bo)
-        h1 = ops.layernorm_residual(ao, x, self.ln1_g, self.ln1_b, c.layer_norm_eps, ph)
+        # the two Dense layers feeding a LayerNorm leave their bias gradient to the LayerNorm backward kernel
+        ao = ops.linear(ctx, self.Wo, self.bo, defer_bias_grad=True)
+        h1 = ops.layernorm_residual(ao, x, self.ln1_g, self.ln1_b, c.layer_norm_eps, ph, x_bias=self.bo)
         a = ops.linear(h1, self.W1, self.b1, "gelu")
-        o = ops.linear(a, self.W2, self.b2)
-        y = ops.layernorm_residual(o, h1, self.ln2_g, self.ln2_b, c.layer_norm_eps, ph)
+        o = ops.linear(a, self.W2, self.b2, defer_bias_grad=True)
+        y = ops.layernorm_residual(o, h1, self.ln2_g, self.ln2_b, c.layer_norm_eps, ph, x_bias=self.b2)
         return (y,)
 
     # Keras/HF variable order: query k,b; key k,b; value k,b; attn-out k,b; LN g,b; inter k,b; out k,b; LN g,b

@@ -276,7 +276,7 @@ def _act_code(act):
     return _lib.ACT[act]
 
 
-def linear(x, W, b=None, activation=None, out_dtype=None):
+def linear(x, W, b=None, activation=None, out_dtype=None, defer_bias_grad=False):
     """y = act(x @ W + b) with W in Keras layout [in, out] (tf.keras.layers.Dense).
 
     bf16 operands with in/out multiples of 8 run on the tcgen05 GEMM; anything else (the K-tag
@@ -299,11 +299,11 @@ def linear(x, W, b=None, activation=None, out_dtype=None):
                 g = cast(g, BF16)
                 need_dz = act != 0
                 dz = Tensor(g.shape, BF16) if need_dz else g
-                ws = Tensor((int(_lib.call("polus_colsum_ws_floats", N)),), F32) if b is not None else None
-                if need_dz or b is not None:
+                # defer_bias_grad: the consumer (layernorm_residual with x_bias=b) already added colsum(g) to b.grad
+                want_bias = b is not None and not (defer_bias_grad and act == 0)
+                if need_dz or want_bias:
                     _lib.call("polus_act_bwd_colsum", g.ptr, z.ptr if z is not None else None, M, N, act,
-                              dz.ptr if need_dz else None, b.grad.ptr if b is not None else None,
-                              ws.ptr if ws is not None else None, device.stream())
+                              dz.ptr if need_dz else None, b.grad.ptr if want_bias else None, None, device.stream())
                 # dW[K,N] += x^T dz : A = x (MN-major over K), B = dz (MN-major over N), reduce over M
                 _gemm(K, N, M, _operand(xb.ptr, K, True, BF16), _operand(dz.ptr, N, True, BF16),
                       W.grad.ptr, N, F32, accumulate=1, split_k=0)
@@ -416,8 +416,10 @@ def embed_layernorm(ids, token_type_ids, word, pos, type_, gamma, beta, eps=1e-1
     return y
 
 
-def layernorm_residual(x, res, gamma, beta, eps=1e-12, p_drop=0.0):
-    """y = LN(dropout(x) + res)  (HF TFBertSelfOutput / TFBertOutput).  x is consumed (overwritten by z)."""
+def layernorm_residual(x, res, gamma, beta, eps=1e-12, p_drop=0.0, x_bias=None):
+    """y = LN(dropout(x) + res)  (HF TFBertSelfOutput / TFBertOutput).  x is consumed (overwritten by z).
+    x_bias: bias Param of the Dense layer that produced x (called with defer_bias_grad=True): its gradient,
+    colsum(d x), is accumulated by this op's backward kernel instead of a separate pass."""
     H = x.shape[-1]
     M = x.size // H
     x = cast(x, BF16)
@@ -446,10 +448,10 @@ def layernorm_residual(x, res, gamma, beta, eps=1e-12, p_drop=0.0):
                 dres = Tensor(x.shape, BF16)
             else:
                 dres = dx  # identical values: write once
-            ws = Tensor((int(_lib.call("polus_ln_ws_floats", H)),), F32)
             _lib.call("polus_ln_res_bwd", g.ptr, g2.ptr if g2 is not None else None, z.ptr, mean.ptr, rstd.ptr, gamma.ptr,
                       M, H, p_drop, seed, site, step_counter(), dx.ptr, dres.ptr if dres is not None else None,
-                      gamma.grad.ptr, beta.grad.ptr, ws.ptr, device.stream())
+                      gamma.grad.ptr, beta.grad.ptr, x_bias.grad.ptr if x_bias is not None else None, None,
+                      device.stream())
             return [dx, dres, None, None]
         backward.pair_ok = True
         _record(tape, [x, res, gamma, beta], y, backward)
