@@ -20,19 +20,36 @@ act_bwd_colsum_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, i
     const int r1 = min(M, r0 + rows_per_slab);
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (col < N) {
-        for (int r = r0 + warp; r < r1; r += 8) {
-            const long long off = (long long)r * N + col;
-            float g[8];
-            unpack8(ld_stream8(dy + off), g);
-            if (act != POLUS_ACT_NONE) {
-                float zv[8];
-                unpack8(ld_stream8(z + off), zv);
+        // 4 rows per iteration: all loads are issued before the (MUFU-heavy) activation-gradient math
+        constexpr int U = 4;
+        for (int r = r0 + warp; r < r1; r += 8 * U) {
+            bf16x8 gq[U], zq[U];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) g[j] *= act_grad(act, zv[j]);
+            for (int u = 0; u < U; ++u) {
+                const int rr = r + 8 * u;
+                if (rr < r1) {
+                    const long long off = (long long)rr * N + col;
+                    gq[u] = ld_stream8(dy + off);
+                    if (act != POLUS_ACT_NONE) zq[u] = ld_stream8(z + off);
+                }
             }
-            if (dz != nullptr) *reinterpret_cast<bf16x8*>(dz + off) = pack8(g);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] += g[j];
+            for (int u = 0; u < U; ++u) {
+                const int rr = r + 8 * u;
+                if (rr < r1) {
+                    float g[8];
+                    unpack8(gq[u], g);
+                    if (act != POLUS_ACT_NONE) {
+                        float zv[8];
+                        unpack8(zq[u], zv);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) g[j] *= act_grad(act, zv[j]);
+                    }
+                    if (dz != nullptr) *reinterpret_cast<bf16x8*>(dz + (long long)rr * N + col) = pack8(g);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] += g[j];
+                }
+            }
         }
     }
 #pragma unroll

@@ -35,8 +35,11 @@ inline DropCfg make_drop(float p, uint64_t seed, uint32_t site) {
 }
 
 // ------------------------------------------------------------------------------ forward
-template <int MAXC>
-__global__ void __launch_bounds__(kWarps * 32)
+// NC = 16-byte chunks per lane (H <= 256*NC).  All global loads of a row are issued before any arithmetic and the
+// kernel is register-lean (4-warp CTAs, 8 CTAs/SM) because it is latency-bound: ncu showed 13 % of DRAM peak with
+// 20 resident warps and "long scoreboard" as the dominant stall (profiles/r01_ncu_full_summary_v1.txt).
+template <int NC>
+__global__ void __launch_bounds__(128, NC <= 3 ? 8 : (NC == 4 ? 6 : 1))
 ln_res_fwd_kernel(bf16* __restrict__ x, const bf16* __restrict__ res, const float* __restrict__ gamma,
                   const float* __restrict__ beta, int M, int H, float eps, DropCfg dc,
                   const uint32_t* __restrict__ d_step, bf16* __restrict__ y, float* __restrict__ mean_out,
@@ -45,39 +48,44 @@ ln_res_fwd_kernel(bf16* __restrict__ x, const bf16* __restrict__ res, const floa
     const int warp = threadIdx.x >> 5;
     const int chunks = H >> 3;
     const uint32_t step = dc.thresh16 ? *d_step : 0u;
-    for (int row = blockIdx.x * kWarps + warp; row < M; row += gridDim.x * kWarps) {
-        float v[MAXC][8];
-        float sum = 0.f;
+    for (int row = blockIdx.x * 4 + warp; row < M; row += gridDim.x * 4) {
         const long long base = (long long)row * H;
+        bf16x8 xr[NC], rr[NC];
 #pragma unroll
-        for (int i = 0; i < MAXC; ++i) {
+        for (int i = 0; i < NC; ++i) {
             const int c = lane + 32 * i;
             if (c < chunks) {
-                float xv[8];
-                unpack8(*reinterpret_cast<const bf16x8*>(x + base + c * 8), xv);
+                xr[i] = ld_stream8(x + base + c * 8);
+                if (res != nullptr) rr[i] = *reinterpret_cast<const bf16x8*>(res + base + c * 8);
+            }
+        }
+        float v[NC][8];
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            const int c = lane + 32 * i;
+            if (c < chunks) {
+                unpack8(xr[i], v[i]);
                 if (dc.thresh16) {
                     const uint32_t keep = dropout_keep8(dc.seed, dc.site, step, (unsigned long long)row * chunks + c, dc.thresh16);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) xv[j] = ((keep >> j) & 1u) ? xv[j] * dc.inv_keep : 0.f;
+                    for (int j = 0; j < 8; ++j) v[i][j] = ((keep >> j) & 1u) ? v[i][j] * dc.inv_keep : 0.f;
                 }
                 if (res != nullptr) {
                     float rv[8];
-                    unpack8(*reinterpret_cast<const bf16x8*>(res + base + c * 8), rv);
+                    unpack8(rr[i], rv);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) xv[j] += rv[j];
+                    for (int j = 0; j < 8; ++j) v[i][j] += rv[j];
                 }
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    v[i][j] = xv[j];
-                    sum += xv[j];
-                }
-                *reinterpret_cast<bf16x8*>(x + base + c * 8) = pack8(xv);  // z, kept for backward
+                for (int j = 0; j < 8; ++j) sum += v[i][j];
+                *reinterpret_cast<bf16x8*>(x + base + c * 8) = pack8(v[i]);  // z, kept for backward
             }
         }
         const float mean = warp_sum(sum) / (float)H;
         float sq = 0.f;
 #pragma unroll
-        for (int i = 0; i < MAXC; ++i) {
+        for (int i = 0; i < NC; ++i) {
             if (lane + 32 * i < chunks) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -92,7 +100,7 @@ ln_res_fwd_kernel(bf16* __restrict__ x, const bf16* __restrict__ res, const floa
             rstd_out[row] = rstd;
         }
 #pragma unroll
-        for (int i = 0; i < MAXC; ++i) {
+        for (int i = 0; i < NC; ++i) {
             const int c = lane + 32 * i;
             if (c < chunks) {
                 float o[8];
@@ -112,11 +120,12 @@ ln_res_fwd_kernel(bf16* __restrict__ x, const bf16* __restrict__ res, const floa
 
 // ------------------------------------------------------------------------------ backward
 // dz = rstd * (g - mean(g) - xhat * mean(g*xhat)), g = dy*gamma.  Writes dres = dz and dx = dropout'(dz).
-// Per-warp register partials of dgamma = sum dy*xhat, dbeta = sum dy and (optionally) dbias = sum dx -- the bias
-// gradient of the Dense layer that produced x -- are reduced per CTA in shared memory and added to the
-// gradient arena with one fp32 atomic per column per CTA.
-template <int MAXC>
-__global__ void __launch_bounds__(kWarps * 32)
+// dy and z stay PACKED (bf16) in registers between the two passes (xhat and g are recomputed), which keeps the
+// kernel at <= 128 registers => two 8-warp CTAs per SM.  Per-warp register partials of dgamma = sum dy*xhat,
+// dbeta = sum dy and (optionally) dbias = sum dx -- the bias gradient of the Dense layer that produced x -- are
+// reduced per CTA in shared memory and added to the gradient arena with one fp32 atomic per column per CTA.
+template <int NC>
+__global__ void __launch_bounds__(kWarps * 32, NC <= 4 ? 2 : 1)
 ln_res_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, const bf16* __restrict__ z, const float* __restrict__ mean_in,
                   const float* __restrict__ rstd_in, const float* __restrict__ gamma, int M, int H, DropCfg dc,
                   const uint32_t* __restrict__ d_step, bf16* __restrict__ dx, bf16* __restrict__ dres,
@@ -126,39 +135,55 @@ ln_res_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, con
     const int warp = threadIdx.x >> 5;
     const int chunks = H >> 3;
     const uint32_t step = dc.thresh16 ? *d_step : 0u;
-    float dg[MAXC][8], db[MAXC][8], dxs[MAXC][8];
+    float dg[NC][8], db[NC][8], dxs[NC][8];
 #pragma unroll
-    for (int i = 0; i < MAXC; ++i)
+    for (int i = 0; i < NC; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) dg[i][j] = db[i][j] = dxs[i][j] = 0.f;
     for (int row = blockIdx.x * kWarps + warp; row < M; row += gridDim.x * kWarps) {
         const long long base = (long long)row * H;
+        bf16x8 dyr[NC], zr[NC];
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            const int c = lane + 32 * i;
+            if (c < chunks) {
+                dyr[i] = ld_stream8(dy + base + c * 8);
+                zr[i] = ld_stream8(z + base + c * 8);
+            }
+        }
+        if (dy2 != nullptr) {  // second contribution to d(y) (residual stream): summed here, no add kernel
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                const int c = lane + 32 * i;
+                if (c < chunks) {
+                    float a[8], b2[8];
+                    unpack8(dyr[i], a);
+                    unpack8(ld_stream8(dy2 + base + c * 8), b2);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) a[j] += b2[j];
+                    dyr[i] = pack8(a);  // bf16 sum, as the separate add kernel produced
+                }
+            }
+        }
         const float mean = mean_in[row], rstd = rstd_in[row];
-        float g[MAXC][8], xh[MAXC][8];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int i = 0; i < MAXC; ++i) {
+        for (int i = 0; i < NC; ++i) {
             const int c = lane + 32 * i;
             if (c < chunks) {
                 float dyv[8], zv[8];
-                unpack8(ld_stream8(dy + base + c * 8), dyv);
-                if (dy2 != nullptr) {  // second contribution to d(y) (residual stream): summed here, no add kernel
-                    float d2[8];
-                    unpack8(ld_stream8(dy2 + base + c * 8), d2);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) dyv[j] += d2[j];
-                }
-                unpack8(ld_stream8(z + base + c * 8), zv);
+                unpack8(dyr[i], dyv);
+                unpack8(zr[i], zv);
                 const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c * 8));
                 const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c * 8) + 1);
                 const float gam[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    xh[i][j] = (zv[j] - mean) * rstd;
-                    g[i][j] = dyv[j] * gam[j];
-                    s1 += g[i][j];
-                    s2 += g[i][j] * xh[i][j];
-                    dg[i][j] += dyv[j] * xh[i][j];
+                    const float xh = (zv[j] - mean) * rstd;
+                    const float g = dyv[j] * gam[j];
+                    s1 += g;
+                    s2 += g * xh;
+                    dg[i][j] += dyv[j] * xh;
                     db[i][j] += dyv[j];
                 }
             }
@@ -166,12 +191,20 @@ ln_res_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, con
         s1 = warp_sum(s1) / (float)H;
         s2 = warp_sum(s2) / (float)H;
 #pragma unroll
-        for (int i = 0; i < MAXC; ++i) {
+        for (int i = 0; i < NC; ++i) {
             const int c = lane + 32 * i;
             if (c < chunks) {
-                float dz[8];
+                float dyv[8], zv[8], dz[8];
+                unpack8(dyr[i], dyv);
+                unpack8(zr[i], zv);
+                const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c * 8));
+                const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c * 8) + 1);
+                const float gam[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-                for (int j = 0; j < 8; ++j) dz[j] = rstd * (g[i][j] - s1 - xh[i][j] * s2);
+                for (int j = 0; j < 8; ++j) {
+                    const float xh = (zv[j] - mean) * rstd;
+                    dz[j] = rstd * (dyv[j] * gam[j] - s1 - xh * s2);
+                }
                 if (dres != nullptr && dres != dx) *reinterpret_cast<bf16x8*>(dres + base + c * 8) = pack8(dz);
                 if (dc.thresh16) {
                     const uint32_t keep = dropout_keep8(dc.seed, dc.site, step, (unsigned long long)row * chunks + c, dc.thresh16);
@@ -179,8 +212,10 @@ ln_res_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, con
                     for (int j = 0; j < 8; ++j) dz[j] = ((keep >> j) & 1u) ? dz[j] * dc.inv_keep : 0.f;
                 }
                 *reinterpret_cast<bf16x8*>(dx + base + c * 8) = pack8(dz);
+                if (gbias != nullptr) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) dxs[i][j] += dz[j];
+                    for (int j = 0; j < 8; ++j) dxs[i][j] += dz[j];
+                }
             }
         }
     }
@@ -190,7 +225,7 @@ ln_res_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, con
         float* out = which == 0 ? ggamma : (which == 1 ? gbeta : gbias);
         if (out == nullptr) continue;  // uniform
 #pragma unroll
-        for (int i = 0; i < MAXC; ++i) {
+        for (int i = 0; i < NC; ++i) {
             const int c = lane + 32 * i;
             if (c < chunks) {
 #pragma unroll
@@ -433,10 +468,13 @@ extern "C" int polus_ln_res_fwd(polus_bf16_t* x, const polus_bf16_t* res, const 
     if (M == 0) return 0;
     DropCfg dc = make_drop(p_drop, seed, site);
     cudaStream_t st = (cudaStream_t)stream;
-    const int grid = grid_for_rows(M);
-    DISPATCH_MAXC(H,
-        (ln_res_fwd_kernel<4><<<grid, kWarps * 32, 0, st>>>((bf16*)x, (const bf16*)res, gamma, beta, M, H, eps, dc, d_step, (bf16*)y, mean, rstd)),
-        (ln_res_fwd_kernel<16><<<grid, kWarps * 32, 0, st>>>((bf16*)x, (const bf16*)res, gamma, beta, M, H, eps, dc, d_step, (bf16*)y, mean, rstd)));
+    int grid = cdiv(M, 4);
+    const int cap = polus_num_sms() * 16;
+    if (grid > cap) grid = cap;
+    const int nc = cdiv(H, 256);
+#define LN_FWD(NC_) ln_res_fwd_kernel<NC_><<<grid, 128, 0, st>>>((bf16*)x, (const bf16*)res, gamma, beta, M, H, eps, dc, d_step, (bf16*)y, mean, rstd)
+    if (nc <= 1) LN_FWD(1); else if (nc == 2) LN_FWD(2); else if (nc == 3) LN_FWD(3); else if (nc == 4) LN_FWD(4); else LN_FWD(16);
+#undef LN_FWD
     g_launch_count++;
     POLUS_LAUNCH_CHECK();
     return 0;
@@ -456,15 +494,15 @@ extern "C" int polus_ln_res_bwd(const polus_bf16_t* dy, const polus_bf16_t* dy2,
     int grid = grid_for_rows(M);
     if (grid > kBwdBlocks) grid = kBwdBlocks;
     const size_t smem = (size_t)kWarps * H * sizeof(float);
-    if (H <= 1024) {
-        static bool set4 = false;
-        if (!set4) { POLUS_CHECK_CUDA(cudaFuncSetAttribute(ln_res_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 1024 * 4)); set4 = true; }
-        ln_res_bwd_kernel<4><<<grid, kWarps * 32, smem, st>>>((const bf16*)dy, (const bf16*)dy2, (const bf16*)z, mean, rstd, gamma, M, H, dc, d_step, (bf16*)dx, (bf16*)dres, ggamma, gbeta, gbias_x);
-    } else {
-        static bool set16 = false;
-        if (!set16) { POLUS_CHECK_CUDA(cudaFuncSetAttribute(ln_res_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4096 * 4)); set16 = true; }
-        ln_res_bwd_kernel<16><<<grid, kWarps * 32, smem, st>>>((const bf16*)dy, (const bf16*)dy2, (const bf16*)z, mean, rstd, gamma, M, H, dc, d_step, (bf16*)dx, (bf16*)dres, ggamma, gbeta, gbias_x);
+    const int nc = cdiv(H, 256);
+#define LN_BWD(NC_)                                                                                                            \
+    {                                                                                                                          \
+        if (smem > 48 * 1024) POLUS_CHECK_CUDA(cudaFuncSetAttribute(ln_res_bwd_kernel<NC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        ln_res_bwd_kernel<NC_><<<grid, kWarps * 32, smem, st>>>((const bf16*)dy, (const bf16*)dy2, (const bf16*)z, mean, rstd, gamma, M, H, dc, \
+                                                               d_step, (bf16*)dx, (bf16*)dres, ggamma, gbeta, gbias_x);        \
     }
+    if (nc <= 1) LN_BWD(1) else if (nc == 2) LN_BWD(2) else if (nc == 3) LN_BWD(3) else if (nc == 4) LN_BWD(4) else LN_BWD(16)
+#undef LN_BWD
     g_launch_count++;
     POLUS_LAUNCH_CHECK();
     return 0;
