@@ -362,25 +362,50 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             if (t < p.S) mv = p.mask ? (1.0f - (float)p.mask[(long long)b * p.S + t]) * (-10000.0f * kLog2e) : 0.f;
             sMask[t] = mv;
         }
-        // delta_row = sum_d dO[row,d] * O[row,d], L_row, for this thread's row in each query tile
-        float delta[2] = {0.f, 0.f}, Lrow[2] = {0.f, 0.f};
-        for (int i = 0; i < n_qt; ++i) {
-            const int q = i * 128 + row;
-            if (q < p.S) {
-                const bf16* o = ctx + ((long long)b * p.S + q) * H + h * DH;
-                const bf16* d = dctx + ((long long)b * p.S + q) * H + h * DH;
-                float acc = 0.f;
+        // delta_row = sum_d dO[row,d] * O[row,d] and L_row for this thread's row in each query tile.  The pair of
+        // threads sharing a row splits the 64 columns; explicit 128-bit loads, all issued before the arithmetic
+        // (scalar 4-byte loads here were the top stall of v1: profiles/r01_ncu_attention_bwd_v2.txt).
+        float delta0 = 0.f, delta1 = 0.f, L0 = 0.f, L1 = 0.f;
+        {
+            bf16x8 ov[2][4], dv[2][4];
+            bool ok[2];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    float ov[8], dv[8];
-                    unpack8(*reinterpret_cast<const bf16x8*>(o + c * 8), ov);
-                    unpack8(*reinterpret_cast<const bf16x8*>(d + c * 8), dv);
+            for (int i = 0; i < 2; ++i) {
+                const int q = i * 128 + row;
+                ok[i] = (i < n_qt) && (q < p.S);
+                if (ok[i]) {
+                    const bf16* o = ctx + ((long long)b * p.S + q) * H + h * DH + half * 32;
+                    const bf16* d = dctx + ((long long)b * p.S + q) * H + h * DH + half * 32;
 #pragma unroll
-                    for (int x = 0; x < 8; ++x) acc = fmaf(ov[x], dv[x], acc);
+                    for (int c = 0; c < 4; ++c) {
+                        ov[i][c] = ld_stream8(o + c * 8);
+                        dv[i][c] = ld_stream8(d + c * 8);
+                    }
                 }
-                delta[i] = acc;
-                Lrow[i] = p.lse[(long long)(b * p.nh + h) * p.S + q];
             }
+            float part[2] = {0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                if (ok[i]) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        float a[8], d8[8];
+                        unpack8(ov[i][c], a);
+                        unpack8(dv[i][c], d8);
+#pragma unroll
+                        for (int x = 0; x < 8; ++x) part[i] = fmaf(a[x], d8[x], part[i]);
+                    }
+                }
+            }
+            // exchange the two halves of each row through shared memory (sPd is free until the first block)
+            float* ex = reinterpret_cast<float*>(sPd);
+            ex[(half * 2 + 0) * 128 + row] = part[0];
+            ex[(half * 2 + 1) * 128 + row] = part[1];
+            named_bar_sync(1, 256);
+            delta0 = part[0] + ex[((half ^ 1) * 2 + 0) * 128 + row];
+            delta1 = part[1] + ex[((half ^ 1) * 2 + 1) * 128 + row];
+            if (ok[0]) L0 = p.lse[(long long)(b * p.nh + h) * p.S + row];
+            if (ok[1]) L1 = p.lse[(long long)(b * p.nh + h) * p.S + 128 + row];
         }
         named_bar_sync(1, 256);
         const float sc = p.scale;
@@ -394,8 +419,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                 const int q = i * 128 + row;
                 const bool qvalid = q < p.S;
                 const long long grow = (long long)(b * p.nh + h) * p.S + q;
-                const float Ll = qvalid ? Lrow[i] * kLog2e : INFINITY;  // rows beyond S: p = exp2(-inf) = 0
-                const float dl = delta[i];
+                const float Ll = qvalid ? (i == 0 ? L0 : L1) * kLog2e : INFINITY;  // rows beyond S: p = exp2(-inf) = 0
+                const float dl = i == 0 ? delta0 : delta1;
                 const float scl = sc * kLog2e;
 #pragma unroll 1
                 for (int c = 0; c < 2; ++c) {  // 32 keys per chunk

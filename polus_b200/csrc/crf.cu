@@ -27,6 +27,17 @@ namespace {
 //   gamma_t[j]  = alpha-hat_t[j] beta-tilde_t[j] / g_t,                g_t = sum_j alpha-hat_t[j] beta-tilde_t[j]
 //   xi_t[i][j]  = alpha-hat_t[i] E[i][j] w_{t+1}[j] / (d_t g_t)        (pair marginal of t -> t+1)
 // Shared memory: E [K][K], A [K][K], G [K][K], ah [T][K], w [T][K], bt [T][K], d [T].
+// reductions over the first kp lanes only (kp = power of two >= K): log2(kp) shuffles instead of 5 on the
+// sequential critical path (K = 4 tags => 2)
+__device__ __forceinline__ float kmax(float v, int kp) {
+    for (int o = kp >> 1; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float ksum(float v, int kp) {
+    for (int o = kp >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
 __global__ void __launch_bounds__(64)
 crf_nll_kernel(const float* __restrict__ emis, const int32_t* __restrict__ tags, const int32_t* __restrict__ lens,
                const float* __restrict__ trans, const float* __restrict__ weights, int B, int T, int K,
@@ -64,6 +75,8 @@ crf_nll_kernel(const float* __restrict__ emis, const int32_t* __restrict__ tags,
     const int32_t* y = tags + (long long)b * T;
     float* g = gemis + (long long)b * T * K;
     const bool act = lane < K;
+    int kp = 1;
+    while (kp < K) kp <<= 1;
 
     if (len == 0) {
         for (int i = tid; i < T * K; i += 64) g[i] = 0.f;
@@ -73,9 +86,9 @@ crf_nll_kernel(const float* __restrict__ emis, const int32_t* __restrict__ tags,
     if (warp == 0) {
         // ---------------- forward recursion + gold path score
         float xv = act ? x[lane] : -INFINITY;
-        float m = warp_max(xv);
+        float m = kmax(xv, kp);
         float u = act ? expf(xv - m) : 0.f;
-        float c = warp_sum(u);
+        float c = ksum(u, kp);
         float ah = u / c;
         float logZ = m + logf(c);
         if (act) sAh[lane] = ah;
@@ -83,9 +96,9 @@ crf_nll_kernel(const float* __restrict__ emis, const int32_t* __restrict__ tags,
             xv = act ? x[t * K + lane] : -INFINITY;  // issued early: independent of the recurrence
             float s = 0.f;
             for (int i = 0; i < K; ++i) s = fmaf(__shfl_sync(0xffffffffu, ah, i), act ? sE[i * K + lane] : 0.f, s);
-            m = warp_max(xv);
+            m = kmax(xv, kp);
             u = act ? s * expf(xv - m) : 0.f;
-            c = warp_sum(u);
+            c = ksum(u, kp);
             ah = u / c;
             logZ += m + logf(c) + amax;
             if (act) sAh[t * K + lane] = ah;
@@ -106,7 +119,7 @@ crf_nll_kernel(const float* __restrict__ emis, const int32_t* __restrict__ tags,
         float bt = act ? 1.0f : 0.f;  // beta-tilde_{len-1} (any positive constant: marginals renormalise)
         for (int t = len - 1; t >= 0; --t) {
             const float xv = act ? x[t * K + lane] : -INFINITY;
-            const float m = warp_max(xv);
+            const float m = kmax(xv, kp);
             const float wv = act ? expf(xv - m) * bt : 0.f;  // w_t[j]
             if (act) {
                 sBt[t * K + lane] = bt;
@@ -115,7 +128,7 @@ crf_nll_kernel(const float* __restrict__ emis, const int32_t* __restrict__ tags,
             if (t > 0) {
                 float r = 0.f;  // r_{t-1}[i = lane]
                 for (int j = 0; j < K; ++j) r = fmaf(act ? sE[lane * K + j] : 0.f, __shfl_sync(0xffffffffu, wv, j), r);
-                const float d = warp_sum(r);
+                const float d = ksum(r, kp);
                 if (lane == 0) sD[t - 1] = d;
                 bt = r / d;
             }
