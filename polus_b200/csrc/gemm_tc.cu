@@ -523,28 +523,33 @@ extern "C" int polus_gemm_tc(const polus_gemm_t* g, void* stream) {
     const long long mt = cdiv(g->M, BM * CG);
     const long long nb = (long long)batch0 * batch1;
     const int kb_total = cdiv(g->K, BK);
-    // split_k == 0 with accumulate: pick the split that fills the machine (wgrad: few output tiles, long K)
-    int split = g->split_k;
-    if (split == 0) {
-        split = 1;
-        if (g->accumulate && g->act == POLUS_ACT_NONE && g->C2 == nullptr) {
-            const long long ctas = mt * cdiv(g->N, 128) * nb * CG;
-            if (ctas < sms) {
-                split = (int)((sms + ctas - 1) / ctas);
-                const int max_split = kb_total / 4 > 1 ? kb_total / 4 : 1;  // >= 4 k-blocks per split
-                if (split > max_split) split = max_split;
-            }
-        }
-    }
-    if (split < 1) split = 1;
-    // tile width: the widest tile that still yields at least one full wave of CTAs.  (A wave-quantisation
-    // heuristic that preferred 128-wide tiles for N = 768 measured slower: profiles/r01_gemm_shapes_v4.log.)
+    // Tile width and split-K.
+    //  * accumulate GEMMs with split_k == 0 (wgrad: few output tiles, very long K): 256-wide tiles whenever N allows
+    //    (a 128-wide pair tile needs 96 B/clk/SM of operand traffic, more than L2 delivers) and the split that
+    //    minimises waves x (k-blocks per split + fixed tile overhead).
+    //  * everything else: the widest tile that still yields one full wave of CTAs.
+    int split = g->split_k < 1 ? 1 : g->split_k;
     int BN;
+    const long long groups = sms / CG;
     if (g->N <= 64) BN = 64;
     else if (g->N <= 128) BN = 128;
+    else if (g->split_k == 0 && g->accumulate && g->act == POLUS_ACT_NONE && g->C2 == nullptr) BN = 256;
     else {
         const long long ctas256 = mt * cdiv(g->N, 256) * nb * split * CG;
         BN = ctas256 >= sms ? 256 : 128;
+    }
+    if (g->split_k == 0 && g->accumulate && g->act == POLUS_ACT_NONE && g->C2 == nullptr) {
+        const long long tiles = mt * cdiv(g->N, BN) * nb;
+        const int max_split = kb_total / 4 > 1 ? kb_total / 4 : 1;  // >= 4 k-blocks per split
+        long long best_cost = -1;
+        for (int sp = 1; sp <= max_split && sp <= 32; ++sp) {
+            const long long waves = (tiles * sp + groups - 1) / groups;
+            const long long cost = waves * (cdiv(kb_total, sp) + 8);
+            if (best_cost < 0 || cost < best_cost) {
+                best_cost = cost;
+                split = sp;
+            }
+        }
     }
 
     TcParams p;
