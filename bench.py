@@ -192,34 +192,58 @@ def run_ours(args):
         all_ms = [json.loads(b.decode()) for b in comm._host_allgather(json.dumps([ms_dev, ms_e2e]).encode())]
         ms_dev, ms_e2e = max(a[0] for a in all_ms), max(a[1] for a in all_ms)
 
-    # ---- roofline of the dominant kernel family: every tcgen05 GEMM launch of one op-by-op step, event-bracketed
+    # ---- roofline of the dominant kernel family (tcgen05 GEMMs, ~all FLOPs of the step)
+    # (1) one op-by-op step counts the launches and their algorithmic FLOPs (2mnk each);
+    # (2) a second captured graph of the SAME step in which every kernel entry point except polus_gemm_tc is a
+    #     no-op (polus_b200._lib.set_only) replays exactly the step's GEMM launches -- same order, shapes, buffers
+    #     and streams -- and is timed with CUDA events like the step itself: duration of the GEMM launches of one
+    #     step, free of host launch latency (bracketing single launches op-by-op charges ~5 us of host time each);
+    # (3) the marginal figure (step minus the step with polus_gemm_tc ablated) is reported next to it.
     roof = None
     prof = []
     ops.GEMM_PROFILE = prof
     trainer.use_graph = False
-    for i in range(2):  # every rank runs these steps (they contain the gradient allreduce); rank 0 reports
-        prof.clear()
-        float(trainer.train_step(*batches[i]))
+    float(trainer.train_step(*batches[0]))  # every rank runs it (it contains the gradient allreduce)
     ops.GEMM_PROFILE = None
     trainer.use_graph = True
+    tot_flop = sum(flop for kind, flop, _, _ in prof if kind == "tc")
+    n_tc = sum(1 for kind, _, _, _ in prof if kind == "tc")
     barrier()
+
+    def replay_ms(only=None, ablate=None):
+        saved = (trainer._compiled, trainer._warm, _lib._ONLY, _lib._ABLATE)
+        trainer._compiled, trainer._warm = {}, set()
+        if only is not None:
+            _lib.set_only(only)
+        if ablate is not None:
+            _lib._ABLATE = frozenset(ablate)
+        try:
+            for i in range(3):
+                float(trainer.train_step(*dev_batches[i % len(dev_batches)]))
+            ms, _, _ = timed(dev_batches)
+        finally:
+            trainer._compiled, trainer._warm = saved[0], saved[1]
+            _lib._ONLY, _lib._ABLATE = saved[2], saved[3]
+        return ms / args.steps
+
+    gemm_only_ms = replay_ms(only={"polus_gemm_tc"})
+    no_gemm_ms = replay_ms(ablate={"polus_gemm_tc"})
+    dbg("gemm-only replays done")
+    if world > 1:
+        all_g = [json.loads(b.decode()) for b in comm._host_allgather(json.dumps([gemm_only_ms, no_gemm_ms]).encode())]
+        gemm_only_ms, no_gemm_ms = max(a[0] for a in all_g), max(a[1] for a in all_g)
     if rank == 0:
-        tot_ms, tot_flop, n = 0.0, 0.0, 0
-        for kind, flop, e0, e1 in prof:
-            if kind != "tc":
-                continue
-            ms = C.c_float()
-            _lib.call("polus_event_elapsed_ms", e0, e1, C.byref(ms))
-            tot_ms += ms.value
-            tot_flop += flop
-            n += 1
         peaks, how = read_peaks()
         peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
-        achieved = tot_flop / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
+        achieved = tot_flop / (gemm_only_ms * 1e-3) / 1e12 if gemm_only_ms > 0 else 0.0
+        step_ms = ms_dev / args.steps
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "gemm_tc_kernel (all tcgen05 GEMM launches of one step)", "launches": n,
-                "gemm_ms_per_step": tot_ms, "peak_source": f"{how} bf16_tflops_sustained (kernel timed inside a long step)",
-                "step_mfu": (args.batch * TRAIN_GFLOP_PER_SEQ * 1e9 / (ms_dev / args.steps * 1e-3)) / 1e12 / peak}
+                "traffic": None, "kernel": "gemm_tc_kernel (all tcgen05 GEMM launches of one step)", "launches": n_tc,
+                "gemm_ms_per_step": gemm_only_ms, "gemm_gflop_per_step": tot_flop / 1e9,
+                "method": "CUDA-event time of a captured replay of the step's GEMM launches alone (same order/buffers/streams)",
+                "gemm_marginal_ms_per_step": step_ms - no_gemm_ms,
+                "peak_source": f"{how} bf16_tflops_sustained (kernel timed inside a long step)",
+                "step_mfu": (args.batch * TRAIN_GFLOP_PER_SEQ * 1e9 / (step_ms * 1e-3)) / 1e12 / peak}
     if rank != 0:
         return
     seqs = args.batch * world * args.steps

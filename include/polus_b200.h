@@ -40,7 +40,8 @@ typedef enum {
     POLUS_ACT_RELU = 2, /* tutorials/classifier_example.py:46 */
     POLUS_ACT_SWISH = 3, /* polus/ner/models.py:30 */
     POLUS_ACT_TANH = 4, /* HF BertPooler */
-    POLUS_ACT_MISH = 5  /* polus/models.py:53-57 */
+    POLUS_ACT_MISH = 5, /* polus/models.py:53-57 */
+    POLUS_ACT_DERIV = 100 /* polus_act_bwd_colsum only: `z` already holds act'(pre-activation) (polus_gemm_t.c2_kind = 1) */
 } polus_act_t;
 
 /* ---------------------------------------------------------------- runtime / memory ---------- */
@@ -58,7 +59,7 @@ int polus_memcpy_h2d(void* d_dst, const void* h_src, size_t bytes, void* stream)
 int polus_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes, void* stream);
 int polus_memcpy_d2d(void* d_dst, const void* d_src, size_t bytes, void* stream);
 int polus_memset(void* d_ptr, int value, size_t bytes, void* stream);
-int polus_stream_create(void** stream, int high_priority);
+int polus_stream_create(void** stream, int high_priority);  /* 0 normal, 1 highest (collectives), 2 background */
 int polus_stream_destroy(void* stream);
 int polus_stream_sync(void* stream);
 int polus_device_sync(void);
@@ -106,6 +107,14 @@ typedef struct {
     int32_t act;       /* polus_act_t */
     int32_t accumulate; /* 1: C += result (fp32 C only; required when split_k > 1) */
     int32_t split_k;    /* >= 1 */
+    /* Fused backward of an activation layer (tcgen05 path, bf16 C).  Forward: c2_kind = 1 stores act'(pre-activation)
+     * in C2 instead of the pre-activation itself.  Backward (dgrad of the NEXT layer): Emul = that tensor, same
+     * layout as C, multiplies the result element-wise, C = (alpha A.B^T + bias) * Emul, and colsum[n] += sum_m C[m,n]
+     * accumulates the bias gradient (fp32 atomics) -- the tf.GradientTape ops GeluGrad + BiasAddGrad of
+     * polus/training.py:185 without a pass over the [M,N] tensor. */
+    int32_t c2_kind;    /* 0: C2 = pre-activation, 1: C2 = activation derivative */
+    const void* Emul;   /* optional bf16 [M,N] (ldc/cbs0/cbs1 as C); requires act == NONE, no C2 */
+    float* colsum;      /* optional fp32 [N] */
 } polus_gemm_t;
 
 /* tcgen05 / TMEM / TMA GEMM.  Replaces the cuBLAS calls TF makes for HF TFBertLayer's Dense

@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libpolus_b200.so")
 
 F32, BF16, I32, U8 = 0, 1, 2, 3
 ACT = {None: 0, "linear": 0, "none": 0, "gelu": 1, "relu": 2, "swish": 3, "silu": 3, "tanh": 4, "mish": 5}
+ACT_DERIV = 100  # polus_act_bwd_colsum: `z` already holds act'(pre-activation) (written by the forward GEMM, c2_kind = 1)
 UNARY = {"exp": 16, "log": 17, "softplus": 18, "sigmoid": 19, "neg": 20, "square": 21, "scale": 22,
          "gelu": 1, "relu": 2, "swish": 3, "tanh": 4, "mish": 5, "identity": 0}
 
@@ -35,7 +36,7 @@ class Gemm(C.Structure):
                 ("C", C.c_void_p), ("ldc", C.c_int64), ("cbs0", C.c_int64), ("cbs1", C.c_int64),
                 ("c_dtype", C.c_int32), ("C2", C.c_void_p), ("bias", C.c_void_p),
                 ("alpha", C.c_float), ("act", C.c_int32), ("accumulate", C.c_int32),
-                ("split_k", C.c_int32)]
+                ("split_k", C.c_int32), ("c2_kind", C.c_int32), ("Emul", C.c_void_p), ("colsum", C.c_void_p)]
 
 
 class AdamCfg(C.Structure):
@@ -177,8 +178,31 @@ def last_error():
     return load().polus_last_error().decode("utf-8", "replace")
 
 
+# POLUS_ABLATE=name[,name...]: profiling aid (tools/ablate_step.py) -- the listed entry points become no-ops, so the
+# step time without them gives their true marginal cost inside the replayed graph.  Results are garbage by design.
+_ABLATE = frozenset(n for n in os.environ.get("POLUS_ABLATE", "").split(",") if n)
+
+
+_ONLY = None  # set_only(): every kernel entry point NOT in this set becomes a no-op (bench.py's GEMM-only replay)
+_PLUMBING = ("polus_malloc", "polus_free", "polus_host_", "polus_memcpy", "polus_memset", "polus_stream_", "polus_device_",
+             "polus_event_", "polus_graph_", "polus_launch_count", "polus_profiler_", "polus_init", "polus_version",
+             "polus_comm_init", "polus_comm_unique_id", "polus_comm_size", "polus_comm_rank", "polus_comm_destroy")
+
+
+def set_only(names):
+    """Profiling aid: keep memory/stream/graph plumbing and the listed kernel entry points, skip every other one
+    (None restores normal operation).  Used to replay the step's GEMM launches alone, in order, on the step's own
+    buffers, for the roofline figure; results of such a replay are garbage by design."""
+    global _ONLY
+    _ONLY = None if names is None else frozenset(names)
+
+
 def call(name, *args):
     """Call a status-returning entry point; raise the matching Python exception on failure."""
+    if _ABLATE and name in _ABLATE:
+        return 0
+    if _ONLY is not None and name not in _ONLY and name not in _VALUE_RET and not name.startswith(_PLUMBING):
+        return 0
     rc = getattr(load(), name)(*args)
     if name in _VALUE_RET:
         return rc

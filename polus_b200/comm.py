@@ -208,6 +208,7 @@ class _DistributedTape:
         for b in buckets:
             uses = [first_use[id(p)] for p in b[3] if id(p) in first_use]
             ready_at.append(min(uses) if uses else len(tape.nodes))
+        from . import ops
         comm_stream, main = _state["comm_stream"], device.stream()
         pending = sorted(range(len(buckets)), key=lambda i: -ready_at[i])
         events = []
@@ -218,10 +219,9 @@ class _DistributedTape:
             _lib.call("polus_event_create", C.byref(ev))
             _lib.call("polus_event_record", ev, main)
             _lib.call("polus_stream_wait_event", comm_stream, ev)
+            ops.side_join(comm_stream)  # weight gradients of this bucket issued on the background stream
             _lib.call("polus_comm_allreduce_f32", ch.g.ptr + off * 4, n, comm_stream)
             events.append(ev)
-
-        from . import ops
 
         def before_node(idx):
             while pending and ready_at[pending[0]] > idx:

@@ -80,6 +80,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const int b = blockIdx.x / (q_tiles * p.nh);
     const int q0 = qt * 128;
 
+    pdl_trigger();
     if (threadIdx.x == 0) {
         ptx::prefetch_tensormap(&tmQKV);
         ptx::prefetch_tensormap(&tmO);
@@ -94,6 +95,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -272,6 +274,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const int n_qt = (p.S + 127) / 128;   // query tiles (1 or 2)
     const int n_kh = n_qt;                // 128-key blocks
 
+    pdl_trigger();
     if (threadIdx.x == 0) {
         ptx::prefetch_tensormap(&tmQKV);
         ptx::prefetch_tensormap(&tmDO);
@@ -287,6 +290,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_wait();
     constexpr uint32_t C_S = 0, C_DP = 128, C_DQ0 = 256, C_DK = 320, C_DV = 384, C_DQ1 = 448;
 
     if (warp == 0) {
@@ -563,7 +567,7 @@ extern "C" int polus_attention_fwd(const polus_bf16_t* qkv, const int32_t* mask,
     }
     AttnParams p = make_params(B, S, nh, p_drop, seed, site, d_step, mask, lse, keepbits);
     const int q_tiles = (S + 127) / 128;
-    attn_fwd_kernel<<<B * nh * q_tiles, FWD_THREADS, F_SMEM, (cudaStream_t)stream>>>(tq, to, p);
+    POLUS_CHECK_CUDA(polus_launch_pdl(attn_fwd_kernel, dim3(B * nh * q_tiles), dim3(FWD_THREADS), F_SMEM, (cudaStream_t)stream, tq, to, p));
     g_launch_count++;
     POLUS_LAUNCH_CHECK();
     return 0;
@@ -589,7 +593,7 @@ extern "C" int polus_attention_bwd(const polus_bf16_t* qkv, const int32_t* mask,
         set = true;
     }
     AttnParams p = make_params(B, S, nh, p_drop, seed, site, d_step, mask, const_cast<float*>(lse), const_cast<uint32_t*>(keepbits));
-    attn_bwd_kernel<<<B * nh, BWD_THREADS, B_SMEM, (cudaStream_t)stream>>>(tq, tdo, tdq, (const bf16*)ctx, (const bf16*)dctx, p);
+    POLUS_CHECK_CUDA(polus_launch_pdl(attn_bwd_kernel, dim3(B * nh), dim3(BWD_THREADS), B_SMEM, (cudaStream_t)stream, tq, tdo, tdq, (const bf16*)ctx, (const bf16*)dctx, p));
     g_launch_count++;
     POLUS_LAUNCH_CHECK();
     return 0;

@@ -45,12 +45,42 @@ void polus_set_error(const char* fmt, ...);
 
 int polus_num_sms();
 
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  The step is ~260 short kernels (10-60 us) replayed from one CUDA graph; with a
+// programmatic edge the next kernel's CTAs are scheduled while the previous kernel drains and run their private
+// prologue (barrier init, TMEM allocation, descriptor prefetch, parameter loads) up to pdl_wait().  Rules every
+// kernel launched through polus_launch_pdl() follows: (1) pdl_trigger() first thing, (2) EVERY thread executes
+// pdl_wait() before its first global-memory access that is not to immutable launch arguments.  pdl_wait() returns
+// only when all prerequisite grids have completed and flushed, so ordering stays transitive along the stream.
+// POLUS_PDL=0 turns the launch attribute off (then both instructions are no-ops).
+// ---------------------------------------------------------------------------------------------
+bool polus_pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t polus_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                    Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = polus_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ---------------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

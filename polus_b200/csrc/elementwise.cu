@@ -19,6 +19,8 @@ act_bwd_colsum_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, i
     const int r0 = blockIdx.y * rows_per_slab;
     const int r1 = min(M, r0 + rows_per_slab);
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    pdl_trigger();
+    pdl_wait();
     if (col < N) {
         // 4 rows per iteration: all loads are issued before the (MUFU-heavy) activation-gradient math
         constexpr int U = 4;
@@ -43,7 +45,7 @@ act_bwd_colsum_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, i
                         float zv[8];
                         unpack8(zq[u], zv);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) g[j] *= act_grad(act, zv[j]);
+                        for (int j = 0; j < 8; ++j) g[j] *= (act == POLUS_ACT_DERIV ? zv[j] : act_grad(act, zv[j]));
                     }
                     if (dz != nullptr) *reinterpret_cast<bf16x8*>(dz + (long long)rr * N + col) = pack8(g);
 #pragma unroll
@@ -298,7 +300,7 @@ extern "C" int polus_act_bwd_colsum(const polus_bf16_t* dy, const polus_bf16_t* 
     slabs = cdiv(M, rows_per_slab);
     dim3 grid(cdiv(N, 256), slabs);
     (void)ws;
-    act_bwd_colsum_kernel<<<grid, 256, 0, st>>>((const bf16*)dy, (const bf16*)z, M, N, act, (bf16*)dz, gbias, rows_per_slab);
+    POLUS_CHECK_CUDA(polus_launch_pdl(act_bwd_colsum_kernel, grid, dim3(256), 0, st, (const bf16*)dy, (const bf16*)z, M, N, act, (bf16*)dz, gbias, rows_per_slab));
     g_launch_count++;
     POLUS_LAUNCH_CHECK();
     return 0;

@@ -21,6 +21,9 @@ struct SmallParams {
     float alpha;
     int act;
     int accumulate;
+    int c2_kind;
+    const bf16* emul;
+    float* colsum;
 };
 
 __device__ __forceinline__ float load_elem(const void* p, long long idx, int is_bf16) {
@@ -81,11 +84,14 @@ __global__ void __launch_bounds__(256) gemm_small_kernel(const SmallParams p) {
         if (m >= p.M) continue;
         float z = acc[i] * p.alpha + bias;
         const long long idx = c_off + (long long)m * p.ldc + n;
+        if (p.emul) z *= __bfloat162float(p.emul[idx]);
         if (p.C2) {
-            if (p.c_f32) reinterpret_cast<float*>(p.C2)[idx] = z;
-            else reinterpret_cast<bf16*>(p.C2)[idx] = __float2bfloat16(z);
+            const float z2 = p.c2_kind == 1 ? act_grad(p.act, z) : z;
+            if (p.c_f32) reinterpret_cast<float*>(p.C2)[idx] = z2;
+            else reinterpret_cast<bf16*>(p.C2)[idx] = __float2bfloat16(z2);
         }
         float y = act_fwd(p.act, z);
+        if (p.colsum) atomicAdd(p.colsum + n, p.c_f32 ? y : __bfloat162float(__float2bfloat16(y)));
         if (p.c_f32) {
             float* c = reinterpret_cast<float*>(p.C) + idx;
             *c = p.accumulate ? *c + y : y;
@@ -116,6 +122,7 @@ extern "C" int polus_gemm_small(const polus_gemm_t* g, void* stream) {
     p.C = g->C; p.C2 = g->C2; p.ldc = g->ldc; p.cbs0 = g->cbs0; p.cbs1 = g->cbs1;
     p.c_f32 = g->c_dtype == POLUS_F32;
     p.bias = g->bias; p.alpha = g->alpha; p.act = g->act; p.accumulate = g->accumulate;
+    p.c2_kind = g->c2_kind; p.emul = (const bf16*)g->Emul; p.colsum = g->colsum;
     dim3 grid(cdiv(g->N, TS), cdiv(g->M, TS), p.batch0 * batch1);
     POLUS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "polus_gemm_small: problem too large (M=%d batch=%d)", g->M, (int)grid.z);
     gemm_small_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);

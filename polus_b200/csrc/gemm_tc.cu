@@ -55,6 +55,9 @@ struct TcParams {
     int c_f32;
     int accumulate;
     int has_c2;
+    int c2_grad;      // C2 = act'(pre-activation) instead of the pre-activation
+    int has_emul;     // C = (alpha A.B^T + bias) * Emul, Emul read through tmC2
+    float* colsum;    // colsum[n] += sum_m C[m,n]
 };
 
 template <int BN, int CG>
@@ -62,10 +65,10 @@ struct Cfg {
     static constexpr int BN_LOCAL = BN / CG;  // rows of the B tile this CTA stages
     static constexpr int B_STAGE_BYTES = BN_LOCAL * BK * 2;
     static constexpr int kStageBytes = A_STAGE_BYTES + B_STAGE_BYTES;
-    static constexpr int kBudget = 227 * 1024 - 1024 - STG_BYTES - 256;
+    static constexpr int kBudget = 227 * 1024 - 1024 - STG_BYTES - 512;
     static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
     static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
-    static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + STG_BYTES + 256;
+    static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + STG_BYTES + 512;
     static constexpr int kColBlocks = BN / 64;                       // 64-column blocks per tile
     static constexpr int kEpiActive = kColBlocks >= 2 ? 8 : 4;        // epilogue warps that do work
     static constexpr int kBlocksPerWarp = kColBlocks >= 2 ? kColBlocks / 2 : 1;
@@ -84,6 +87,44 @@ __device__ __forceinline__ void apply_act(int act, float* v) {
         case POLUS_ACT_TANH: apply_act32<POLUS_ACT_TANH>(v); break;
         case POLUS_ACT_MISH: apply_act32<POLUS_ACT_MISH>(v); break;
         default: break;
+    }
+}
+
+// y = act(x) and d = act'(x), 32 values, sharing the transcendental work (GELU: one rcp + one ex2 for both)
+template <int ACT>
+__device__ __forceinline__ void act_fwd_grad32(float* v, float* d) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const float x = v[j];
+        if (ACT == POLUS_ACT_GELU) {
+            const float u = fabsf(x) * 0.70710678118654752f;
+            float t;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, u, 1.0f)));
+            float poly = fmaf(t, 1.061405429f, -1.453152027f);
+            poly = fmaf(t, poly, 1.421413741f);
+            poly = fmaf(t, poly, -0.284496736f);
+            poly = fmaf(t, poly, 0.254829592f);
+            const float ex = __expf(-u * u);
+            const float cdf = fmaf(0.5f, copysignf(fmaf(-poly * t, ex, 1.0f), x), 0.5f);
+            v[j] = x * cdf;
+            d[j] = fmaf(x, 0.3989422804014327f * ex, cdf);
+        } else {
+            v[j] = act_fwd(ACT, x);
+            d[j] = act_grad(ACT, x);
+        }
+    }
+}
+__device__ __forceinline__ void apply_act_grad(int act, float* v, float* d) {
+    switch (act) {
+        case POLUS_ACT_GELU: act_fwd_grad32<POLUS_ACT_GELU>(v, d); break;
+        case POLUS_ACT_RELU: act_fwd_grad32<POLUS_ACT_RELU>(v, d); break;
+        case POLUS_ACT_SWISH: act_fwd_grad32<POLUS_ACT_SWISH>(v, d); break;
+        case POLUS_ACT_TANH: act_fwd_grad32<POLUS_ACT_TANH>(v, d); break;
+        case POLUS_ACT_MISH: act_fwd_grad32<POLUS_ACT_MISH>(v, d); break;
+        default:
+#pragma unroll
+            for (int j = 0; j < 32; ++j) d[j] = 1.0f;
+            break;
     }
 }
 
@@ -146,11 +187,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* empty_bar = full_bar + kStages;
     uint64_t* tfull_bar = empty_bar + kStages;
     uint64_t* tempty_bar = tfull_bar + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    uint64_t* emul_bar = tempty_bar + 2;  // [epilogue warp][staging buffer]: Emul tile landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(emul_bar + 2 * kEpiWarps);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
+    pdl_trigger();  // the next kernel may start its own prologue as soon as SMs free up
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmA);
         ptx::prefetch_tensormap(&tmB);
@@ -165,6 +208,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ptx::mbar_init(&tfull_bar[s], 1);
             ptx::mbar_init(&tempty_bar[s], C::kEpiActive * CG);  // one arrive per working epilogue warp of the group
         }
+        for (int s = 0; s < 2 * kEpiWarps; ++s) ptx::mbar_init(&emul_bar[s], 1);
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
@@ -176,6 +220,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (CG == 2) ptx::cluster_sync();  // peer barriers initialised before any remote arrive / multicast commit
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();  // operands / outputs of earlier kernels are touched only from here on
 
     auto decode = [&](int t, int& mt, int& nt, int& sp, int& b0, int& b1) {
         mt = t % p.m_tiles;
@@ -290,6 +335,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t acc_phase = 0;
         int stores_in_flight = 0;
         int nblk = 0;  // staged blocks so far: alternates the two staging buffers across tiles too
+        // ---- Emul prefetch: the multiplier tile of block n+1 is fetched by TMA into the C2 half of the OTHER staging
+        // buffer while block n is processed (that half was last read, and fenced, at block n-1).
+        auto blk_valid = [&](int t, int i) -> bool {
+            if (t >= p.num_tiles || i >= C::kBlocksPerWarp) return false;
+            int mt, nt, sp, b0, b1;
+            decode(t, mt, nt, sp, b0, b1);
+            return nt * BN + (half * C::kBlocksPerWarp + i) * 64 < p.N;
+        };
+        auto advance = [&](int& t, int& i) {
+            ++i;
+            while (t < p.num_tiles && !blk_valid(t, i)) {
+                t += tile_step;
+                i = 0;
+            }
+        };
+        auto emul_issue = [&](int t, int i, int slot) {
+            if (lane == 0) {
+                int mt, nt, sp, b0, b1;
+                decode(t, mt, nt, sp, b0, b1);
+                uint64_t* bar = &emul_bar[e * 2 + slot];
+                ptx::mbar_expect_tx(bar, STG_BLOCK);
+                ptx::tma_load_4d(stg + slot * (2 * STG_BLOCK) + STG_BLOCK, &tmC2, bar, nt * BN + (half * C::kBlocksPerWarp + i) * 64,
+                                 (mt * CG + (int)cta_rank) * BM + quad * 32, b0, b1);
+            }
+        };
+        int pf_t = tile0, pf_i = -1;
+        if (p.has_emul) {
+            advance(pf_t, pf_i);
+            if (pf_t < p.num_tiles) emul_issue(pf_t, pf_i, 0);
+        }
         for (int t = tile0; t < p.num_tiles; t += tile_step) {
             int mt, nt, sp, b0, b1;
             decode(t, mt, nt, sp, b0, b1);
@@ -298,6 +373,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int row0 = (mt * CG + (int)cta_rank) * BM + quad * 32;
             const int row = row0 + lane;
             const long long row_off = (long long)b0 * p.cbs0 + (long long)b1 * p.cbs1 + (long long)row * p.ldc;
+            (void)row_off;
             const bool add_bias = (p.bias != nullptr) && (sp == 0);
 #pragma unroll 1
             for (int i = 0; i < C::kBlocksPerWarp; ++i) {
@@ -307,12 +383,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int buf = nblk & 1;
                 uint8_t* blkC = stg + buf * (2 * STG_BLOCK);
                 uint8_t* blkC2 = blkC + STG_BLOCK;
+                if (p.has_emul) {
+                    advance(pf_t, pf_i);  // (pf_t, pf_i) was this block; now the next valid one
+                    if (pf_t < p.num_tiles) emul_issue(pf_t, pf_i, buf ^ 1);
+                }
                 if (stores_in_flight >= 2) {
                     // the TMA store that last read this staging buffer must be done reading it
                     if (lane == 0) ptx::tma_store_wait_read<1>();
                     __syncwarp();
                     stores_in_flight = 1;
                 }
+                if (p.has_emul) ptx::mbar_wait(&emul_bar[e * 2 + buf], (uint32_t)(nblk >> 1) & 1u);
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int col0 = colb + h * 32;
@@ -321,8 +402,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         ptx::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + cb * 64 + h * 32, v);
                         ptx::tmem_ld_wait();
                         const int nvalid = min(32, p.N - col0);
+                        if (p.alpha != 1.0f) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+                            for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+                        }
                         if (add_bias) {
                             if (nvalid == 32) {
 #pragma unroll
@@ -343,8 +426,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             // fp32 output: the two 32-column chunks of this block use the buffer's two 4 KB halves
                             apply_act(p.act, v);
                             stage_row_f32(h == 0 ? blkC : blkC2, lane, v);
+                        } else if (p.has_emul) {
+                            // multiplier tile (rows >= M / columns >= N arrive as zeros): same swizzled layout as the staging block
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                float m8[8];
+                                unpack8(*reinterpret_cast<const bf16x8*>(blkC2 + lane * 128 + (((h * 4 + j) ^ (lane & 7)) << 4)), m8);
+#pragma unroll
+                                for (int x = 0; x < 8; ++x) v[8 * j + x] *= m8[x];
+                            }
+                            stage_row(blkC, lane, h, v);
+                        } else if (p.has_c2 && p.c2_grad) {
+                            float d[32];
+                            apply_act_grad(p.act, v, d);
+                            stage_row(blkC2, lane, h, d);  // act'(z): the next layer's dgrad multiplies by it
+                            stage_row(blkC, lane, h, v);
                         } else {
-                            if (p.has_c2) stage_row(blkC2, lane, h, v);  // pre-activation copy (GELU backward)
+                            if (p.has_c2) stage_row(blkC2, lane, h, v);  // pre-activation copy
                             apply_act(p.act, v);
                             stage_row(blkC, lane, h, v);
                         }
@@ -367,6 +465,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (p.has_c2) ptx::tma_store_4d(&tmC2, blkC2, colb, row0, b0, b1);
                     }
                     ptx::tma_store_commit();
+                }
+                if (p.colsum != nullptr && !p.c_f32) {
+                    // column sums of the staged (bf16-rounded) block: lane L owns columns 2L, 2L+1 -- word L of every row,
+                    // so each row is read as one conflict-free 128-byte wavefront
+                    const int nrows = min(32, p.M - row0);
+                    float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+                    for (int r = 0; r < 32; ++r) {
+                        if (r < nrows) {
+                            const uint32_t w = *reinterpret_cast<const uint32_t*>(blkC + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4) + (lane & 3) * 4);
+                            s0 += __uint_as_float(w << 16);
+                            s1 += __uint_as_float(w & 0xFFFF0000u);
+                        }
+                    }
+                    const int c = colb + 2 * lane;
+                    if (c < p.N) atomicAdd(p.colsum + c, s0);
+                    if (c + 1 < p.N) atomicAdd(p.colsum + c + 1, s1);
                 }
                 ++stores_in_flight;
                 ++nblk;
@@ -464,13 +579,15 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = C::kSmemBytes;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CG;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = polus_pdl_enabled() ? 2 : 1;
     POLUS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tc2, p));
     g_launch_count++;
     POLUS_LAUNCH_CHECK();
@@ -503,6 +620,10 @@ const char* why_unsupported(const polus_gemm_t* g) {
     if (g->accumulate && g->c_dtype != POLUS_F32) return "accumulate requires fp32 C";
     if (g->split_k > 1 && (!g->accumulate || g->act != POLUS_ACT_NONE || g->C2)) return "split_k needs accumulate, no activation";
     if (g->c_dtype != POLUS_F32 && g->c_dtype != POLUS_BF16) return "C dtype";
+    if (g->Emul && (g->c_dtype != POLUS_BF16 || g->C2 || g->act != POLUS_ACT_NONE || !aligned16(g->Emul)))
+        return "Emul requires bf16 C, no C2 and no activation";
+    if (g->colsum && g->c_dtype != POLUS_BF16) return "colsum requires bf16 C";
+    if (g->c2_kind != 0 && g->c2_kind != 1) return "c2_kind";
     return nullptr;
 }
 
@@ -574,6 +695,9 @@ extern "C" int polus_gemm_tc(const polus_gemm_t* g, void* stream) {
     p.c_f32 = g->c_dtype == POLUS_F32;
     p.accumulate = g->accumulate;
     p.has_c2 = g->C2 != nullptr;
+    p.c2_grad = g->c2_kind == 1;
+    p.has_emul = g->Emul != nullptr;
+    p.colsum = g->colsum;
 
     CUtensorMap ta, tb, tc, tc2;
     int rc = make_map(&ta, g->A, g->M, g->K, batch0, batch1, BM);
@@ -583,8 +707,8 @@ extern "C" int polus_gemm_tc(const polus_gemm_t* g, void* stream) {
     if (!p.c_f32) {  // bf16 outputs leave through TMA stores of 32-row x 64-column blocks
         rc = encode_map(&tc, g->C, g->N, g->M, g->ldc, batch0, g->cbs0, batch1, g->cbs1, 32);
         if (rc) return rc;
-        if (p.has_c2) {
-            rc = encode_map(&tc2, g->C2, g->N, g->M, g->ldc, batch0, g->cbs0, batch1, g->cbs1, 32);
+        if (p.has_c2 || p.has_emul) {
+            rc = encode_map(&tc2, p.has_c2 ? g->C2 : const_cast<void*>(g->Emul), g->N, g->M, g->ldc, batch0, g->cbs0, batch1, g->cbs1, 32);
             if (rc) return rc;
         } else {
             tc2 = tc;

@@ -47,6 +47,8 @@ ln_res_fwd_kernel(bf16* __restrict__ x, const bf16* __restrict__ res, const floa
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int chunks = H >> 3;
+    pdl_trigger();
+    pdl_wait();
     const uint32_t step = dc.thresh16 ? *d_step : 0u;
     for (int row = blockIdx.x * 4 + warp; row < M; row += gridDim.x * 4) {
         const long long base = (long long)row * H;
@@ -134,12 +136,14 @@ ln_res_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, con
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int chunks = H >> 3;
-    const uint32_t step = dc.thresh16 ? *d_step : 0u;
+    pdl_trigger();
     float dg[NC][8], db[NC][8], dxs[NC][8];
 #pragma unroll
     for (int i = 0; i < NC; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) dg[i][j] = db[i][j] = dxs[i][j] = 0.f;
+    pdl_wait();
+    const uint32_t step = dc.thresh16 ? *d_step : 0u;
     for (int row = blockIdx.x * kWarps + warp; row < M; row += gridDim.x * kWarps) {
         const long long base = (long long)row * H;
         bf16x8 dyr[NC], zr[NC];
@@ -472,7 +476,7 @@ extern "C" int polus_ln_res_fwd(polus_bf16_t* x, const polus_bf16_t* res, const 
     const int cap = polus_num_sms() * 16;
     if (grid > cap) grid = cap;
     const int nc = cdiv(H, 256);
-#define LN_FWD(NC_) ln_res_fwd_kernel<NC_><<<grid, 128, 0, st>>>((bf16*)x, (const bf16*)res, gamma, beta, M, H, eps, dc, d_step, (bf16*)y, mean, rstd)
+#define LN_FWD(NC_) POLUS_CHECK_CUDA(polus_launch_pdl(ln_res_fwd_kernel<NC_>, dim3(grid), dim3(128), 0, st, (bf16*)x, (const bf16*)res, gamma, beta, M, H, eps, dc, d_step, (bf16*)y, mean, rstd))
     if (nc <= 1) LN_FWD(1); else if (nc == 2) LN_FWD(2); else if (nc == 3) LN_FWD(3); else if (nc == 4) LN_FWD(4); else LN_FWD(16);
 #undef LN_FWD
     g_launch_count++;
@@ -498,8 +502,8 @@ extern "C" int polus_ln_res_bwd(const polus_bf16_t* dy, const polus_bf16_t* dy2,
 #define LN_BWD(NC_)                                                                                                            \
     {                                                                                                                          \
         if (smem > 48 * 1024) POLUS_CHECK_CUDA(cudaFuncSetAttribute(ln_res_bwd_kernel<NC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        ln_res_bwd_kernel<NC_><<<grid, kWarps * 32, smem, st>>>((const bf16*)dy, (const bf16*)dy2, (const bf16*)z, mean, rstd, gamma, M, H, dc, \
-                                                               d_step, (bf16*)dx, (bf16*)dres, ggamma, gbeta, gbias_x);        \
+        POLUS_CHECK_CUDA(polus_launch_pdl(ln_res_bwd_kernel<NC_>, dim3(grid), dim3(kWarps * 32), smem, st, (const bf16*)dy, (const bf16*)dy2, (const bf16*)z, mean, rstd, gamma, M, H, dc, \
+                                                               d_step, (bf16*)dx, (bf16*)dres, ggamma, gbeta, gbias_x));       \
     }
     if (nc <= 1) LN_BWD(1) else if (nc == 2) LN_BWD(2) else if (nc == 3) LN_BWD(3) else if (nc == 4) LN_BWD(4) else LN_BWD(16)
 #undef LN_BWD

@@ -5,6 +5,7 @@
 #include <cuda_profiler_api.h>
 #include <atomic>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <unordered_map>
 
 std::atomic<long long> g_launch_count{0};
@@ -29,6 +30,11 @@ int polus_num_sms() {
         if (g_num_sms <= 0) g_num_sms = 148;
     }
     return g_num_sms;
+}
+
+bool polus_pdl_enabled() {
+    static const bool on = !(getenv("POLUS_PDL") && atoi(getenv("POLUS_PDL")) == 0);
+    return on;
 }
 
 extern "C" {
@@ -114,7 +120,12 @@ int polus_stream_create(void** stream, int high_priority) {
     int lo = 0, hi = 0;
     POLUS_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     cudaStream_t s;
-    POLUS_CHECK_CUDA(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, high_priority ? hi : lo));
+    // 0 = normal (one level above the lowest when the device has more than two levels), 1 = highest (collectives),
+    // 2 = background (lowest: weight-gradient GEMMs that fill the tails of the main chain)
+    int prio = lo;
+    if (high_priority == 1) prio = hi;
+    else if (high_priority == 0 && lo - hi >= 2) prio = lo - 1;
+    POLUS_CHECK_CUDA(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, prio));
     *stream = s;
     return 0;
 }

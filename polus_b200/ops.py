@@ -132,6 +132,7 @@ def run_backward(nodes, loss, before_node=None):
                 prev.append(gi)
             else:
                 grads[id(t)] = [prev, gi]
+    side_join()  # weight gradients issued on the background stream are complete from here on
     return grads
 
 
@@ -163,6 +164,9 @@ def _recording(*inputs):
 
 def _record(tape, inputs, output, backward):
     output.requires_grad = True
+    for t in inputs:
+        if t is not None and not isinstance(t, Param):
+            t.consumers += 1
     tape.nodes.append(Node(list(inputs), output, backward))
     return output
 
@@ -176,6 +180,66 @@ def _accumulate(a, b):
     out = Tensor(a.shape, F32)
     _lib.call("polus_binary_f32", 0, a32.ptr, b32.ptr, a.size, b.size, out.ptr, device.stream())
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# background stream for weight-gradient GEMMs
+# ------------------------------------------------------------------------------------------------
+# Nothing in backward consumes dW before the optimizer (or the bucket allreduce), while the dgrad chain is strictly
+# serial and most of its GEMMs end in a partly filled wave (96 pair-tiles on 74 SM pairs for the 768-wide ones).
+# While a step is being captured, wgrad GEMMs are issued on a low-priority side stream, so in the replayed graph
+# they run in those tails and next to the memory-bound LayerNorm / activation-gradient kernels.  Only during
+# capture: there activation blocks are never recycled (tensor._Pool.trace), so the side stream cannot observe a
+# buffer being reused by the main chain.
+import os as _os
+
+SIDE_WGRAD = _os.environ.get("POLUS_SIDE_WGRAD", "1") != "0"
+_side = {"stream": None, "events": [], "next": 0, "dirty": False}
+
+
+def _side_event():
+    i = _side["next"]
+    if i == len(_side["events"]):
+        ev = C.c_void_p()
+        _lib.call("polus_event_create", C.byref(ev))
+        _side["events"].append(ev)
+    _side["next"] = i + 1
+    return _side["events"][i]
+
+
+def side_active():
+    from . import tensor as _t
+    return SIDE_WGRAD and _t._pool.trace is not None
+
+
+def side_reset():
+    """Called when a capture begins: events of an earlier capture may be reused."""
+    _side["next"] = 0
+    _side["dirty"] = False
+
+
+def side_fork():
+    """Side stream observes everything issued on the main stream so far; returns the side stream."""
+    if _side["stream"] is None:
+        s = C.c_void_p()
+        _lib.call("polus_stream_create", C.byref(s), 2)
+        _side["stream"] = s.value
+    ev = _side_event()
+    _lib.call("polus_event_record", ev, device.stream())
+    _lib.call("polus_stream_wait_event", _side["stream"], ev)
+    _side["dirty"] = True
+    return _side["stream"]
+
+
+def side_join(stream=None):
+    """`stream` (default: main) waits for every wgrad issued on the side stream so far."""
+    if not _side["dirty"]:
+        return
+    ev = _side_event()
+    _lib.call("polus_event_record", ev, _side["stream"])
+    _lib.call("polus_stream_wait_event", stream if stream is not None else device.stream(), ev)
+    if stream is None:
+        _side["dirty"] = False
 
 
 # ------------------------------------------------------------------------------------------------
@@ -242,13 +306,16 @@ def _operand(t_ptr, ld, mn_major, dtype, bs0=0, bs1=0):
 
 
 def _gemm(M, N, K, A, B, c_ptr, ldc, c_dtype, bias=None, act=0, c2=None, alpha=1.0, accumulate=0, split_k=1,
-          batch0=1, batch1=1, cbs0=0, cbs1=0, force_small=False):
+          batch0=1, batch1=1, cbs0=0, cbs1=0, force_small=False, stream=None, c2_kind=0, emul=None, colsum=None):
+    if stream is None:
+        stream = device.stream()
     g = _lib.Gemm()
     g.M, g.N, g.K, g.batch0, g.batch1 = M, N, K, batch0, batch1
     g.A, g.B = A, B
     g.C, g.ldc, g.cbs0, g.cbs1, g.c_dtype = c_ptr, ldc, cbs0, cbs1, c_dtype
     g.C2, g.bias = c2, bias
     g.alpha, g.act, g.accumulate, g.split_k = alpha, act, accumulate, split_k
+    g.c2_kind, g.Emul, g.colsum = c2_kind, emul, colsum
     use_tc = (not force_small and A.dtype == BF16 and B.dtype == BF16
               and _lib.call("polus_gemm_tc_supported", C.byref(g)) == 1)
     prof = GEMM_PROFILE
@@ -256,14 +323,14 @@ def _gemm(M, N, K, A, B, c_ptr, ldc, c_dtype, bias=None, act=0, c2=None, alpha=1
         e0, e1 = C.c_void_p(), C.c_void_p()
         _lib.call("polus_event_create", C.byref(e0))
         _lib.call("polus_event_create", C.byref(e1))
-        _lib.call("polus_event_record", e0, device.stream())
+        _lib.call("polus_event_record", e0, stream)
     if use_tc:
-        _lib.call("polus_gemm_tc", C.byref(g), device.stream())
+        _lib.call("polus_gemm_tc", C.byref(g), stream)
     else:
         g.split_k = 1
-        _lib.call("polus_gemm_small", C.byref(g), device.stream())
+        _lib.call("polus_gemm_small", C.byref(g), stream)
     if prof is not None:
-        _lib.call("polus_event_record", e1, device.stream())
+        _lib.call("polus_event_record", e1, stream)
         prof.append(("tc" if use_tc else "small", 2.0 * M * N * K * batch0 * batch1, e0, e1))
     return "tc" if use_tc else "small"
 
@@ -291,28 +358,43 @@ def linear(x, W, b=None, activation=None, out_dtype=None, defer_bias_grad=False)
     if use_tc:
         xb = cast(x, BF16)
         y = Tensor(lead + (N,), BF16)
-        z = Tensor(lead + (N,), BF16) if (act != 0 and tape is not None) else None
+        # with an activation the GEMM epilogue also stores act'(z) (not z): backward is then one multiply, which the
+        # dgrad GEMM of the layer that consumes y applies in its own epilogue together with the bias-gradient column
+        # sums (FUSE_ACT_BWD) -- no pass over the [M,N] tensor for GeluGrad / BiasAddGrad
+        d = Tensor(lead + (N,), BF16) if (act != 0 and tape is not None) else None
         _gemm(M, N, K, _operand(xb.ptr, K, False, BF16), _operand(W.shadow.ptr, N, True, BF16),
-              y.ptr, N, BF16, bias=b.ptr if b is not None else None, act=act, c2=z.ptr if z is not None else None)
+              y.ptr, N, BF16, bias=b.ptr if b is not None else None, act=act, c2=d.ptr if d is not None else None, c2_kind=1)
         if tape is not None:
-            def backward(g, xb=xb, z=z):
+            if d is not None and FUSE_ACT_BWD:
+                y.bwd_fuse = (d, b.grad if b is not None else None)
+
+            def backward(g, xb=xb, d=d):
                 g = cast(g, BF16)
                 need_dz = act != 0
-                dz = Tensor(g.shape, BF16) if need_dz else g
-                # defer_bias_grad: the consumer (layernorm_residual with x_bias=b) already added colsum(g) to b.grad
-                want_bias = b is not None and not (defer_bias_grad and act == 0)
+                if need_dz and g.fused_for == id(y):
+                    dz, need_dz, want_bias = g, False, False  # the producer of g already applied act' and summed the bias grad
+                else:
+                    dz = Tensor(g.shape, BF16) if need_dz else g
+                    # defer_bias_grad: the consumer (layernorm_residual with x_bias=b) already added colsum(g) to b.grad
+                    want_bias = b is not None and not (defer_bias_grad and act == 0)
                 if need_dz or want_bias:
-                    _lib.call("polus_act_bwd_colsum", g.ptr, z.ptr if z is not None else None, M, N, act,
+                    _lib.call("polus_act_bwd_colsum", g.ptr, d.ptr if d is not None else None, M, N, _lib.ACT_DERIV if need_dz else 0,
                               dz.ptr if need_dz else None, b.grad.ptr if want_bias else None, None, device.stream())
                 # dW[K,N] += x^T dz : A = x (MN-major over K), B = dz (MN-major over N), reduce over M
                 _gemm(K, N, M, _operand(xb.ptr, K, True, BF16), _operand(dz.ptr, N, True, BF16),
-                      W.grad.ptr, N, F32, accumulate=1, split_k=0)
+                      W.grad.ptr, N, F32, accumulate=1, split_k=0, stream=side_fork() if side_active() else None)
                 dx = None
                 if xb.requires_grad:
                     dx = Tensor(lead + (K,), BF16)
-                    # dx[M,K] = dz[M,N] . W[K,N]^T : both K-major over N
-                    _gemm(M, K, N, _operand(dz.ptr, N, False, BF16), _operand(W.shadow.ptr, N, False, BF16),
-                          dx.ptr, K, BF16)
+                    fuse = xb.bwd_fuse if (xb.bwd_fuse is not None and xb.consumers == 1) else None
+                    # dx[M,K] = dz[M,N] . W[K,N]^T : both K-major over N  (* act'(z_prev), + bias-grad column sums when fused)
+                    kind = _gemm(M, K, N, _operand(dz.ptr, N, False, BF16), _operand(W.shadow.ptr, N, False, BF16),
+                                 dx.ptr, K, BF16, emul=fuse[0].ptr if fuse else None,
+                                 colsum=fuse[1].ptr if (fuse and fuse[1] is not None) else None)
+                    if fuse and kind == "tc":
+                        dx.fused_for = id(xb)
+                    elif fuse:
+                        raise RuntimeError("fused activation backward needs the tcgen05 GEMM path")
                 return [dx, None, None]
             _record(tape, [xb, W, b], y, backward)
         return y
@@ -517,6 +599,7 @@ def attention(qkv, mask, n_heads, p_drop=0.0):
 
 
 FUSED_ATTENTION = __import__("os").environ.get("POLUS_FUSED_ATTN", "1") != "0"
+FUSE_ACT_BWD = __import__("os").environ.get("POLUS_FUSE_ACT_BWD", "1") != "0"
 
 
 def _attention_fused(qkv, mask, n_heads, p_drop):
@@ -535,7 +618,7 @@ def _attention_fused(qkv, mask, n_heads, p_drop):
               lse.ptr, kptr, device.stream())
     tape = _recording(qkv)
     if tape is not None:
-        def backward(g):
+        def backward(g, _alive=(keep, mask)):  # the closure uses raw pointers: keep their owners out of the pool
             g = cast(g, BF16)
             dqkv = Tensor((Bsz, S, H3), BF16)
             _lib.call("polus_attention_bwd", qkv.ptr, mptr, ctx.ptr, g.ptr, lse.ptr, Bsz, S, n_heads, dh, p_drop, seed, site,

@@ -147,6 +147,7 @@ class _CompiledStep:
     def capture(self):
         st = device.stream()
         ops.reset_dropout_sites()
+        ops.side_reset()
         self.blocks = tensor.begin_trace()
         try:
             _lib.call("polus_graph_begin", st)

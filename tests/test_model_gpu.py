@@ -56,7 +56,47 @@ def test_graph_replay_equals_eager(monkeypatch):
     np.testing.assert_allclose(lg, le, rtol=1e-3)
     for a, b in zip(wg, we):
         d = np.abs(a - b)
-        assert d.max() <= 5e-3 and d.mean() <= 1e-4, (d.max(), d.mean())
+        assert d.max() <= 5e-3 and d.mean() <= 2e-4, (d.max(), d.mean())
+
+
+@pytest.mark.gpu
+def test_graph_replay_gradients_equal_eager(monkeypatch):
+    """Sharp check of the captured step's scheduling (programmatic dependent launches, weight gradients on the
+    background stream, csrc/common.cuh + ops.side_fork): with lr = 0 the weights never move, so the gradients of
+    every step are a fixed function of (weights, batch, Philox counters) and Adam's first moment m after 4 steps
+    must agree between op-by-op execution and graph replay up to the order of fp32 atomic accumulation.  A kernel
+    that ran ahead of its producer (or a wgrad that read a recycled buffer) shows up as an O(1) relative error."""
+    from polus_b200 import ops, tensor
+    from polus_b200.models import BertConfig
+    from polus_b200.ner.models import BertNERModel
+    from polus_b200.optimizers import Adam
+    from polus_b200.training import ClassifierTrainer
+    from polus_b200.utils import set_random_seed
+    from tests.parity import make_batch
+
+    def run(eager):
+        monkeypatch.setenv("POLUS_EAGER", "1" if eager else "0")
+        tensor.reset_arena()
+        set_random_seed(5)
+        ops.set_step(0)
+        cfg = BertConfig(vocab_size=1000, hidden_size=256, num_hidden_layers=3, num_attention_heads=4, intermediate_size=1024,
+                         max_position_embeddings=128)
+        model = BertNERModel(cfg, output_classes=4)
+        rng = np.random.default_rng(0)
+        ids, mask, tt, tags = make_batch(rng, 8, 128, 1000, 4)
+        x = {"input_ids": ids, "attention_mask": mask, "token_type_ids": tt}
+        y = np.eye(4, dtype=np.float32)[tags]
+        opt = Adam(0.0)
+        tr = ClassifierTrainer(model, opt, model.loss)
+        losses = [float(tr.train_step(x, y)) for _ in range(4)]
+        m = opt.variables()[0].numpy()
+        return losses, m
+    le, me = run(True)
+    lg, mg = run(False)
+    np.testing.assert_allclose(lg, le, rtol=1e-5)
+    scale = np.abs(me).max()
+    assert scale > 0
+    assert np.abs(mg - me).max() <= 2e-4 * scale, (np.abs(mg - me).max(), scale)
 
 
 def test_tutorial_classifier_macro_f1():
