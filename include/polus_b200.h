@@ -158,16 +158,19 @@ size_t polus_embed_ws_floats(int B, int S, int H); /* size of d_ws above */
 int polus_ln_res_fwd(polus_bf16_t* d_x_inout, const polus_bf16_t* d_res, const float* d_gamma,
                      const float* d_beta, int M, int H, float eps, float p_drop, uint64_t seed,
                      uint32_t site, const uint32_t* d_step, polus_bf16_t* d_y, float* d_mean,
-                     float* d_rstd, void* stream);
+                     float* d_rstd, uint8_t* d_keepbits, void* stream);
+/* d_keepbits (may be NULL): [M * H/8] bytes, the dropout decisions of this call (bit j of byte c = element 8c+j kept);
+ * handing them to polus_ln_res_bwd saves it the Philox regeneration. */
 /* d(y) = d_dy (+ d_dy2 when not NULL: a second contribution from the residual stream, summed in-kernel).
  * Writes d_dx (through dropout) and d_dres (may be NULL; may alias d_dx when p_drop == 0); dgamma/dbeta are
  * accumulated; d_gbias_x (may be NULL) also receives the column sums of d_dx, i.e. the bias gradient of the Dense
- * layer that produced x, saving that layer a separate reduction pass.  d_ws is unused (kept for ABI stability). */
+ * layer that produced x, saving that layer a separate reduction pass.  d_keepbits: the forward call's dropout
+ * decisions, or NULL to regenerate them from (seed, site, *d_step). */
 int polus_ln_res_bwd(const polus_bf16_t* d_dy, const polus_bf16_t* d_dy2, const polus_bf16_t* d_z,
                      const float* d_mean, const float* d_rstd, const float* d_gamma, int M, int H, float p_drop,
                      uint64_t seed, uint32_t site, const uint32_t* d_step, polus_bf16_t* d_dx,
-                     polus_bf16_t* d_dres, float* d_ggamma, float* d_gbeta, float* d_gbias_x, float* d_ws,
-                     void* stream);
+                     polus_bf16_t* d_dres, float* d_ggamma, float* d_gbeta, float* d_gbias_x,
+                     const uint8_t* d_keepbits, void* stream);
 size_t polus_ln_ws_floats(int H);
 
 /* HF TFBertSelfAttention softmax: P = softmax(scores*scale + (1-mask)*-10000) (polus/models.py:
@@ -194,7 +197,9 @@ int polus_attention_fwd(const polus_bf16_t* d_qkv, const int32_t* d_mask, int B,
 int polus_attention_bwd(const polus_bf16_t* d_qkv, const int32_t* d_mask, const polus_bf16_t* d_ctx,
                         const polus_bf16_t* d_dctx, const float* d_lse, int B, int S, int nh, int head_dim,
                         float p_drop, uint64_t seed, uint32_t site, const uint32_t* d_step,
-                        const uint32_t* d_keepbits, polus_bf16_t* d_dqkv, void* stream);
+                        const uint32_t* d_keepbits, polus_bf16_t* d_dqkv, float* d_gbias_qkv, void* stream);
+/* d_gbias_qkv (may be NULL): [3*nh*head_dim] fp32, += column sums of d_dqkv -- the BiasAddGrad of the QKV projection
+ * (polus/training.py:185), taken from the tiles while they are still in shared memory. */
 
 /* dz = dy * act'(z); column sums of dz accumulated into d_gbias (bias gradient).
  * act == NONE with d_dz == NULL: bias gradient only.  d_ws: polus_colsum_ws_floats(N). */

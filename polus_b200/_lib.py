@@ -89,7 +89,7 @@ _SIGS = {
     "polus_embed_ln_bwd": [p, p, p, p, p, p, p, i32, i32, i32, i32, i32, f32, u64, u32, p, p, p, p, p, p, p, p],
     "polus_embed_ws_floats": [i32, i32, i32],
     "polus_add_bf16": [p, p, p, i64, p],
-    "polus_ln_res_fwd": [p, p, p, p, i32, i32, f32, f32, u64, u32, p, p, p, p, p],
+    "polus_ln_res_fwd": [p, p, p, p, i32, i32, f32, f32, u64, u32, p, p, p, p, p, p],
     "polus_ln_res_bwd": [p, p, p, p, p, p, i32, i32, f32, u64, u32, p, p, p, p, p, p, p, p],
     "polus_ln_ws_floats": [i32],
     "polus_softmax_fwd": [p, p, i32, i32, i32, i32, f32, f32, u64, u32, p, p, p, p],
@@ -97,7 +97,7 @@ _SIGS = {
     "polus_attention_supported": [i32, i32],
     "polus_attention_keepbits_words": [i32, i32, i32],
     "polus_attention_fwd": [p, p, i32, i32, i32, i32, f32, u64, u32, p, p, p, p, p],
-    "polus_attention_bwd": [p, p, p, p, p, i32, i32, i32, i32, f32, u64, u32, p, p, p, p],
+    "polus_attention_bwd": [p, p, p, p, p, i32, i32, i32, i32, f32, u64, u32, p, p, p, p, p],
     "polus_act_bwd_colsum": [p, p, i32, i32, i32, p, p, p, p],
     "polus_colsum_ws_floats": [i32],
     "polus_dropout": [p, p, i64, f32, u64, u32, p, p],

@@ -45,6 +45,7 @@ struct AttnParams {
     const int32_t* mask;   // [B,S] or null
     float* lse;            // [B,nh,S]
     uint32_t* keepbits;    // [B*nh*S][S/32] dropout keep bits (forward writes, backward reads); null when p = 0
+    float* gbias;          // backward: [3H] bias gradient of the QKV projection += column sums of dqkv; may be null
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -415,6 +416,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         const float sc = p.scale;
         uint32_t ph1 = 0;
         int blk = 0;
+        // bias gradient of the QKV projection = column sums of dQ | dK | dV: thread (w = lane, rg = e) adds the column pair
+        // (2w, 2w+1) over rows [16 rg, 16 rg + 16) of every drained tile, from the staged bf16 values
+        float bsum[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
         for (int j = 0; j < n_kh; ++j) {
             for (int i = 0; i < n_qt; ++i, ++blk) {
                 ptx::mbar_wait(&bars[1], ph1);
@@ -463,7 +467,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                 if (last_i || last_j) {
                     ptx::mbar_wait(&bars[3], blk & 1);  // this block's MMAs (incl. the accumulations) have retired
                     ptx::tc_fence_after();
-                    auto drain = [&](uint32_t col, int slot, int row0) {
+                    auto drain = [&](uint32_t col, int slot, int row0, float* bs) {
                         float v[32];
                         ptx::tmem_ld32(lane_addr + col + half * 32, v);
                         ptx::tmem_ld_wait();
@@ -478,17 +482,37 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                         if (half == 0 && lane == 0) {
                             ptx::tma_store_4d(&tmDQKV, sPd + quad * 4096, 0, row0 + quad * 32, slot, b);
                             ptx::tma_store_commit();
-                            ptx::tma_store_wait_read<0>();
                         }
+                        if (p.gbias != nullptr) {
+                            const int nrows = min(128, p.S - row0);
+#pragma unroll 4
+                            for (int rr = 0; rr < 16; ++rr) {
+                                const int r = e * 16 + rr;
+                                if (r < nrows) {
+                                    const uint32_t w = *reinterpret_cast<const uint32_t*>(sPd + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
+                                    bs[0] += __uint_as_float(w << 16);
+                                    bs[1] += __uint_as_float(w & 0xFFFF0000u);
+                                }
+                            }
+                        }
+                        if (half == 0 && lane == 0) ptx::tma_store_wait_read<0>();
                         named_bar_sync(1, 256);  // staging tile free again
                     };
                     if (last_i) {
-                        drain(C_DK, p.nh + h, j * 128);
-                        drain(C_DV, 2 * p.nh + h, j * 128);
+                        drain(C_DK, p.nh + h, j * 128, bsum[1]);
+                        drain(C_DV, 2 * p.nh + h, j * 128, bsum[2]);
                     }
-                    if (last_j) drain(i == 0 ? C_DQ0 : C_DQ1, h, i * 128);
+                    if (last_j) drain(i == 0 ? C_DQ0 : C_DQ1, h, i * 128, bsum[0]);
                     ptx::tc_fence_before();
                 }
+            }
+        }
+        if (p.gbias != nullptr) {
+#pragma unroll
+            for (int s3 = 0; s3 < 3; ++s3) {
+                float* gb = p.gbias + (s3 * p.nh + h) * DH + 2 * lane;
+                atomicAdd(gb, bsum[s3][0]);
+                atomicAdd(gb + 1, bsum[s3][1]);
             }
         }
     }
@@ -534,13 +558,14 @@ int head_map(CUtensorMap* m, const void* ptr, int B, int S, int slots, int box_r
 }
 
 AttnParams make_params(int B, int S, int nh, float p_drop, uint64_t seed, uint32_t site, const uint32_t* d_step,
-                       const int32_t* mask, float* lse, uint32_t* keepbits) {
+                       const int32_t* mask, float* lse, uint32_t* keepbits, float* gbias = nullptr) {
     AttnParams p;
     p.B = B; p.S = S; p.nh = nh;
     p.scale = 1.0f / sqrtf((float)DH);
     p.thresh16 = p_drop > 0.f ? (uint32_t)lrintf(p_drop * 65536.0f) : 0u;
     p.inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
     p.seed = seed; p.site = site; p.d_step = d_step; p.mask = mask; p.lse = lse; p.keepbits = keepbits;
+    p.gbias = gbias;
     return p;
 }
 
@@ -576,7 +601,7 @@ extern "C" int polus_attention_fwd(const polus_bf16_t* qkv, const int32_t* mask,
 extern "C" int polus_attention_bwd(const polus_bf16_t* qkv, const int32_t* mask, const polus_bf16_t* ctx,
                                    const polus_bf16_t* dctx, const float* lse, int B, int S, int nh, int dh, float p_drop,
                                    uint64_t seed, uint32_t site, const uint32_t* d_step, const uint32_t* keepbits,
-                                   polus_bf16_t* dqkv, void* stream) {
+                                   polus_bf16_t* dqkv, float* gbias_qkv, void* stream) {
     POLUS_REQUIRE(polus_attention_supported(S, dh), "polus_attention_bwd: needs head_dim 64 and S <= 256, S %% 32 == 0 (got S=%d dh=%d)", S, dh);
     POLUS_REQUIRE(p_drop == 0.f || keepbits != nullptr, "polus_attention_bwd: dropout needs the forward's keepbits");
     if (B == 0) return 0;
@@ -592,7 +617,7 @@ extern "C" int polus_attention_bwd(const polus_bf16_t* qkv, const int32_t* mask,
         POLUS_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
         set = true;
     }
-    AttnParams p = make_params(B, S, nh, p_drop, seed, site, d_step, mask, const_cast<float*>(lse), const_cast<uint32_t*>(keepbits));
+    AttnParams p = make_params(B, S, nh, p_drop, seed, site, d_step, mask, const_cast<float*>(lse), const_cast<uint32_t*>(keepbits), gbias_qkv);
     POLUS_CHECK_CUDA(polus_launch_pdl(attn_bwd_kernel, dim3(B * nh), dim3(BWD_THREADS), B_SMEM, (cudaStream_t)stream, tq, tdo, tdq, (const bf16*)ctx, (const bf16*)dctx, p));
     g_launch_count++;
     POLUS_LAUNCH_CHECK();

@@ -154,6 +154,45 @@ __device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint32_t site, 
     return m;
 }
 
+// The same decisions as dropout_keep8, applied directly to 8 fp32 values (v = keep ? v * inv_keep : 0) without building
+// the mask first: low lane of word i decides element 2i, high lane element 2i+1;  (w << 16) >= (t << 16)  <=>  lo >= t
+// and  w >= (t << 16)  <=>  hi >= t.  Returns the 8 keep bits (dead code unless the caller stores them).
+__device__ __forceinline__ uint32_t dropout_apply8(uint64_t seed, uint32_t site, uint32_t step, uint64_t idx8,
+                                                   uint32_t thresh16, float inv_keep, float* v) {
+    uint4 r = philox4x32_10(make_uint4((uint32_t)idx8, (uint32_t)(idx8 >> 32), site, step),
+                            make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    const uint32_t th = thresh16 << 16;
+    uint32_t bits = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const bool klo = (w[i] << 16) >= th;
+        const bool khi = w[i] >= th;
+        v[2 * i] = klo ? v[2 * i] * inv_keep : 0.f;
+        v[2 * i + 1] = khi ? v[2 * i + 1] * inv_keep : 0.f;
+        bits |= (klo ? 1u : 0u) << (2 * i);
+        bits |= (khi ? 1u : 0u) << (2 * i + 1);
+    }
+    return bits;
+}
+// dropout from stored keep bits (bit j = element j)
+__device__ __forceinline__ void dropout_apply8_bits(uint32_t bits, float inv_keep, float* v) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (bits & (1u << j)) ? v[j] * inv_keep : 0.f;
+}
+
+// explicit 128-bit global accesses (the struct-copy form sometimes splits into 32-bit stores)
+__device__ __forceinline__ void st_global16(void* p, const bf16x8& v) {
+    const uint32_t* u = reinterpret_cast<const uint32_t*>(&v);
+    asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]) : "memory");
+}
+__device__ __forceinline__ bf16x8 ld_global16(const void* p) {
+    bf16x8 r;
+    uint32_t* u = reinterpret_cast<uint32_t*>(&r);
+    asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]) : "l"(p));
+    return r;
+}
+
 // erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, below fp32 resolution of the GELU output); ~12 instructions
 // and branch-free (erff() diverges per element), which matters in the FFN-up GEMM epilogue.
 __device__ __forceinline__ float fast_erf(float x) {

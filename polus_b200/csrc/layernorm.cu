@@ -35,30 +35,40 @@ inline DropCfg make_drop(float p, uint64_t seed, uint32_t site) {
 }
 
 // ------------------------------------------------------------------------------ forward
-// NC = 16-byte chunks per lane (H <= 256*NC).  All global loads of a row are issued before any arithmetic and the
-// kernel is register-lean (4-warp CTAs, 8 CTAs/SM) because it is latency-bound: ncu showed 13 % of DRAM peak with
-// 20 resident warps and "long scoreboard" as the dominant stall (profiles/r01_ncu_full_summary_v1.txt).
-template <int NC>
-__global__ void __launch_bounds__(128, NC <= 3 ? 8 : (NC == 4 ? 6 : 1))
+// NC = 16-byte chunks per lane (H <= 256*NC); FULL: H == 256*NC exactly (no bounds checks: BERT-base 768, large 1024).
+// Instruction-bound as much as HBM-bound (ablation: profiles/r01_ablation_v8_marginal_costs.txt), so the code is
+// written for instruction count: all global loads of a row issued first, 128-bit accesses only, dropout applied straight
+// from the Philox words (keep bits saved, one byte per chunk, so that backward does not run Philox again), deviations
+// d = v - mean kept in place of v, gamma/beta staged in shared memory once per CTA.
+template <int NC, bool FULL>
+__global__ void __launch_bounds__(128, NC <= 3 ? 6 : (NC == 4 ? 4 : 1))
 ln_res_fwd_kernel(bf16* __restrict__ x, const bf16* __restrict__ res, const float* __restrict__ gamma,
                   const float* __restrict__ beta, int M, int H, float eps, DropCfg dc,
                   const uint32_t* __restrict__ d_step, bf16* __restrict__ y, float* __restrict__ mean_out,
-                  float* __restrict__ rstd_out) {
+                  float* __restrict__ rstd_out, uint8_t* __restrict__ keepbits) {
+    extern __shared__ float sgb[];  // gamma [H] | beta [H]
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int chunks = H >> 3;
     pdl_trigger();
+    // parameters are last written by the optimizer of the PREVIOUS step: safe to stage before the dependency wait
+    for (int i = threadIdx.x; i < (H >> 2); i += blockDim.x) {
+        reinterpret_cast<float4*>(sgb)[i] = __ldg(reinterpret_cast<const float4*>(gamma) + i);
+        reinterpret_cast<float4*>(sgb + H)[i] = __ldg(reinterpret_cast<const float4*>(beta) + i);
+    }
     pdl_wait();
+    __syncthreads();
     const uint32_t step = dc.thresh16 ? *d_step : 0u;
+    const float inv_h = 1.0f / (float)H;
     for (int row = blockIdx.x * 4 + warp; row < M; row += gridDim.x * 4) {
         const long long base = (long long)row * H;
         bf16x8 xr[NC], rr[NC];
 #pragma unroll
         for (int i = 0; i < NC; ++i) {
             const int c = lane + 32 * i;
-            if (c < chunks) {
+            if (FULL || c < chunks) {
                 xr[i] = ld_stream8(x + base + c * 8);
-                if (res != nullptr) rr[i] = *reinterpret_cast<const bf16x8*>(res + base + c * 8);
+                if (res != nullptr) rr[i] = ld_global16(res + base + c * 8);
             }
         }
         float v[NC][8];
@@ -66,12 +76,11 @@ ln_res_fwd_kernel(bf16* __restrict__ x, const bf16* __restrict__ res, const floa
 #pragma unroll
         for (int i = 0; i < NC; ++i) {
             const int c = lane + 32 * i;
-            if (c < chunks) {
+            if (FULL || c < chunks) {
                 unpack8(xr[i], v[i]);
                 if (dc.thresh16) {
-                    const uint32_t keep = dropout_keep8(dc.seed, dc.site, step, (unsigned long long)row * chunks + c, dc.thresh16);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) v[i][j] = ((keep >> j) & 1u) ? v[i][j] * dc.inv_keep : 0.f;
+                    const uint32_t bits = dropout_apply8(dc.seed, dc.site, step, (unsigned long long)row * chunks + c, dc.thresh16, dc.inv_keep, v[i]);
+                    if (keepbits != nullptr) keepbits[(long long)row * chunks + c] = (uint8_t)bits;
                 }
                 if (res != nullptr) {
                     float rv[8];
@@ -81,22 +90,22 @@ ln_res_fwd_kernel(bf16* __restrict__ x, const bf16* __restrict__ res, const floa
                 }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) sum += v[i][j];
-                *reinterpret_cast<bf16x8*>(x + base + c * 8) = pack8(v[i]);  // z, kept for backward
+                st_global16(x + base + c * 8, pack8(v[i]));  // z, kept for backward
             }
         }
-        const float mean = warp_sum(sum) / (float)H;
+        const float mean = warp_sum(sum) * inv_h;
         float sq = 0.f;
 #pragma unroll
         for (int i = 0; i < NC; ++i) {
-            if (lane + 32 * i < chunks) {
+            if (FULL || lane + 32 * i < chunks) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float d = v[i][j] - mean;
-                    sq += d * d;
+                    v[i][j] -= mean;
+                    sq = fmaf(v[i][j], v[i][j], sq);
                 }
             }
         }
-        const float rstd = rsqrtf(warp_sum(sq) / (float)H + eps);
+        const float rstd = rsqrtf(warp_sum(sq) * inv_h + eps);
         if (lane == 0) {
             mean_out[row] = mean;
             rstd_out[row] = rstd;
@@ -104,17 +113,15 @@ ln_res_fwd_kernel(bf16* __restrict__ x, const bf16* __restrict__ res, const floa
 #pragma unroll
         for (int i = 0; i < NC; ++i) {
             const int c = lane + 32 * i;
-            if (c < chunks) {
+            if (FULL || c < chunks) {
                 float o[8];
-                const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c * 8));
-                const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c * 8) + 1);
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c * 8));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c * 8) + 1);
+                const float4 g0 = reinterpret_cast<const float4*>(sgb + c * 8)[0], g1 = reinterpret_cast<const float4*>(sgb + c * 8)[1];
+                const float4 b0 = reinterpret_cast<const float4*>(sgb + H + c * 8)[0], b1 = reinterpret_cast<const float4*>(sgb + H + c * 8)[1];
                 const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
                 const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * g[j] + b[j];
-                *reinterpret_cast<bf16x8*>(y + base + c * 8) = pack8(o);
+                for (int j = 0; j < 8; ++j) o[j] = fmaf(v[i][j] * rstd, g[j], b[j]);
+                st_global16(y + base + c * 8, pack8(o));
             }
         }
     }
@@ -126,40 +133,49 @@ ln_res_fwd_kernel(bf16* __restrict__ x, const bf16* __restrict__ res, const floa
 // kernel at <= 128 registers => two 8-warp CTAs per SM.  Per-warp register partials of dgamma = sum dy*xhat,
 // dbeta = sum dy and (optionally) dbias = sum dx -- the bias gradient of the Dense layer that produced x -- are
 // reduced per CTA in shared memory and added to the gradient arena with one fp32 atomic per column per CTA.
-template <int NC>
+// keepbits: the forward kernel's dropout decisions (one byte per chunk); NULL => regenerated with Philox.
+template <int NC, bool FULL>
 __global__ void __launch_bounds__(kWarps * 32, NC <= 4 ? 2 : 1)
 ln_res_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, const bf16* __restrict__ z, const float* __restrict__ mean_in,
                   const float* __restrict__ rstd_in, const float* __restrict__ gamma, int M, int H, DropCfg dc,
                   const uint32_t* __restrict__ d_step, bf16* __restrict__ dx, bf16* __restrict__ dres,
-                  float* __restrict__ ggamma, float* __restrict__ gbeta, float* __restrict__ gbias) {
-    extern __shared__ float red[];  // [kWarps][H]
+                  float* __restrict__ ggamma, float* __restrict__ gbeta, float* __restrict__ gbias,
+                  const uint8_t* __restrict__ keepbits) {
+    extern __shared__ float red[];  // [kWarps][H] reduction scratch | gamma [H]
+    float* sg = red + kWarps * H;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int chunks = H >> 3;
     pdl_trigger();
+    for (int i = threadIdx.x; i < (H >> 2); i += blockDim.x)
+        reinterpret_cast<float4*>(sg)[i] = __ldg(reinterpret_cast<const float4*>(gamma) + i);
     float dg[NC][8], db[NC][8], dxs[NC][8];
 #pragma unroll
     for (int i = 0; i < NC; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) dg[i][j] = db[i][j] = dxs[i][j] = 0.f;
     pdl_wait();
+    __syncthreads();
     const uint32_t step = dc.thresh16 ? *d_step : 0u;
+    const float inv_h = 1.0f / (float)H;
     for (int row = blockIdx.x * kWarps + warp; row < M; row += gridDim.x * kWarps) {
         const long long base = (long long)row * H;
         bf16x8 dyr[NC], zr[NC];
+        uint32_t kb[NC];
 #pragma unroll
         for (int i = 0; i < NC; ++i) {
             const int c = lane + 32 * i;
-            if (c < chunks) {
+            if (FULL || c < chunks) {
                 dyr[i] = ld_stream8(dy + base + c * 8);
                 zr[i] = ld_stream8(z + base + c * 8);
+                if (dc.thresh16 && keepbits != nullptr) kb[i] = keepbits[(long long)row * chunks + c];
             }
         }
         if (dy2 != nullptr) {  // second contribution to d(y) (residual stream): summed here, no add kernel
 #pragma unroll
             for (int i = 0; i < NC; ++i) {
                 const int c = lane + 32 * i;
-                if (c < chunks) {
+                if (FULL || c < chunks) {
                     float a[8], b2[8];
                     unpack8(dyr[i], a);
                     unpack8(ld_stream8(dy2 + base + c * 8), b2);
@@ -169,53 +185,51 @@ ln_res_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, con
                 }
             }
         }
-        const float mean = mean_in[row], rstd = rstd_in[row];
+        const float rstd = rstd_in[row];
+        const float nmr = -mean_in[row] * rstd;
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int i = 0; i < NC; ++i) {
             const int c = lane + 32 * i;
-            if (c < chunks) {
+            if (FULL || c < chunks) {
                 float dyv[8], zv[8];
                 unpack8(dyr[i], dyv);
                 unpack8(zr[i], zv);
-                const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c * 8));
-                const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c * 8) + 1);
+                const float4 g0 = reinterpret_cast<const float4*>(sg + c * 8)[0], g1 = reinterpret_cast<const float4*>(sg + c * 8)[1];
                 const float gam[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float xh = (zv[j] - mean) * rstd;
+                    const float xh = fmaf(zv[j], rstd, nmr);
                     const float g = dyv[j] * gam[j];
                     s1 += g;
-                    s2 += g * xh;
-                    dg[i][j] += dyv[j] * xh;
+                    s2 = fmaf(g, xh, s2);
+                    dg[i][j] = fmaf(dyv[j], xh, dg[i][j]);
                     db[i][j] += dyv[j];
                 }
             }
         }
-        s1 = warp_sum(s1) / (float)H;
-        s2 = warp_sum(s2) / (float)H;
+        const float c1 = warp_sum(s1) * inv_h * rstd;
+        const float c2 = warp_sum(s2) * inv_h * rstd;
 #pragma unroll
         for (int i = 0; i < NC; ++i) {
             const int c = lane + 32 * i;
-            if (c < chunks) {
+            if (FULL || c < chunks) {
                 float dyv[8], zv[8], dz[8];
                 unpack8(dyr[i], dyv);
                 unpack8(zr[i], zv);
-                const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c * 8));
-                const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c * 8) + 1);
+                const float4 g0 = reinterpret_cast<const float4*>(sg + c * 8)[0], g1 = reinterpret_cast<const float4*>(sg + c * 8)[1];
                 const float gam[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float xh = (zv[j] - mean) * rstd;
-                    dz[j] = rstd * (dyv[j] * gam[j] - s1 - xh * s2);
+                    const float xh = fmaf(zv[j], rstd, nmr);
+                    dz[j] = fmaf(-xh, c2, fmaf(dyv[j] * gam[j], rstd, -c1));  // rstd * (g - mean(g) - xhat * mean(g xhat))
                 }
-                if (dres != nullptr && dres != dx) *reinterpret_cast<bf16x8*>(dres + base + c * 8) = pack8(dz);
+                if (dres != nullptr && dres != dx) st_global16(dres + base + c * 8, pack8(dz));
                 if (dc.thresh16) {
-                    const uint32_t keep = dropout_keep8(dc.seed, dc.site, step, (unsigned long long)row * chunks + c, dc.thresh16);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) dz[j] = ((keep >> j) & 1u) ? dz[j] * dc.inv_keep : 0.f;
+                    if (keepbits != nullptr) dropout_apply8_bits(kb[i], dc.inv_keep, dz);
+                    else dropout_apply8(dc.seed, dc.site, step, (unsigned long long)row * chunks + c, dc.thresh16, dc.inv_keep, dz);
                 }
-                *reinterpret_cast<bf16x8*>(dx + base + c * 8) = pack8(dz);
+                st_global16(dx + base + c * 8, pack8(dz));
                 if (gbias != nullptr) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) dxs[i][j] += dz[j];
@@ -231,9 +245,11 @@ ln_res_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, con
 #pragma unroll
         for (int i = 0; i < NC; ++i) {
             const int c = lane + 32 * i;
-            if (c < chunks) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) red[warp * H + c * 8 + j] = which == 0 ? dg[i][j] : (which == 1 ? db[i][j] : dxs[i][j]);
+            if (FULL || c < chunks) {
+                float* r8 = red + warp * H + c * 8;
+                const float* src = which == 0 ? dg[i] : (which == 1 ? db[i] : dxs[i]);
+                reinterpret_cast<float4*>(r8)[0] = make_float4(src[0], src[1], src[2], src[3]);
+                reinterpret_cast<float4*>(r8)[1] = make_float4(src[4], src[5], src[6], src[7]);
             }
         }
         __syncthreads();
@@ -465,7 +481,7 @@ extern "C" size_t polus_ln_ws_floats(int H) { return (size_t)kBwdBlocks * 2 * (s
 
 extern "C" int polus_ln_res_fwd(polus_bf16_t* x, const polus_bf16_t* res, const float* gamma, const float* beta, int M,
                                 int H, float eps, float p_drop, uint64_t seed, uint32_t site, const uint32_t* d_step,
-                                polus_bf16_t* y, float* mean, float* rstd, void* stream) {
+                                polus_bf16_t* y, float* mean, float* rstd, uint8_t* keepbits, void* stream) {
     POLUS_REQUIRE(M >= 0 && H > 0 && H % 8 == 0 && H <= 4096, "polus_ln_res_fwd: H must be a multiple of 8 and <= 4096 (got %d)", H);
     POLUS_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "polus_ln_res_fwd: bad dropout %f", p_drop);
     POLUS_REQUIRE(p_drop == 0.f || d_step != nullptr, "polus_ln_res_fwd: dropout needs d_step");
@@ -476,8 +492,10 @@ extern "C" int polus_ln_res_fwd(polus_bf16_t* x, const polus_bf16_t* res, const 
     const int cap = polus_num_sms() * 16;
     if (grid > cap) grid = cap;
     const int nc = cdiv(H, 256);
-#define LN_FWD(NC_) POLUS_CHECK_CUDA(polus_launch_pdl(ln_res_fwd_kernel<NC_>, dim3(grid), dim3(128), 0, st, (bf16*)x, (const bf16*)res, gamma, beta, M, H, eps, dc, d_step, (bf16*)y, mean, rstd))
-    if (nc <= 1) LN_FWD(1); else if (nc == 2) LN_FWD(2); else if (nc == 3) LN_FWD(3); else if (nc == 4) LN_FWD(4); else LN_FWD(16);
+    const size_t smem_f = (size_t)2 * H * sizeof(float);
+#define LN_FWD(NC_, FULL_) POLUS_CHECK_CUDA(polus_launch_pdl(ln_res_fwd_kernel<NC_, FULL_>, dim3(grid), dim3(128), smem_f, st, (bf16*)x, (const bf16*)res, gamma, beta, M, H, eps, dc, d_step, (bf16*)y, mean, rstd, keepbits))
+    if (H == 768) LN_FWD(3, true); else if (H == 1024) LN_FWD(4, true); else if (H == 256) LN_FWD(1, true); else if (H == 512) LN_FWD(2, true);
+    else if (nc <= 1) LN_FWD(1, false); else if (nc == 2) LN_FWD(2, false); else if (nc == 3) LN_FWD(3, false); else if (nc == 4) LN_FWD(4, false); else LN_FWD(16, false);
 #undef LN_FWD
     g_launch_count++;
     POLUS_LAUNCH_CHECK();
@@ -487,9 +505,8 @@ extern "C" int polus_ln_res_fwd(polus_bf16_t* x, const polus_bf16_t* res, const 
 extern "C" int polus_ln_res_bwd(const polus_bf16_t* dy, const polus_bf16_t* dy2, const polus_bf16_t* z, const float* mean,
                                 const float* rstd, const float* gamma, int M, int H, float p_drop, uint64_t seed,
                                 uint32_t site, const uint32_t* d_step, polus_bf16_t* dx, polus_bf16_t* dres,
-                                float* ggamma, float* gbeta, float* gbias_x, float* ws, void* stream) {
+                                float* ggamma, float* gbeta, float* gbias_x, const uint8_t* keepbits, void* stream) {
     POLUS_REQUIRE(M >= 0 && H > 0 && H % 8 == 0 && H <= 4096, "polus_ln_res_bwd: H must be a multiple of 8 and <= 4096 (got %d)", H);
-    (void)ws;
     POLUS_REQUIRE(dx != nullptr, "polus_ln_res_bwd: dx required");
     POLUS_REQUIRE(!(p_drop > 0.f && dres == dx), "polus_ln_res_bwd: dres may alias dx only without dropout");
     if (M == 0) return 0;
@@ -497,15 +514,16 @@ extern "C" int polus_ln_res_bwd(const polus_bf16_t* dy, const polus_bf16_t* dy2,
     cudaStream_t st = (cudaStream_t)stream;
     int grid = grid_for_rows(M);
     if (grid > kBwdBlocks) grid = kBwdBlocks;
-    const size_t smem = (size_t)kWarps * H * sizeof(float);
+    const size_t smem = (size_t)(kWarps + 1) * H * sizeof(float);
     const int nc = cdiv(H, 256);
-#define LN_BWD(NC_)                                                                                                            \
+#define LN_BWD(NC_, FULL_)                                                                                                     \
     {                                                                                                                          \
-        if (smem > 48 * 1024) POLUS_CHECK_CUDA(cudaFuncSetAttribute(ln_res_bwd_kernel<NC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        POLUS_CHECK_CUDA(polus_launch_pdl(ln_res_bwd_kernel<NC_>, dim3(grid), dim3(kWarps * 32), smem, st, (const bf16*)dy, (const bf16*)dy2, (const bf16*)z, mean, rstd, gamma, M, H, dc, \
-                                                               d_step, (bf16*)dx, (bf16*)dres, ggamma, gbeta, gbias_x));       \
+        if (smem > 48 * 1024) POLUS_CHECK_CUDA(cudaFuncSetAttribute(ln_res_bwd_kernel<NC_, FULL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        POLUS_CHECK_CUDA(polus_launch_pdl(ln_res_bwd_kernel<NC_, FULL_>, dim3(grid), dim3(kWarps * 32), smem, st, (const bf16*)dy, (const bf16*)dy2, (const bf16*)z, mean, rstd, gamma, M, H, dc, \
+                                          d_step, (bf16*)dx, (bf16*)dres, ggamma, gbeta, gbias_x, keepbits));                  \
     }
-    if (nc <= 1) LN_BWD(1) else if (nc == 2) LN_BWD(2) else if (nc == 3) LN_BWD(3) else if (nc == 4) LN_BWD(4) else LN_BWD(16)
+    if (H == 768) LN_BWD(3, true) else if (H == 1024) LN_BWD(4, true) else if (H == 256) LN_BWD(1, true) else if (H == 512) LN_BWD(2, true)
+    else if (nc <= 1) LN_BWD(1, false) else if (nc == 2) LN_BWD(2, false) else if (nc == 3) LN_BWD(3, false) else if (nc == 4) LN_BWD(4, false) else LN_BWD(16, false)
 #undef LN_BWD
     g_launch_count++;
     POLUS_LAUNCH_CHECK();

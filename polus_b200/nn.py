@@ -304,8 +304,10 @@ class BertLayer(Layer):
         x = ops.cast(as_tensor(hidden_states), BF16)
         pa = c.attention_probs_dropout_prob if training else 0.0
         ph = c.hidden_dropout_prob if training else 0.0
-        qkv = ops.linear(x, self.Wqkv, self.bqkv)
-        ctx = ops.attention(qkv, attention_mask, c.num_attention_heads, pa)
+        # fused attention backward also sums the QKV bias gradient from the dQ|dK|dV tiles it holds in shared memory
+        fuse_b = ops.attention_takes_bias_grad(x.shape[-2], c.hidden_size // c.num_attention_heads)
+        qkv = ops.linear(x, self.Wqkv, self.bqkv, defer_bias_grad=fuse_b)
+        ctx = ops.attention(qkv, attention_mask, c.num_attention_heads, pa, qkv_bias=self.bqkv if fuse_b else None)
         # the two Dense layers feeding a LayerNorm leave their bias gradient to the LayerNorm backward kernel
         ao = ops.linear(ctx, self.Wo, self.bo, defer_bias_grad=True)
         h1 = ops.layernorm_residual(ao, x, self.ln1_g, self.ln1_b, c.layer_norm_eps, ph, x_bias=self.bo)

@@ -511,9 +511,11 @@ def layernorm_residual(x, res, gamma, beta, eps=1e-12, p_drop=0.0, x_bias=None):
     mean, rstd = Tensor((M,), F32), Tensor((M,), F32)
     site = _next_site() if p_drop > 0 else 0
     seed = _rng_state["seed"]
-    _lib.call("polus_ln_res_fwd", x.ptr, res.ptr if res is not None else None, gamma.ptr, beta.ptr, M, H, eps, p_drop,
-              seed, site, step_counter(), y.ptr, mean.ptr, rstd.ptr, device.stream())
     tape = _recording(x, res, gamma, beta)
+    # dropout decisions, one byte per 8 elements, handed to backward (saves it the Philox regeneration)
+    keep = Tensor((M * (H // 8),), U8) if (p_drop > 0 and tape is not None) else None
+    _lib.call("polus_ln_res_fwd", x.ptr, res.ptr if res is not None else None, gamma.ptr, beta.ptr, M, H, eps, p_drop,
+              seed, site, step_counter(), y.ptr, mean.ptr, rstd.ptr, keep.ptr if keep is not None else None, device.stream())
     if tape is not None:
         z = x  # now holds dropout(x) + res
 
@@ -532,15 +534,15 @@ def layernorm_residual(x, res, gamma, beta, eps=1e-12, p_drop=0.0, x_bias=None):
                 dres = dx  # identical values: write once
             _lib.call("polus_ln_res_bwd", g.ptr, g2.ptr if g2 is not None else None, z.ptr, mean.ptr, rstd.ptr, gamma.ptr,
                       M, H, p_drop, seed, site, step_counter(), dx.ptr, dres.ptr if dres is not None else None,
-                      gamma.grad.ptr, beta.grad.ptr, x_bias.grad.ptr if x_bias is not None else None, None,
-                      device.stream())
+                      gamma.grad.ptr, beta.grad.ptr, x_bias.grad.ptr if x_bias is not None else None,
+                      keep.ptr if keep is not None else None, device.stream())
             return [dx, dres, None, None]
         backward.pair_ok = True
         _record(tape, [x, res, gamma, beta], y, backward)
     return y
 
 
-def attention(qkv, mask, n_heads, p_drop=0.0):
+def attention(qkv, mask, n_heads, p_drop=0.0, qkv_bias=None):
     """Multi-head self-attention core on the packed projection qkv [B,S,3H] (q|k|v column blocks):
     softmax(QK^T/sqrt(dh) + (1-mask)*-10000) V  ->  ctx [B,S,H]   (HF TFBertSelfAttention; mask constant
     from polus/models.py:175-195).  Three batched tcgen05 GEMM launches + one softmax launch; the head
@@ -551,7 +553,7 @@ def attention(qkv, mask, n_heads, p_drop=0.0):
     assert dh % 8 == 0 and S % 8 == 0, "attention needs head_dim and sequence length multiples of 8"
     qkv = cast(qkv, BF16)
     if FUSED_ATTENTION and _lib.call("polus_attention_supported", S, dh) == 1:
-        return _attention_fused(qkv, mask, n_heads, p_drop)
+        return _attention_fused(qkv, mask, n_heads, p_drop, qkv_bias)
     nb = Bsz * n_heads
     scale = 1.0 / math.sqrt(dh)
     q_ptr, k_ptr, v_ptr = qkv.ptr, qkv.ptr + H * 2, qkv.ptr + 2 * H * 2
@@ -602,7 +604,13 @@ FUSED_ATTENTION = __import__("os").environ.get("POLUS_FUSED_ATTN", "1") != "0"
 FUSE_ACT_BWD = __import__("os").environ.get("POLUS_FUSE_ACT_BWD", "1") != "0"
 
 
-def _attention_fused(qkv, mask, n_heads, p_drop):
+def attention_takes_bias_grad(S, head_dim):
+    """True when ops.attention(..., qkv_bias=b) will accumulate b's gradient itself (fused kernels): the caller then
+    builds the QKV projection with defer_bias_grad=True."""
+    return bool(FUSED_ATTENTION and head_dim % 8 == 0 and S % 8 == 0 and _lib.call("polus_attention_supported", S, head_dim) == 1)
+
+
+def _attention_fused(qkv, mask, n_heads, p_drop, qkv_bias=None):
     """One kernel per direction: scores and probabilities stay in TMEM / shared memory (csrc/attention.cu)."""
     Bsz, S, H3 = qkv.shape
     H = H3 // 3
@@ -622,7 +630,7 @@ def _attention_fused(qkv, mask, n_heads, p_drop):
             g = cast(g, BF16)
             dqkv = Tensor((Bsz, S, H3), BF16)
             _lib.call("polus_attention_bwd", qkv.ptr, mptr, ctx.ptr, g.ptr, lse.ptr, Bsz, S, n_heads, dh, p_drop, seed, site,
-                      step_counter(), kptr, dqkv.ptr, device.stream())
+                      step_counter(), kptr, dqkv.ptr, qkv_bias.grad.ptr if qkv_bias is not None else None, device.stream())
             return [dqkv]
         _record(tape, [qkv], ctx, backward)
     return ctx

@@ -44,13 +44,23 @@ def test_error_convention_without_gpu():
     assert _lib.last_error() != ""
 
 
-def test_struct_layout_matches_header():
-    """ctypes mirrors of polus_gemm_t / polus_adam_cfg_t: sizes the C compiler would produce."""
+def test_struct_layout_matches_header(tmp_path):
+    """ctypes mirrors of polus_gemm_t / polus_operand_t / polus_adam_cfg_t against what the C compiler makes of
+    include/polus_b200.h: sizes and the offsets of every field a caller sets."""
     import ctypes as C
+    import subprocess
     from polus_b200 import _lib
-    assert C.sizeof(_lib.Operand) == 40
-    assert C.sizeof(_lib.Gemm) == 20 + 4 + 80 + 8 + 24 + 8 + 8 + 8 + 16  # incl. alignment padding
-    assert C.sizeof(_lib.AdamCfg) == 40
+    fields = ["M", "K", "batch1", "A", "B", "C", "ldc", "c_dtype", "C2", "bias", "alpha", "act", "accumulate", "split_k",
+              "c2_kind", "Emul", "colsum"]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "polus_b200.h"\nint main(void){\n'
+                   'printf("%zu %zu %zu\\n", sizeof(polus_operand_t), sizeof(polus_gemm_t), sizeof(polus_adam_cfg_t));\n'
+                   + "".join(f'printf("%zu\\n", offsetof(polus_gemm_t, {f}));\n' for f in fields) + "return 0;}\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert [C.sizeof(_lib.Operand), C.sizeof(_lib.Gemm), C.sizeof(_lib.AdamCfg)] == [int(x) for x in out[:3]]
+    assert [getattr(_lib.Gemm, f).offset for f in fields] == [int(x) for x in out[3:]]
 
 
 def test_product_path_never_imports_the_oracle():

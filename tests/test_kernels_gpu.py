@@ -76,7 +76,10 @@ def test_ln_residual_fwd_bwd(dev, M, H, p):
     dx_t, dres_t = new((M, H), BF16), new((M, H), BF16)
     x_t, res_t, g_t, b_t, y_t = T(x, BF16), T(res, BF16), T(gamma), T(beta), new((M, H), BF16)
     mean_t, rstd_t = new((M,), F32), new((M,), F32)
-    call("polus_ln_res_fwd", x_t.ptr, res_t.ptr, g_t.ptr, b_t.ptr, M, H, 1e-12, p, seed, site, sp, y_t.ptr, mean_t.ptr, rstd_t.ptr, st())
+    from polus_b200.tensor import U8
+    keep_t = new((max(M * (H // 8), 1),), U8)
+    call("polus_ln_res_fwd", x_t.ptr, res_t.ptr, g_t.ptr, b_t.ptr, M, H, 1e-12, p, seed, site, sp, y_t.ptr, mean_t.ptr, rstd_t.ptr,
+         keep_t.ptr if p > 0 else None, st())
     if M == 0:
         return
     mask = philox.dropout_scale_mask((M, H), p, seed, site, step) if p > 0 else np.ones((M, H), np.float32)
@@ -93,7 +96,14 @@ def test_ln_residual_fwd_bwd(dev, M, H, p):
     dy_b = dev.bf16_round((dy - dy_a).astype(np.float32))
     dy = dy_a + dy_b
     call("polus_ln_res_bwd", T(dy_a, BF16).ptr, T(dy_b, BF16).ptr, x_t.ptr, mean_t.ptr, rstd_t.ptr, g_t.ptr, M, H, p, seed,
-         site, sp, dx_t.ptr, dres_t.ptr, ggam.ptr, gbet.ptr, gbx.ptr, None, st())
+         site, sp, dx_t.ptr, dres_t.ptr, ggam.ptr, gbet.ptr, gbx.ptr, keep_t.ptr if p > 0 else None, st())
+    if p > 0:  # keep bits are exactly the oracle's Philox decisions; regenerating them in-kernel gives the same dx
+        bits = np.unpackbits(keep_t.numpy()[:M * (H // 8)].reshape(M, H // 8, 1), axis=2, bitorder="little").reshape(M, H)
+        assert np.array_equal(bits.astype(bool), mask > 0)
+        dx2_t = new((M, H), BF16)
+        call("polus_ln_res_bwd", T(dy_a, BF16).ptr, T(dy_b, BF16).ptr, x_t.ptr, mean_t.ptr, rstd_t.ptr, g_t.ptr, M, H, p, seed,
+             site, sp, dx2_t.ptr, dres_t.ptr, new((H,), F32).ptr, new((H,), F32).ptr, None, None, st())
+        assert np.array_equal(dx2_t.numpy(), dx_t.numpy())
     _, cache_dev = R.layer_norm(z_dev.astype(np.float64), gamma, beta)
     dz_ref, gg_ref, gb_ref = R.layer_norm_bwd(dy.astype(np.float64), cache_dev, gamma)
     tol = 3 * BF16_EPS * (1 + np.abs(dz_ref).max())
@@ -480,6 +490,9 @@ def test_fused_attention_fwd_bwd(dev, B, nh, S, p, use_mask):
     ops.set_seed(77)
     ops.set_step(3)
 
+    from polus_b200.tensor import Param
+    bias = Param(np.zeros(3 * H, np.float32), name="qkv_bias")  # only its .grad is touched
+
     def run(fused):
         ops.FUSED_ATTENTION = fused
         ops.reset_dropout_sites()
@@ -487,7 +500,7 @@ def test_fused_attention_fwd_bwd(dev, B, nh, S, p, use_mask):
         x.requires_grad = True
         m = Tensor.from_numpy(mask, I32) if use_mask else None
         with ops.GradientTape() as tape:
-            ctx = ops.attention(x, m, nh, p)
+            ctx = ops.attention(x, m, nh, p, qkv_bias=bias if fused else None)
         # seed the backward with dctx: d(sum(ctx*dctx))
         tape.nodes[-1].output = ctx
         g = tape.nodes[-1].backward(Tensor.from_numpy(dctx, BF16))[0]
@@ -497,6 +510,9 @@ def test_fused_attention_fwd_bwd(dev, B, nh, S, p, use_mask):
         ctx_u, dq_u = run(False)
     finally:
         ops.FUSED_ATTENTION = True
+    # the fused backward also accumulates the QKV bias gradient = column sums of the dqkv it stored
+    gb_ref = dq_f.astype(np.float64).reshape(-1, 3 * H).sum(0)
+    np.testing.assert_allclose(bias.grad.numpy(), gb_ref, rtol=1e-4, atol=1e-4 * (np.abs(gb_ref).max() + 1))
     # oracle (float64) with the same dropout mask (site 1 of this step)
     q, k, v = [qkv[..., i * H:(i + 1) * H].reshape(B, S, nh, dh).transpose(0, 2, 1, 3).astype(np.float64) for i in range(3)]
     sc = q @ k.transpose(0, 1, 3, 2) / 8.0 + (R.attention_mask_additive(mask) if use_mask else 0.0)
