@@ -193,24 +193,33 @@ __device__ __forceinline__ bf16x8 ld_global16(const void* p) {
     return r;
 }
 
-// erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, below fp32 resolution of the GELU output); ~12 instructions
-// and branch-free (erff() diverges per element), which matters in the FFN-up GEMM epilogue.
-__device__ __forceinline__ float fast_erf(float x) {
-    const float u = fabsf(x);
-    float t;  // MUFU.RCP (approximate, 1 ulp): the IEEE __frcp_rn is a multi-instruction subroutine
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, u, 1.0f)));
-    float poly = fmaf(t, 1.061405429f, -1.453152027f);
-    poly = fmaf(t, poly, 1.421413741f);
-    poly = fmaf(t, poly, -0.284496736f);
-    poly = fmaf(t, poly, 0.254829592f);
-    const float r = 1.0f - poly * t * __expf(-u * u);
-    return copysignf(r, x);
+// Exact-erf GELU pieces (HF hidden_act="gelu"), written for instruction count -- the FFN-up GEMM epilogue is bound by
+// FMA-pipe issue slots, not by MUFU (tools/ubench/alu.cu: FFMA 113/clk/SM, MUFU 16/clk/SM, concurrent).
+//   erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7): erf|u| = 1 - (a1 t + .. + a5 t^5) exp(-u^2), t = 1/(1 + p u), u = |x|/sqrt2.
+//   phi = exp(-x^2/2)/sqrt(2 pi) comes out of ONE ex2 (its log2 prescale folded into the exponent FFMA) and the
+//   polynomial coefficients carry the factor sqrt(2 pi)/2, so that h = poly(t) t phi = (1 - erf|u|)/2 and
+//   Phi(x) = 1/2 + copysign(1/2 - h, x).  15 FMA/ALU instructions + 2 MUFU for y = x Phi and y' = Phi + x phi together
+//   (was 21; max abs error vs fp64: 5e-7, checked in numpy).
+__device__ __forceinline__ void gelu_cdf_pdf(float x, float& cdf, float& pdf) {
+    float t, e;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(fabsf(x), 0.3275911f * 0.70710678118654752f, 1.0f)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(x * x, -0.7213475108146667f, -1.325748085975647f)));
+    float poly = fmaf(t, 1.3302744626998901f, -1.8212559223175049f);
+    poly = fmaf(t, poly, 1.781477928161621f);
+    poly = fmaf(t, poly, -0.3565637767314911f);
+    poly = fmaf(t, poly, 0.3193815350532532f);
+    const float r = fmaf(-poly * t, e, 0.5f);  // 1/2 - h
+    cdf = 0.5f + copysignf(r, x);
+    pdf = e;
 }
-
 // activations (polus_act_t)
 __device__ __forceinline__ float act_fwd(int act, float x) {
     switch (act) {
-        case POLUS_ACT_GELU: return 0.5f * x * (1.0f + fast_erf(x * 0.70710678118654752f));
+        case POLUS_ACT_GELU: {
+            float cdf, pdf;
+            gelu_cdf_pdf(x, cdf, pdf);
+            return x * cdf;
+        }
         case POLUS_ACT_RELU: return fmaxf(x, 0.0f);
         case POLUS_ACT_SWISH: return x / (1.0f + __expf(-x));
         case POLUS_ACT_TANH: return tanhf(x);
@@ -223,19 +232,10 @@ __device__ __forceinline__ float act_fwd(int act, float x) {
 }
 __device__ __forceinline__ float act_grad(int act, float x) {
     switch (act) {
-        case POLUS_ACT_GELU: {
-            // Phi(x) + x phi(x); erf's exp(-u^2) with u = x/sqrt(2) IS exp(-x^2/2): one exponential for both terms
-            const float u = fabsf(x) * 0.70710678118654752f;
-            float t;
-            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, u, 1.0f)));
-            float poly = fmaf(t, 1.061405429f, -1.453152027f);
-            poly = fmaf(t, poly, 1.421413741f);
-            poly = fmaf(t, poly, -0.284496736f);
-            poly = fmaf(t, poly, 0.254829592f);
-            const float ex = __expf(-u * u);
-            const float erf_abs = 1.0f - poly * t * ex;
-            const float cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
-            return fmaf(x, 0.3989422804014327f * ex, cdf);
+        case POLUS_ACT_GELU: {  // Phi(x) + x phi(x)
+            float cdf, pdf;
+            gelu_cdf_pdf(x, cdf, pdf);
+            return fmaf(x, pdf, cdf);
         }
         case POLUS_ACT_RELU: return x > 0.0f ? 1.0f : 0.0f;
         case POLUS_ACT_SWISH: {

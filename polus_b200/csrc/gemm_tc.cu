@@ -36,17 +36,25 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
-constexpr int kThreads = 384;
 constexpr int kEpiWarps = 8;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int STG_BLOCK = 32 * 128;                       // one staging block: 32 rows x 64 bf16, swizzled
-constexpr int STG_BYTES = kEpiWarps * 2 /*bufs*/ * 2 /*C,C2*/ * STG_BLOCK;  // 64 KB
+// Epilogue staging: ONE buffer per epilogue warp, 4 KB (a 32-row x 64-column bf16 block) or 8 KB when the launch also
+// needs a second block (C2 output, the Emul multiplier tile, or the second 32-column half of an fp32 block).  Every byte
+// not spent here is operand-ring depth, which is what the main loop lives on: with the former 2 x 8 KB per warp the
+// 256-wide pair tile had 3 stages; 5-6 stages run the same shapes 1.2-1.35x faster (profiles/r01_gemm_stage_raster_exp.log).
+constexpr int kSmemTotal = 227 * 1024;
+constexpr int kBarBytes = 512;
+constexpr int kMaxStages = 8;
 
 struct TcParams {
     int M, N, K;
     int batch0;
     int m_tiles, n_tiles, split_k, kb_total, kb_per_split;
     int num_tiles;
+    int n_stages;     // operand-ring depth (<= kMaxStages)
+    int stg_warp;     // staging bytes per epilogue warp: STG_BLOCK or 2 * STG_BLOCK
+    int group_m;      // rasterisation: tiles are ordered in groups of group_m m-tiles x all n-tiles (m fastest inside a group)
     void* C;
     long long ldc, cbs0, cbs1;
     const float* bias;
@@ -65,14 +73,20 @@ struct Cfg {
     static constexpr int BN_LOCAL = BN / CG;  // rows of the B tile this CTA stages
     static constexpr int B_STAGE_BYTES = BN_LOCAL * BK * 2;
     static constexpr int kStageBytes = A_STAGE_BYTES + B_STAGE_BYTES;
-    static constexpr int kBudget = 227 * 1024 - 1024 - STG_BYTES - 512;
-    static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
     static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
-    static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + STG_BYTES + 512;
+    static int stages(int stg_warp) {
+        const int n = (kSmemTotal - 1024 - kEpiWarps * stg_warp - kBarBytes) / kStageBytes;
+        return n > kMaxStages ? kMaxStages : n;
+    }
+    static int smem_bytes(int stg_warp) { return 1024 + stages(stg_warp) * kStageBytes + kEpiWarps * stg_warp + kBarBytes; }
     static constexpr int kColBlocks = BN / 64;                       // 64-column blocks per tile
     static constexpr int kEpiActive = kColBlocks >= 2 ? 8 : 4;        // epilogue warps that do work
     static constexpr int kBlocksPerWarp = kColBlocks >= 2 ? kColBlocks / 2 : 1;
 };
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 template <int ACT>
 __device__ __forceinline__ void apply_act32(float* v) {
@@ -97,17 +111,10 @@ __device__ __forceinline__ void act_fwd_grad32(float* v, float* d) {
     for (int j = 0; j < 32; ++j) {
         const float x = v[j];
         if (ACT == POLUS_ACT_GELU) {
-            const float u = fabsf(x) * 0.70710678118654752f;
-            float t;
-            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, u, 1.0f)));
-            float poly = fmaf(t, 1.061405429f, -1.453152027f);
-            poly = fmaf(t, poly, 1.421413741f);
-            poly = fmaf(t, poly, -0.284496736f);
-            poly = fmaf(t, poly, 0.254829592f);
-            const float ex = __expf(-u * u);
-            const float cdf = fmaf(0.5f, copysignf(fmaf(-poly * t, ex, 1.0f), x), 0.5f);
+            float cdf, pdf;
+            gelu_cdf_pdf(x, cdf, pdf);
             v[j] = x * cdf;
-            d[j] = fmaf(x, 0.3989422804014327f * ex, cdf);
+            d[j] = fmaf(x, pdf, cdf);
         } else {
             v[j] = act_fwd(ACT, x);
             d[j] = act_grad(ACT, x);
@@ -137,6 +144,30 @@ __device__ __forceinline__ void stage_row(uint8_t* block, int lane, int half, co
     }
 }
 
+// 8 fp32 -> 8 bf16 into 16-byte chunk `chunk` (0..7) of row `lane`
+__device__ __forceinline__ void stage8(uint8_t* block, int lane, int chunk, const float* v8) {
+    *reinterpret_cast<bf16x8*>(block + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = pack8(v8);
+}
+// y = act(x), d = act'(x) for 8 values
+__device__ __forceinline__ void act_fwd_grad8(int act, float* v, float* d) {
+    if (act == POLUS_ACT_GELU) {  // the case that matters (warp-uniform branch)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float cdf, pdf;
+            gelu_cdf_pdf(v[j], cdf, pdf);
+            d[j] = fmaf(v[j], pdf, cdf);
+            v[j] *= cdf;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float x = v[j];
+            v[j] = act_fwd(act, x);
+            d[j] = act_grad(act, x);
+        }
+    }
+}
+
 // 32 fp32 (one 128-byte row) into row `lane` of a swizzled [32 rows][128 B] block
 __device__ __forceinline__ void stage_row_f32(uint8_t* block, int lane, const float* v) {
 #pragma unroll
@@ -146,29 +177,12 @@ __device__ __forceinline__ void stage_row_f32(uint8_t* block, int lane, const fl
     }
 }
 
-__device__ __forceinline__ void store_f32_chunk(const TcParams& p, const float* v, long long row_off, int col0, int nvalid) {
-    float* c = reinterpret_cast<float*>(p.C) + row_off + col0;
-    if (p.accumulate) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-            if (j < nvalid) atomicAdd(c + j, v[j]);
-    } else if (nvalid == 32) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(c + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-            if (j < nvalid) c[j] = v[j];
-    }
-}
-
-template <int BN, bool A_MN, bool B_MN, int CG>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int BN, bool A_MN, bool B_MN, int CG, int EPI>
+__global__ void __launch_bounds__(128 + 32 * EPI, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, const TcParams p) {
     using C = Cfg<BN, CG>;
-    constexpr int kStages = C::kStages;
+    const int kStages = p.n_stages;
     constexpr int BN_LOCAL = C::BN_LOCAL;
     constexpr int B_STAGE_BYTES = C::B_STAGE_BYTES;
     constexpr uint32_t kStageTx = (A_STAGE_BYTES + B_STAGE_BYTES) * CG;  // bytes landing on the leader's barrier
@@ -183,12 +197,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* sA = smem;
     uint8_t* sB = smem + kStages * A_STAGE_BYTES;
     uint8_t* sStage = smem + kStages * (A_STAGE_BYTES + B_STAGE_BYTES);  // 1024-aligned (stage sizes are multiples of 4 KB)
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sStage + STG_BYTES);
-    uint64_t* empty_bar = full_bar + kStages;
-    uint64_t* tfull_bar = empty_bar + kStages;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sStage + kEpiWarps * p.stg_warp);
+    uint64_t* empty_bar = full_bar + kMaxStages;
+    uint64_t* tfull_bar = empty_bar + kMaxStages;
     uint64_t* tempty_bar = tfull_bar + 2;
-    uint64_t* emul_bar = tempty_bar + 2;  // [epilogue warp][staging buffer]: Emul tile landed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(emul_bar + 2 * kEpiWarps);
+    uint64_t* emul_bar = tempty_bar + 2;  // [epilogue warp]: Emul tile landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(emul_bar + kEpiWarps);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -206,9 +220,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(&tfull_bar[s], 1);
-            ptx::mbar_init(&tempty_bar[s], C::kEpiActive * CG);  // one arrive per working epilogue warp of the group
+            ptx::mbar_init(&tempty_bar[s], (EPI == 16 ? 16 : C::kEpiActive) * CG);  // one arrive per working epilogue warp of the group
         }
-        for (int s = 0; s < 2 * kEpiWarps; ++s) ptx::mbar_init(&emul_bar[s], 1);
+        for (int s = 0; s < kEpiWarps; ++s) ptx::mbar_init(&emul_bar[s], 1);
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
@@ -223,10 +237,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     pdl_wait();  // operands / outputs of earlier kernels are touched only from here on
 
     auto decode = [&](int t, int& mt, int& nt, int& sp, int& b0, int& b1) {
-        mt = t % p.m_tiles;
-        t /= p.m_tiles;
-        nt = t % p.n_tiles;
-        t /= p.n_tiles;
+        const int mn = p.m_tiles * p.n_tiles;
+        const int r = t % mn;
+        t /= mn;
+        const int per_group = p.group_m * p.n_tiles;
+        const int g = r / per_group;
+        const int gm = min(p.group_m, p.m_tiles - g * p.group_m);  // the last group may be narrower
+        const int rr = r - g * per_group;
+        mt = g * p.group_m + rr % gm;
+        nt = rr / gm;
         sp = t % p.split_k;
         t /= p.split_k;
         b0 = t % p.batch0;
@@ -325,18 +344,171 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
         }
-    } else if (warp >= 4 && (warp - 4) < C::kEpiActive) {
+    } else if (EPI == 16 && warp >= 4) {
+        // ------------------------------------------------------------ epilogue, 16 warps (bf16 outputs with per-element
+        // math: activation + derivative, multiplier tile + column sums).  With 8 warps those epilogues ran at IPC 0.28 per
+        // scheduler -- two resident warps cannot cover MUFU / TMEM-load / shared-memory latency -- and paced the whole GEMM
+        // (profiles/r01_ncu_summary_v10_fwd.txt: tensor pipe 34 % active on the FFN-up GEMM).  Warps pair up on a block:
+        // warp (quad, cg, h) owns TMEM lanes 32*quad.. and the 32-column half h of 64-column block cg*kBPP + i; the pair
+        // shares one staging buffer (C | C2 or Emul) and one named barrier.
+        const int e = warp - 4;
+        const int quad = e & 3;
+        const int h = (e >> 2) & 1;
+        const int cg = e >> 3;
+        const int pair = quad + 4 * cg;
+        const int bar_id = 2 + pair;
+        constexpr int kBPP = (BN / 64) / 2 > 0 ? (BN / 64) / 2 : 1;  // 64-column blocks per pair per tile
+        uint8_t* blkC = sStage + pair * p.stg_warp;
+        uint8_t* blkC2 = blkC + STG_BLOCK;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        bool store_pending = false;
+        int nblk = 0;
+        auto blk_valid = [&](int t, int i) -> bool {
+            if (t >= p.num_tiles || i >= kBPP) return false;
+            int mt, nt, sp, b0, b1;
+            decode(t, mt, nt, sp, b0, b1);
+            return nt * BN + (cg * kBPP + i) * 64 < p.N;
+        };
+        auto advance = [&](int& t, int& i) {
+            ++i;
+            while (t < p.num_tiles && !blk_valid(t, i)) {
+                t += tile_step;
+                i = 0;
+            }
+        };
+        auto emul_issue = [&](int t, int i) {
+            if (h == 0 && lane == 0) {
+                int mt, nt, sp, b0, b1;
+                decode(t, mt, nt, sp, b0, b1);
+                ptx::mbar_expect_tx(&emul_bar[pair], STG_BLOCK);
+                ptx::tma_load_4d(blkC2, &tmC2, &emul_bar[pair], nt * BN + (cg * kBPP + i) * 64,
+                                 (mt * CG + (int)cta_rank) * BM + quad * 32, b0, b1);
+            }
+        };
+        int pf_t = tile0, pf_i = -1;
+        if (p.has_emul) {
+            advance(pf_t, pf_i);
+            if (pf_t < p.num_tiles) emul_issue(pf_t, pf_i);
+        }
+        for (int t = tile0; t < p.num_tiles; t += tile_step) {
+            int mt, nt, sp, b0, b1;
+            decode(t, mt, nt, sp, b0, b1);
+            ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+            ptx::tc_fence_after();
+            const int row0 = (mt * CG + (int)cta_rank) * BM + quad * 32;
+            const bool add_bias = (p.bias != nullptr) && (sp == 0);
+#pragma unroll 1
+            for (int i = 0; i < kBPP; ++i) {
+                const int cb = cg * kBPP + i;
+                const int colb = nt * BN + cb * 64;
+                if (colb >= p.N) break;  // uniform for the pair
+                if (store_pending && h == 0 && lane == 0) ptx::tma_store_wait_read<0>();  // previous block's stores have read the buffer
+                named_bar_sync(bar_id, 64);
+                if (p.has_emul) ptx::mbar_wait(&emul_bar[pair], (uint32_t)nblk & 1u);
+                const int col0 = colb + h * 32;
+                if (col0 < p.N) {
+                    float v[32];
+                    ptx::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + cb * 64 + h * 32, v);
+                    ptx::tmem_ld_wait();
+                    const int nvalid = min(32, p.N - col0);
+                    if (p.alpha != 1.0f) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+                    }
+                    if (add_bias) {
+                        if (nvalid == 32) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
+                                v[4 * j] += bv.x;
+                                v[4 * j + 1] += bv.y;
+                                v[4 * j + 2] += bv.z;
+                                v[4 * j + 3] += bv.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (j < nvalid) v[j] += __ldg(p.bias + col0 + j);
+                        }
+                    }
+                    if (p.has_emul) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float m8[8];
+                            unpack8(*reinterpret_cast<const bf16x8*>(blkC2 + lane * 128 + (((h * 4 + j) ^ (lane & 7)) << 4)), m8);
+#pragma unroll
+                            for (int x = 0; x < 8; ++x) v[8 * j + x] *= m8[x];
+                        }
+                        stage_row(blkC, lane, h, v);
+                    } else if (p.has_c2 && p.c2_grad) {
+                        // 8 values at a time: 96 registers per thread do not hold 32 results and 32 derivatives
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float d8[8];
+                            act_fwd_grad8(p.act, v + 8 * j, d8);
+                            stage8(blkC2, lane, h * 4 + j, d8);
+                            stage8(blkC, lane, h * 4 + j, v + 8 * j);
+                        }
+                    } else {
+                        if (p.has_c2) stage_row(blkC2, lane, h, v);
+                        apply_act(p.act, v);
+                        stage_row(blkC, lane, h, v);
+                    }
+                }
+                ptx::fence_proxy_async_smem();
+                named_bar_sync(bar_id, 64);  // both halves staged; both warps are done with the multiplier tile
+                if (p.has_emul) {
+                    advance(pf_t, pf_i);
+                    if (pf_t < p.num_tiles) emul_issue(pf_t, pf_i);
+                }
+                if (h == 0 && lane == 0) {
+                    ptx::tma_store_4d(&tmC, blkC, colb, row0, b0, b1);
+                    if (p.has_c2) ptx::tma_store_4d(&tmC2, blkC2, colb, row0, b0, b1);
+                    ptx::tma_store_commit();
+                }
+                store_pending = true;
+                if (p.colsum != nullptr && h == 1) {
+                    const int nrows = min(32, p.M - row0);
+                    float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+                    for (int r = 0; r < 32; ++r) {
+                        if (r < nrows) {
+                            const uint32_t w = *reinterpret_cast<const uint32_t*>(blkC + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4) + (lane & 3) * 4);
+                            s0 += __uint_as_float(w << 16);
+                            s1 += __uint_as_float(w & 0xFFFF0000u);
+                        }
+                    }
+                    const int c = colb + 2 * lane;
+                    if (c < p.N) atomicAdd(p.colsum + c, s0);
+                    if (c + 1 < p.N) atomicAdd(p.colsum + c + 1, s1);
+                }
+                ++nblk;
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (CG == 2) ptx::mbar_arrive_remote(&tempty_bar[acc], 0);
+                else ptx::mbar_arrive(&tempty_bar[acc]);
+            }
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+        if (h == 0 && lane == 0) ptx::tma_store_wait_all();  // smem must outlive the bulk stores
+    } else if (EPI == 8 && warp >= 4 && (warp - 4) < C::kEpiActive) {
         // ------------------------------------------------------------ epilogue (TMEM lane = row)
         const int e = warp - 4;
         const int quad = e & 3;   // TMEM lanes [32*quad, 32*quad+32)  (hardware: warp_id % 4)
         const int half = e >> 2;  // which half of the tile's 64-column blocks
-        uint8_t* stg = sStage + e * (4 * STG_BLOCK);  // [buf][C | C2]
+        uint8_t* stg = sStage + e * p.stg_warp;  // [C | C2 or Emul or second fp32 half]
         int acc = 0;
         uint32_t acc_phase = 0;
         int stores_in_flight = 0;
-        int nblk = 0;  // staged blocks so far: alternates the two staging buffers across tiles too
-        // ---- Emul prefetch: the multiplier tile of block n+1 is fetched by TMA into the C2 half of the OTHER staging
-        // buffer while block n is processed (that half was last read, and fenced, at block n-1).
+        int nblk = 0;  // blocks staged so far (phase of this warp's Emul barrier)
+        // ---- Emul prefetch: the multiplier tile of block n+1 is fetched by TMA into the second half of the staging
+        // buffer as soon as block n's has been consumed into registers.
         auto blk_valid = [&](int t, int i) -> bool {
             if (t >= p.num_tiles || i >= C::kBlocksPerWarp) return false;
             int mt, nt, sp, b0, b1;
@@ -350,20 +522,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 i = 0;
             }
         };
-        auto emul_issue = [&](int t, int i, int slot) {
+        auto emul_issue = [&](int t, int i) {
             if (lane == 0) {
                 int mt, nt, sp, b0, b1;
                 decode(t, mt, nt, sp, b0, b1);
-                uint64_t* bar = &emul_bar[e * 2 + slot];
+                uint64_t* bar = &emul_bar[e];
                 ptx::mbar_expect_tx(bar, STG_BLOCK);
-                ptx::tma_load_4d(stg + slot * (2 * STG_BLOCK) + STG_BLOCK, &tmC2, bar, nt * BN + (half * C::kBlocksPerWarp + i) * 64,
+                ptx::tma_load_4d(stg + STG_BLOCK, &tmC2, bar, nt * BN + (half * C::kBlocksPerWarp + i) * 64,
                                  (mt * CG + (int)cta_rank) * BM + quad * 32, b0, b1);
             }
         };
         int pf_t = tile0, pf_i = -1;
         if (p.has_emul) {
             advance(pf_t, pf_i);
-            if (pf_t < p.num_tiles) emul_issue(pf_t, pf_i, 0);
+            if (pf_t < p.num_tiles) emul_issue(pf_t, pf_i);
         }
         for (int t = tile0; t < p.num_tiles; t += tile_step) {
             int mt, nt, sp, b0, b1;
@@ -371,29 +543,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ptx::mbar_wait(&tfull_bar[acc], acc_phase);
             ptx::tc_fence_after();
             const int row0 = (mt * CG + (int)cta_rank) * BM + quad * 32;
-            const int row = row0 + lane;
-            const long long row_off = (long long)b0 * p.cbs0 + (long long)b1 * p.cbs1 + (long long)row * p.ldc;
-            (void)row_off;
             const bool add_bias = (p.bias != nullptr) && (sp == 0);
 #pragma unroll 1
             for (int i = 0; i < C::kBlocksPerWarp; ++i) {
                 const int cb = half * C::kBlocksPerWarp + i;
                 const int colb = nt * BN + cb * 64;
                 if (colb >= p.N) break;  // warp-uniform
-                const int buf = nblk & 1;
-                uint8_t* blkC = stg + buf * (2 * STG_BLOCK);
-                uint8_t* blkC2 = blkC + STG_BLOCK;
-                if (p.has_emul) {
-                    advance(pf_t, pf_i);  // (pf_t, pf_i) was this block; now the next valid one
-                    if (pf_t < p.num_tiles) emul_issue(pf_t, pf_i, buf ^ 1);
-                }
-                if (stores_in_flight >= 2) {
-                    // the TMA store that last read this staging buffer must be done reading it
-                    if (lane == 0) ptx::tma_store_wait_read<1>();
+                uint8_t* blkC = stg;
+                uint8_t* blkC2 = stg + STG_BLOCK;
+                if (stores_in_flight) {
+                    // the TMA store of the previous block must be done reading the staging buffer
+                    if (lane == 0) ptx::tma_store_wait_read<0>();
                     __syncwarp();
-                    stores_in_flight = 1;
+                    stores_in_flight = 0;
                 }
-                if (p.has_emul) ptx::mbar_wait(&emul_bar[e * 2 + buf], (uint32_t)(nblk >> 1) & 1u);
+                if (p.has_emul) ptx::mbar_wait(&emul_bar[e], (uint32_t)nblk & 1u);
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int col0 = colb + h * 32;
@@ -450,6 +614,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 ptx::fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA engine
                 __syncwarp();
+                if (p.has_emul) {
+                    // every lane has consumed this block's multiplier tile (program order + the fence/syncwarp above):
+                    // fetch the next block's now, so that it lands while this warp waits for its next accumulator
+                    advance(pf_t, pf_i);
+                    if (pf_t < p.num_tiles) emul_issue(pf_t, pf_i);
+                }
                 if (lane == 0) {
                     // rows >= M and columns >= N are clipped by the tensor map
                     if (p.c_f32) {
@@ -561,23 +731,25 @@ int make_map(CUtensorMap* map, const polus_operand_t& op, long long mn_len, long
     return encode_map(map, op.ptr, inner, rows, op.ld, batch0, op.bs0, batch1, op.bs1, op.mn_major ? BK : box_mn);
 }
 
-template <int BN, bool A_MN, bool B_MN, int CG>
+template <int BN, bool A_MN, bool B_MN, int CG, int EPI = 8>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tc2,
-           const TcParams& p, cudaStream_t st) {
-    auto kern = gemm_tc_kernel<BN, A_MN, B_MN, CG>;
+           const TcParams& p_in, cudaStream_t st) {
+    auto kern = gemm_tc_kernel<BN, A_MN, B_MN, CG, EPI>;
     using C = Cfg<BN, CG>;
-    static_assert(C::kStages >= 2, "pipeline needs at least two stages");
     static bool attr_set = false;
     if (!attr_set) {
-        POLUS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+        POLUS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
         attr_set = true;
     }
+    TcParams p = p_in;
+    p.n_stages = C::stages(p.stg_warp);
+    POLUS_REQUIRE(p.n_stages >= 2, "polus_gemm_tc: operand ring needs at least two stages");
     int groups = polus_num_sms() / CG;
     if (p.num_tiles < groups) groups = p.num_tiles;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(groups * CG);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = C::kSmemBytes;
+    cfg.blockDim = dim3(128 + 32 * EPI);
+    cfg.dynamicSmemBytes = C::smem_bytes(p.stg_warp);
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -685,6 +857,10 @@ extern "C" int polus_gemm_tc(const polus_gemm_t* g, void* stream) {
     p.kb_per_split = cdiv(p.kb_total, split);
     p.split_k = cdiv(p.kb_total, p.kb_per_split);
     p.num_tiles = (int)(mt * p.n_tiles * p.split_k * nb);
+    // Rasterisation: concurrently running tiles form (about) an 8 x 9 patch of the tile grid instead of a 74 x 1 column
+    // strip, so each A row block and each B column block in flight is shared by 8-9 clusters (measured 1.05-1.15x).
+    static const int group_env = getenv("POLUS_GEMM_GROUP_M") ? atoi(getenv("POLUS_GEMM_GROUP_M")) : 8;
+    p.group_m = (group_env > 0 && group_env < p.m_tiles) ? group_env : p.m_tiles;
     p.C = g->C;
     p.ldc = g->ldc;
     p.cbs0 = g->cbs0;
@@ -698,6 +874,8 @@ extern "C" int polus_gemm_tc(const polus_gemm_t* g, void* stream) {
     p.c2_grad = g->c2_kind == 1;
     p.has_emul = g->Emul != nullptr;
     p.colsum = g->colsum;
+    p.stg_warp = (p.c_f32 || p.has_c2 || p.has_emul) ? 2 * STG_BLOCK : STG_BLOCK;
+    p.n_stages = 0;  // set per instantiation in launch()
 
     CUtensorMap ta, tb, tc, tc2;
     int rc = make_map(&ta, g->A, g->M, g->K, batch0, batch1, BM);
@@ -719,6 +897,13 @@ extern "C" int polus_gemm_tc(const polus_gemm_t* g, void* stream) {
         tc2 = tc;
     }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    // epilogues with per-element math run on the 16-epilogue-warp instantiation (256-wide pair tiles, A K-major:
+    // the FFN-up forward GEMM and the dgrad GEMM that applies act' and sums the bias gradient)
+    static const int epi_env = getenv("POLUS_GEMM_EPI16") ? atoi(getenv("POLUS_GEMM_EPI16")) : 1;
+    if (CG == 2 && BN == 256 && !p.c_f32 && !g->A.mn_major && epi_env && (p.act != POLUS_ACT_NONE || p.has_emul || p.has_c2)) {
+        if (g->B.mn_major) return launch<256, false, true, 2, 16>(ta, tb, tc, tc2, p, st);
+        return launch<256, false, false, 2, 16>(ta, tb, tc, tc2, p, st);
+    }
     if (CG == 2) {
         if (BN == 128) return launch_major<128, 2>(g->A.mn_major, g->B.mn_major, ta, tb, tc, tc2, p, st);
         return launch_major<256, 2>(g->A.mn_major, g->B.mn_major, ta, tb, tc, tc2, p, st);

@@ -25,7 +25,8 @@ def op(ptr, ld, mn, bs0=0, bs1=0):
     return _lib.Operand(ptr, ld, bs0, bs1, mn, _lib.BF16)
 
 
-def case(name, M_, N_, K_, A, B, ldc, c_dtype, b0=1, b1=1, cbs0=0, cbs1=0, acc=0, split=1, act=0, c2=False, use_bias=True, count=1):
+def case(name, M_, N_, K_, A, B, ldc, c_dtype, b0=1, b1=1, cbs0=0, cbs1=0, acc=0, split=1, act=0, c2=False, use_bias=True, count=1,
+         c2_kind=0, emul=False, colsum=True):
     g = _lib.Gemm()
     g.M, g.N, g.K, g.batch0, g.batch1 = M_, N_, K_, b0, b1
     g.A, g.B = A, B
@@ -33,6 +34,9 @@ def case(name, M_, N_, K_, A, B, ldc, c_dtype, b0=1, b1=1, cbs0=0, cbs1=0, acc=0
     g.C2 = (out.ptr + (1 << 29)) if c2 else None
     g.bias = bias.ptr if use_bias else None
     g.alpha, g.act, g.accumulate, g.split_k = 1.0, act, acc, split
+    g.c2_kind = c2_kind
+    if emul:  # fused activation backward: multiplier tile + bias-gradient column sums
+        g.Emul, g.colsum = out.ptr + (1 << 29), (bias.ptr if colsum else None)
     assert _lib.call("polus_gemm_tc_supported", C.byref(g)) == 1, (name, _lib.last_error())
     e0, e1 = C.c_void_p(), C.c_void_p()
     _lib.call("polus_event_create", C.byref(e0)); _lib.call("polus_event_create", C.byref(e1))
@@ -58,16 +62,22 @@ tot = 0.0
 L = 12
 tot += case("fwd_qkv", M, 3 * H, H, op(a, H, 0), op(b, 3 * H, 1), 3 * H, _lib.BF16, count=L)
 tot += case("fwd_attn_out", M, H, H, op(a, H, 0), op(b, H, 1), H, _lib.BF16, count=L)
-tot += case("fwd_ffn1_gelu", M, I, H, op(a, H, 0), op(b, I, 1), I, _lib.BF16, act=1, c2=True, count=L)
+tot += case("fwd_ffn1_gelu+gelu'", M, I, H, op(a, H, 0), op(b, I, 1), I, _lib.BF16, act=1, c2=True, c2_kind=1, count=L)
 tot += case("fwd_ffn2", M, H, I, op(a, I, 0), op(b, H, 1), H, _lib.BF16, count=L)
 tot += case("dgrad_qkv", M, H, 3 * H, op(a, 3 * H, 0), op(b, 3 * H, 0), H, _lib.BF16, use_bias=False, count=L)
 tot += case("dgrad_attn_out", M, H, H, op(a, H, 0), op(b, H, 0), H, _lib.BF16, use_bias=False, count=L)
 tot += case("dgrad_ffn1", M, H, I, op(a, I, 0), op(b, I, 0), H, _lib.BF16, use_bias=False, count=L)
-tot += case("dgrad_ffn2", M, I, H, op(a, H, 0), op(b, H, 0), I, _lib.BF16, use_bias=False, count=L)
+tot += case("dgrad_ffn2*gelu'+colsum", M, I, H, op(a, H, 0), op(b, H, 0), I, _lib.BF16, use_bias=False, emul=True, count=L)
+case("  (same without colsum)", M, I, H, op(a, H, 0), op(b, H, 0), I, _lib.BF16, use_bias=False, emul=True, colsum=False, count=L)
+case("  (plain dgrad_ffn2, no Emul)", M, I, H, op(a, H, 0), op(b, H, 0), I, _lib.BF16, use_bias=False, count=L)
 tot += case("wgrad_qkv", H, 3 * H, M, op(a, H, 1), op(b, 3 * H, 1), 3 * H, _lib.F32, acc=1, split=0, use_bias=False, count=L)
 tot += case("wgrad_attn_out", H, H, M, op(a, H, 1), op(b, H, 1), H, _lib.F32, acc=1, split=0, use_bias=False, count=L)
 tot += case("wgrad_ffn1", H, I, M, op(a, H, 1), op(b, I, 1), I, _lib.F32, acc=1, split=0, use_bias=False, count=L)
 tot += case("wgrad_ffn2", I, H, M, op(a, I, 1), op(b, H, 1), H, _lib.F32, acc=1, split=0, use_bias=False, count=L)
+print(json.dumps({"total_gemm_ms_per_step": round(tot, 3), "batch": Bsz}))
+if len(sys.argv) <= 2:
+    sys.exit(0)
+# batched attention GEMMs of the UNFUSED path (S > 256 only; not part of the S=256 step)
 H3 = 3 * H
 qkv = lambda ptr, mn: op(ptr, H3, mn, dh, S * H3)
 pm = lambda ptr, mn: op(ptr, S, mn, S * S, S * S * nh)
