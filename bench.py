@@ -244,6 +244,37 @@ def run_ours(args):
                 "gemm_marginal_ms_per_step": step_ms - no_gemm_ms,
                 "peak_source": f"{how} bf16_tflops_sustained (kernel timed inside a long step)",
                 "step_mfu": (args.batch * TRAIN_GFLOP_PER_SEQ * 1e9 / (step_ms * 1e-3)) / 1e12 / peak}
+    # ---- the exchange step alone: bucketed NCCL allreduce of the fp32 gradient arena, back to back (in the step it is
+    # overlapped with backward); bus bandwidth = bytes * 2(N-1)/N / time  (NCCL's definition)
+    allreduce = None
+    if world > 1:
+        buckets = comm.plan_buckets(trainer.trainable_weights)
+        nbytes = sum(n for _, _, n, _ in buckets) * 4
+        st = device.stream()
+
+        def ar_all():
+            for ch, off, n, _ in buckets:
+                _lib.call("polus_comm_allreduce_f32", ch.g.ptr + off * 4, n, st)
+        for _ in range(3):
+            ar_all()
+        e0, e1 = ev(), ev()
+        barrier()
+        _lib.call("polus_event_record", e0, st)
+        for _ in range(10):
+            ar_all()
+        _lib.call("polus_event_record", e1, st)
+        barrier()
+        ms = C.c_float()
+        _lib.call("polus_event_elapsed_ms", e0, e1, C.byref(ms))
+        ar_ms = max(json.loads(b.decode()) for b in comm._host_allgather(json.dumps(ms.value / 10).encode()))
+        # leave the gradient arena zeroed, as the optimizer kernel does
+        for ch, off, n, _ in buckets:
+            _lib.call("polus_memset", ch.g.ptr + off * 4, 0, n * 4, st)
+        device.device_sync()
+        allreduce = {"bytes": int(nbytes), "buckets": len(buckets), "ms": ar_ms,
+                     "busbw_GBps": nbytes * 2 * (world - 1) / world / (ar_ms * 1e-3) / 1e9,
+                     "nvlink_peak_GBps": 900.0, "nvlink_measured_allreduce_GBps": 725.0,
+                     "note": "standalone, back to back; inside the step it runs on a side stream under backward"}
     if rank != 0:
         return
     seqs = args.batch * world * args.steps
@@ -262,6 +293,8 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "sequences/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "roofline": roof}
+    if allreduce is not None:
+        line["allreduce"] = allreduce
     if world == 1 and not args.no_cpu_baseline:
         from oracle import torch_ref
         sps, dt, threads = torch_ref.time_train_steps(batch=args.ref_batch, seq=SEQ, steps=2, warmup=1)

@@ -145,6 +145,33 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             if (t < p.S) mv = p.mask ? (1.0f - (float)p.mask[(long long)b * p.S + t]) * -10000.0f : 0.f;
             sMask[t] = mv;
         }
+        // Dropout decisions of this thread's 128 probabilities, made (and written out for the backward kernel) while the
+        // Q/K/V tiles are still in flight and the first MMA runs: 16 Philox blocks that used to sit between the two
+        // softmax passes (attention_fwd p=0.1 vs p=0: +50 % time, profiles/r01_kernel_times_v9_b64.log).
+        const uint32_t step = p.thresh16 ? *p.d_step : 0u;
+        const bool qvalid = q0 + row < p.S;
+        const long long grow = ((long long)(b * p.nh + h) * p.S + (q0 + row));  // row of the [B*nh*S, S] probability matrix
+        const int chunks_per_row = p.S >> 3;
+        uint32_t kbits[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+        if (p.thresh16) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int kc = half * 128 + c * 32;
+                if (qvalid && kc < p.S) {
+                    uint32_t bits = 0;
+#pragma unroll
+                    for (int g8 = 0; g8 < 4; ++g8) {
+                        const int key0 = kc + g8 * 8;
+                        uint32_t keep = 0xFFu;
+                        if (key0 < p.S)
+                            keep = dropout_keep8(p.seed, p.site, step, (unsigned long long)grow * chunks_per_row + (key0 >> 3), p.thresh16);
+                        bits |= keep << (8 * g8);
+                    }
+                    kbits[c] = bits;
+                    p.keepbits[grow * (p.S >> 5) + (kc >> 5)] = bits;  // reused by the backward kernel
+                }
+            }
+        }
         named_bar_sync(1, 256);
         ptx::mbar_wait(&bars[1], 0);
         ptx::tc_fence_after();
@@ -162,13 +189,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         named_bar_sync(1, 256);
         mx = fmaxf(mx, sRed[(half ^ 1) * 128 + row]);  // keys beyond S are -inf, real keys finite: mx is finite
         named_bar_sync(1, 256);                        // sRed is reused for the sums below
-        const uint32_t step = p.thresh16 ? *p.d_step : 0u;
-        const bool qvalid = q0 + row < p.S;
-        const long long grow = ((long long)(b * p.nh + h) * p.S + (q0 + row));  // row of the [B*nh*S, S] probability matrix
-        const int chunks_per_row = p.S >> 3;
         float sum = 0.f;
         const float mxl = mx * kLog2e;
-#pragma unroll 1
+        const float scl = sc * kLog2e;
+#pragma unroll
         for (int c = 0; c < 4; ++c) {
             float v[32];
             ptx::tmem_ld32(lane_addr + half * 128 + c * 32, v);
@@ -176,22 +200,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             const int kc = half * 128 + c * 32;  // first key of this chunk
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                v[j] = exp2f(fmaf(fmaf(v[j], sc, sMask[kc + j]), kLog2e, -mxl));
+                v[j] = exp2f(fmaf(v[j], scl, fmaf(sMask[kc + j], kLog2e, -mxl)));
                 sum += v[j];
             }
             if (p.thresh16) {
-                uint32_t bits = 0;
+                const uint32_t bits = kbits[c];
 #pragma unroll
-                for (int g8 = 0; g8 < 4; ++g8) {
-                    const int key0 = kc + g8 * 8;
-                    uint32_t keep = 0xFFu;
-                    if (key0 < p.S && qvalid)
-                        keep = dropout_keep8(p.seed, p.site, step, (unsigned long long)grow * chunks_per_row + (key0 >> 3), p.thresh16);
-                    bits |= keep << (8 * g8);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) v[g8 * 8 + j] = ((keep >> j) & 1u) ? v[g8 * 8 + j] * p.inv_keep : 0.f;
-                }
-                if (qvalid && kc < p.S) p.keepbits[grow * (p.S >> 5) + (kc >> 5)] = bits;  // reused by the backward kernel
+                for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? v[j] * p.inv_keep : 0.f;
             }
             // keys [kc, kc+32) -> k-block kc/64, 16-byte chunks ((kc/32)&1)*4 .. +3 of row `row`
             uint8_t* blk = sP + (kc >> 6) * 16384 + row * 128;
@@ -241,8 +256,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 }
 
 // ================================================================================================ backward
-// 288 threads: warp 0 = TMA + MMA issue, warps 1-8: thread = (query row, 64-key half of the 128-key block).
-constexpr int BWD_THREADS = 288;
+// 544 threads: warp 0 = TMA + MMA issue, warps 1-16: thread = (query row, 32-key quarter of the 128-key block).
+// Sixteen softmax warps (four per scheduler): with eight, the exp / dS arithmetic of a block ran at a fraction of the
+// issue rate -- two warps per scheduler cannot cover TMEM-load, MUFU and shared-memory latency -- and the kernel's time
+// was the sum of its serial phases (profiles/r01_attn_bwd_stalls_v10.txt).
+constexpr int BWD_SM_WARPS = 16;
+constexpr int BWD_SM_THREADS = BWD_SM_WARPS * 32;
+constexpr int BWD_THREADS = 32 + BWD_SM_THREADS;
 constexpr int B_SQ = 0;                   // 32 KB: Q rows 0..255
 constexpr int B_SK = B_SQ + 32768;
 constexpr int B_SV = B_SK + 32768;
@@ -282,7 +302,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         ptx::prefetch_tensormap(&tmDQKV);
         ptx::mbar_init(&bars[0], 1);
         ptx::mbar_init(&bars[1], 1);
-        ptx::mbar_init(&bars[2], 256);
+        ptx::mbar_init(&bars[2], BWD_SM_THREADS);
         ptx::mbar_init(&bars[3], 1);
         ptx::fence_barrier_init();
     }
@@ -310,90 +330,106 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             const uint32_t aQ = ptx::smem_u32(sQ), aK = ptx::smem_u32(sK), aV = ptx::smem_u32(sV), aDO = ptx::smem_u32(sDO);
             const uint32_t aPd = ptx::smem_u32(sPd), aDS = ptx::smem_u32(sDS);
             uint32_t ph2 = 0;
-            int blk = 0;
-            for (int j = 0; j < n_kh; ++j) {
-                for (int i = 0; i < n_qt; ++i, ++blk) {
-                    if (blk > 0) {  // previous block's MMAs must have drained S/dP (TMEM) and Pd/dS (smem)
-                        ptx::mbar_wait(&bars[3], (blk - 1) & 1);
-                        ptx::tc_fence_after();
-                    }
-                    {   // S_ij = Q_i K_j^T ; dP_ij = dO_i V_j^T   (M128 N128 K64)
-                        constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, 128, 0, 0);
+            // S_ij = Q_i K_j^T ; dP_ij = dO_i V_j^T   (M128 N128 K64) -> bars[1]
+            auto issue_scores = [&](int i, int j) {
+                constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, 128, 0, 0);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            ptx::umma_bf16(tmem + C_S, ptx::umma_desc(kbase, aQ + i * 16384 + k * 32),
-                                           ptx::umma_desc(kbase, aK + j * 16384 + k * 32), idesc, k > 0);
+                for (int k = 0; k < 4; ++k)
+                    ptx::umma_bf16(tmem + C_S, ptx::umma_desc(kbase, aQ + i * 16384 + k * 32),
+                                   ptx::umma_desc(kbase, aK + j * 16384 + k * 32), idesc, k > 0);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            ptx::umma_bf16(tmem + C_DP, ptx::umma_desc(kbase, aDO + i * 16384 + k * 32),
-                                           ptx::umma_desc(kbase, aV + j * 16384 + k * 32), idesc, k > 0);
-                        ptx::umma_commit(&bars[1]);
-                    }
-                    ptx::mbar_wait(&bars[2], ph2);
-                    ph2 ^= 1;
-                    ptx::tc_fence_after();
-                    {   // dV_j += Pd_ij^T dO_i ; dK_j += dS_ij^T Q_i   (A MN-major over keys, B MN-major over d; M128 N64 K128)
-                        constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, 64, 1, 1);
+                for (int k = 0; k < 4; ++k)
+                    ptx::umma_bf16(tmem + C_DP, ptx::umma_desc(kbase, aDO + i * 16384 + k * 32),
+                                   ptx::umma_desc(kbase, aV + j * 16384 + k * 32), idesc, k > 0);
+                ptx::umma_commit(&bars[1]);
+            };
+            issue_scores(0, 0);
+            const int n_blk = n_kh * n_qt;
+            for (int blk = 0; blk < n_blk; ++blk) {
+                const int j = blk / n_qt, i = blk % n_qt;
+                // Pd_ij / dS_ij are in shared memory and every softmax thread has read S_ij / dP_ij out of TMEM
+                ptx::mbar_wait(&bars[2], ph2);
+                ph2 ^= 1;
+                ptx::tc_fence_after();
+                // the NEXT block's scores first: they only need the S / dP columns, so the softmax threads can start on
+                // them while the three accumulating products of this block are still running (they wait for bars[3] of
+                // this block only before overwriting Pd / dS)
+                if (blk + 1 < n_blk) issue_scores((blk + 1) % n_qt, (blk + 1) / n_qt);
+                {   // dV_j += Pd_ij^T dO_i ; dK_j += dS_ij^T Q_i   (A MN-major over keys, B MN-major over d; M128 N64 K128)
+                    constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, 64, 1, 1);
 #pragma unroll
-                        for (int k = 0; k < 8; ++k)
-                            ptx::umma_bf16(tmem + C_DV, ptx::umma_desc(mn1, aPd + k * 2048),
-                                           ptx::umma_desc(mn1, aDO + i * 16384 + k * 2048), idesc, (i > 0 || k > 0));
+                    for (int k = 0; k < 8; ++k)
+                        ptx::umma_bf16(tmem + C_DV, ptx::umma_desc(mn1, aPd + k * 2048),
+                                       ptx::umma_desc(mn1, aDO + i * 16384 + k * 2048), idesc, (i > 0 || k > 0));
 #pragma unroll
-                        for (int k = 0; k < 8; ++k)
-                            ptx::umma_bf16(tmem + C_DK, ptx::umma_desc(mn1, aDS + k * 2048),
-                                           ptx::umma_desc(mn1, aQ + i * 16384 + k * 2048), idesc, (i > 0 || k > 0));
-                    }
-                    {   // dQ_i += dS_ij K_j   (A K-major: 2 k-blocks of 64 keys; B = K_j rows as MN-major over d; M128 N64 K128)
-                        constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, 64, 0, 1);
-                        const uint32_t cdq = i == 0 ? C_DQ0 : C_DQ1;
-#pragma unroll
-                        for (int k = 0; k < 8; ++k)
-                            ptx::umma_bf16(tmem + cdq, ptx::umma_desc(kbase, aDS + (k >> 2) * 16384 + (k & 3) * 32),
-                                           ptx::umma_desc(mn1, aK + j * 16384 + k * 2048), idesc, (j > 0 || k > 0));
-                    }
-                    ptx::umma_commit(&bars[3]);
+                    for (int k = 0; k < 8; ++k)
+                        ptx::umma_bf16(tmem + C_DK, ptx::umma_desc(mn1, aDS + k * 2048),
+                                       ptx::umma_desc(mn1, aQ + i * 16384 + k * 2048), idesc, (i > 0 || k > 0));
                 }
+                {   // dQ_i += dS_ij K_j   (A K-major: 2 k-blocks of 64 keys; B = K_j rows as MN-major over d; M128 N64 K128)
+                    constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, 64, 0, 1);
+                    const uint32_t cdq = i == 0 ? C_DQ0 : C_DQ1;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        ptx::umma_bf16(tmem + cdq, ptx::umma_desc(kbase, aDS + (k >> 2) * 16384 + (k & 3) * 32),
+                                       ptx::umma_desc(mn1, aK + j * 16384 + k * 2048), idesc, (j > 0 || k > 0));
+                }
+                ptx::umma_commit(&bars[3]);
             }
         }
     } else {
-        const int t = threadIdx.x - 32;   // 0..255
-        const int e = warp - 1;
-        const int quad = warp & 3;
-        const int half = e >> 2;          // keys [64*half, +64) of the current 128-key block
+        const int t = threadIdx.x - 32;   // 0..511
+        const int e = warp - 1;           // 0..15
+        const int quad = warp & 3;        // TMEM lane quadrant this warp may access
+        const int q4 = e >> 2;            // keys [32*q4, +32) of the current 128-key block
         const int row = quad * 32 + lane;
         const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
-        {
+        if (t < 256) {
             float mv = -INFINITY;
             if (t < p.S) mv = p.mask ? (1.0f - (float)p.mask[(long long)b * p.S + t]) * (-10000.0f * kLog2e) : 0.f;
             sMask[t] = mv;
         }
-        // delta_row = sum_d dO[row,d] * O[row,d] and L_row for this thread's row in each query tile.  The pair of
-        // threads sharing a row splits the 64 columns; explicit 128-bit loads, all issued before the arithmetic
-        // (scalar 4-byte loads here were the top stall of v1: profiles/r01_ncu_attention_bwd_v2.txt).
+        // delta_row = sum_d dO[row,d] * O[row,d] and L_row for this thread's row in each query tile.  The four threads
+        // sharing a row split the 64 columns; explicit 128-bit loads, all issued before the arithmetic.
         float delta0 = 0.f, delta1 = 0.f, L0 = 0.f, L1 = 0.f;
+        // dropout keep bits of every block this thread will process (4 words), fetched now so that no global load sits
+        // on the per-block critical path
+        uint32_t kbits[2][2];
         {
-            bf16x8 ov[2][4], dv[2][4];
+            bf16x8 ov[2][2], dv[2][2];
             bool ok[2];
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 const int q = i * 128 + row;
                 ok[i] = (i < n_qt) && (q < p.S);
                 if (ok[i]) {
-                    const bf16* o = ctx + ((long long)b * p.S + q) * H + h * DH + half * 32;
-                    const bf16* d = dctx + ((long long)b * p.S + q) * H + h * DH + half * 32;
+                    const bf16* o = ctx + ((long long)b * p.S + q) * H + h * DH + q4 * 16;
+                    const bf16* d = dctx + ((long long)b * p.S + q) * H + h * DH + q4 * 16;
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
+                    for (int c = 0; c < 2; ++c) {
                         ov[i][c] = ld_stream8(o + c * 8);
                         dv[i][c] = ld_stream8(d + c * 8);
                     }
                 }
             }
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int q = i * 128 + row, kc = j * 128 + q4 * 32;
+                    uint32_t bits = 0xFFFFFFFFu;
+                    if (p.thresh16 && i < n_qt && j < n_kh && q < p.S && kc < p.S)
+                        bits = p.keepbits[((long long)(b * p.nh + h) * p.S + q) * (p.S >> 5) + (kc >> 5)];
+                    kbits[j][i] = bits;
+                }
+            if (ok[0]) L0 = p.lse[(long long)(b * p.nh + h) * p.S + row];
+            if (ok[1]) L1 = p.lse[(long long)(b * p.nh + h) * p.S + 128 + row];
             float part[2] = {0.f, 0.f};
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 if (ok[i]) {
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
+                    for (int c = 0; c < 2; ++c) {
                         float a[8], d8[8];
                         unpack8(ov[i][c], a);
                         unpack8(dv[i][c], d8);
@@ -402,60 +438,97 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                     }
                 }
             }
-            // exchange the two halves of each row through shared memory (sPd is free until the first block)
+            // exchange the four quarters of each row through shared memory (sPd is free until the first block)
             float* ex = reinterpret_cast<float*>(sPd);
-            ex[(half * 2 + 0) * 128 + row] = part[0];
-            ex[(half * 2 + 1) * 128 + row] = part[1];
-            named_bar_sync(1, 256);
-            delta0 = part[0] + ex[((half ^ 1) * 2 + 0) * 128 + row];
-            delta1 = part[1] + ex[((half ^ 1) * 2 + 1) * 128 + row];
-            if (ok[0]) L0 = p.lse[(long long)(b * p.nh + h) * p.S + row];
-            if (ok[1]) L1 = p.lse[(long long)(b * p.nh + h) * p.S + 128 + row];
+            ex[(q4 * 2 + 0) * 128 + row] = part[0];
+            ex[(q4 * 2 + 1) * 128 + row] = part[1];
+            named_bar_sync(1, BWD_SM_THREADS);
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+                delta0 += ex[(qq * 2 + 0) * 128 + row];
+                delta1 += ex[(qq * 2 + 1) * 128 + row];
+            }
         }
-        named_bar_sync(1, 256);
+        named_bar_sync(1, BWD_SM_THREADS);
         const float sc = p.scale;
         uint32_t ph1 = 0;
         int blk = 0;
         // bias gradient of the QKV projection = column sums of dQ | dK | dV: thread (w = lane, rg = e) adds the column pair
-        // (2w, 2w+1) over rows [16 rg, 16 rg + 16) of every drained tile, from the staged bf16 values
+        // (2w, 2w+1) over rows [8 rg, 8 rg + 8) of every drained tile, from the staged bf16 values
         float bsum[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
-        for (int j = 0; j < n_kh; ++j) {
-            for (int i = 0; i < n_qt; ++i, ++blk) {
+        // TMEM accumulator columns `col` (this thread: row `row`, 16 of the 64 columns) -> bf16 -> swizzled staging tile
+        auto stage_acc = [&](uint32_t col, uint8_t* tile) {
+            float v[16];
+            ptx::tmem_ld16(lane_addr + col + q4 * 16, v);
+            ptx::tmem_ld_wait();
+            uint8_t* stg = tile + row * 128;
+#pragma unroll
+            for (int x = 0; x < 2; ++x) {
+                const int chunk = (q4 * 2 + x) ^ (row & 7);
+                *reinterpret_cast<bf16x8*>(stg + chunk * 16) = pack8(v + 8 * x);
+            }
+        };
+        auto colsum_tile = [&](const uint8_t* tile, int row0, float* bs) {
+            const int nrows = min(128, p.S - row0);
+#pragma unroll
+            for (int rr = 0; rr < 8; ++rr) {
+                const int r = e * 8 + rr;
+                if (r < nrows) {
+                    const uint32_t w = *reinterpret_cast<const uint32_t*>(tile + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
+                    bs[0] += __uint_as_float(w << 16);
+                    bs[1] += __uint_as_float(w & 0xFFFF0000u);
+                }
+            }
+        };
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            if (j >= n_kh) break;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                if (i >= n_qt) break;
                 ptx::mbar_wait(&bars[1], ph1);
                 ph1 ^= 1;
                 ptx::tc_fence_after();
                 const int q = i * 128 + row;
                 const bool qvalid = q < p.S;
-                const long long grow = (long long)(b * p.nh + h) * p.S + q;
                 const float Ll = qvalid ? (i == 0 ? L0 : L1) * kLog2e : INFINITY;  // rows beyond S: p = exp2(-inf) = 0
                 const float dl = i == 0 ? delta0 : delta1;
                 const float scl = sc * kLog2e;
-#pragma unroll 1
-                for (int c = 0; c < 2; ++c) {  // 32 keys per chunk
-                    const int kl = half * 64 + c * 32;   // key offset inside the 128-key block
-                    const int kc = j * 128 + kl;         // absolute first key
-                    float s[32], dp[32];
-                    ptx::tmem_ld32(lane_addr + C_S + kl, s);
-                    ptx::tmem_ld32(lane_addr + C_DP + kl, dp);
-                    ptx::tmem_ld_wait();
-                    uint32_t bits = 0xFFFFFFFFu;  // keep bits written by the forward kernel (same Philox stream)
-                    if (p.thresh16 && qvalid && kc < p.S) bits = p.keepbits[grow * (p.S >> 5) + (kc >> 5)];
-                    float pd[32];
+                const int kl = q4 * 32;              // key offset inside the 128-key block
+                const int kc = j * 128 + kl;         // absolute first key
+                const uint32_t bits = kbits[j][i];  // keep bits written by the forward kernel (same Philox stream)
+                bf16x8 pdq[4], dsq[4];              // results stay packed (16 registers) until the stores are allowed
 #pragma unroll
-                    for (int x = 0; x < 32; ++x) {
-                        const float pr = exp2f(fmaf(s[x], scl, sMask[kc + x]) - Ll);   // sMask holds mask * log2(e)
-                        const float m = ((bits >> x) & 1u) ? p.inv_keep : 0.f;         // dropout multiplier
-                        pd[x] = pr * m;                                                // dropped probability (for dV)
-                        dp[x] = (pr * sc) * fmaf(dp[x], m, -dl);                       // dS = P (dP - delta) / sqrt(dh)
+                for (int sub = 0; sub < 2; ++sub) {  // 16 keys at a time: 96 registers per thread
+                    float s[16], dp[16];
+                    ptx::tmem_ld16(lane_addr + C_S + kl + 16 * sub, s);
+                    ptx::tmem_ld16(lane_addr + C_DP + kl + 16 * sub, dp);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int x = 0; x < 16; ++x) {
+                        const float pr = exp2f(fmaf(s[x], scl, sMask[kc + 16 * sub + x]) - Ll);  // sMask holds mask * log2(e)
+                        const float m = ((bits >> (16 * sub + x)) & 1u) ? p.inv_keep : 0.f;      // dropout multiplier
+                        s[x] = pr * m;                                                           // dropped probability (for dV)
+                        dp[x] = (pr * sc) * fmaf(dp[x], m, -dl);                                 // dS = P (dP - delta) / sqrt(dh)
                     }
-                    // 64 keys of this half = key group `half`; this chunk fills 16-byte chunks c*4 .. c*4+3 of row `row`
-                    uint8_t* bp = sPd + half * 16384 + row * 128;
-                    uint8_t* bs = sDS + half * 16384 + row * 128;
+                    pdq[2 * sub] = pack8(s);
+                    pdq[2 * sub + 1] = pack8(s + 8);
+                    dsq[2 * sub] = pack8(dp);
+                    dsq[2 * sub + 1] = pack8(dp + 8);
+                }
+                if (blk > 0) {
+                    // the previous block's accumulating products read Pd / dS from shared memory: they must have
+                    // retired before these stores (S / dP of THIS block were issued ahead of them)
+                    ptx::mbar_wait(&bars[3], (blk - 1) & 1);
+                }
+                {   // keys [kl, kl+32) -> key group kl/64, 16-byte chunks ((kl/32)&1)*4 .. +3 of row `row`
+                    uint8_t* bp = sPd + (q4 >> 1) * 16384 + row * 128;
+                    uint8_t* bs = sDS + (q4 >> 1) * 16384 + row * 128;
 #pragma unroll
                     for (int x = 0; x < 4; ++x) {
-                        const int chunk = (c * 4 + x) ^ (row & 7);
-                        *reinterpret_cast<bf16x8*>(bp + chunk * 16) = pack8(pd + 8 * x);
-                        *reinterpret_cast<bf16x8*>(bs + chunk * 16) = pack8(dp + 8 * x);
+                        const int chunk = ((q4 & 1) * 4 + x) ^ (row & 7);
+                        *reinterpret_cast<bf16x8*>(bp + chunk * 16) = pdq[x];
+                        *reinterpret_cast<bf16x8*>(bs + chunk * 16) = dsq[x];
                     }
                 }
                 ptx::fence_proxy_async_smem();
@@ -467,52 +540,51 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                 if (last_i || last_j) {
                     ptx::mbar_wait(&bars[3], blk & 1);  // this block's MMAs (incl. the accumulations) have retired
                     ptx::tc_fence_after();
-                    auto drain = [&](uint32_t col, int slot, int row0, float* bs) {
-                        float v[32];
-                        ptx::tmem_ld32(lane_addr + col + half * 32, v);
-                        ptx::tmem_ld_wait();
-                        uint8_t* stg = sPd + row * 128;  // [128 rows][128 B]; Pd/dS are free until the next arrive on bars[2]
-#pragma unroll
-                        for (int x = 0; x < 4; ++x) {
-                            const int chunk = (half * 4 + x) ^ (row & 7);
-                            *reinterpret_cast<bf16x8*>(stg + chunk * 16) = pack8(v + 8 * x);
-                        }
-                        ptx::fence_proxy_async_smem();
-                        named_bar_sync(1, 256);
-                        if (half == 0 && lane == 0) {
-                            ptx::tma_store_4d(&tmDQKV, sPd + quad * 4096, 0, row0 + quad * 32, slot, b);
-                            ptx::tma_store_commit();
-                        }
-                        if (p.gbias != nullptr) {
-                            const int nrows = min(128, p.S - row0);
-#pragma unroll 4
-                            for (int rr = 0; rr < 16; ++rr) {
-                                const int r = e * 16 + rr;
-                                if (r < nrows) {
-                                    const uint32_t w = *reinterpret_cast<const uint32_t*>(sPd + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
-                                    bs[0] += __uint_as_float(w << 16);
-                                    bs[1] += __uint_as_float(w & 0xFFFF0000u);
-                                }
-                            }
-                        }
-                        if (half == 0 && lane == 0) ptx::tma_store_wait_read<0>();
-                        named_bar_sync(1, 256);  // staging tile free again
-                    };
+                    // Pd / dS are free until the next block's stores: dK -> first 16 KB of Pd, dV -> first 16 KB of dS,
+                    // dQ -> second 16 KB of Pd; one barrier pair for all tiles of this block
                     if (last_i) {
-                        drain(C_DK, p.nh + h, j * 128, bsum[1]);
-                        drain(C_DV, 2 * p.nh + h, j * 128, bsum[2]);
+                        stage_acc(C_DK, sPd);
+                        stage_acc(C_DV, sDS);
                     }
-                    if (last_j) drain(i == 0 ? C_DQ0 : C_DQ1, h, i * 128, bsum[0]);
+                    if (last_j) stage_acc(i == 0 ? C_DQ0 : C_DQ1, sPd + 16384);
+                    ptx::fence_proxy_async_smem();
+                    named_bar_sync(1, BWD_SM_THREADS);
+                    if (q4 == 0 && lane == 0) {
+                        if (last_i) {
+                            ptx::tma_store_4d(&tmDQKV, sPd + quad * 4096, 0, j * 128 + quad * 32, p.nh + h, b);
+                            ptx::tma_store_4d(&tmDQKV, sDS + quad * 4096, 0, j * 128 + quad * 32, 2 * p.nh + h, b);
+                        }
+                        if (last_j) ptx::tma_store_4d(&tmDQKV, sPd + 16384 + quad * 4096, 0, i * 128 + quad * 32, h, b);
+                        ptx::tma_store_commit();
+                    }
+                    if (p.gbias != nullptr) {
+                        if (last_i) {
+                            colsum_tile(sPd, j * 128, bsum[1]);
+                            colsum_tile(sDS, j * 128, bsum[2]);
+                        }
+                        if (last_j) colsum_tile(sPd + 16384, i * 128, bsum[0]);
+                    }
+                    if (q4 == 0 && lane == 0) ptx::tma_store_wait_read<0>();
+                    named_bar_sync(1, BWD_SM_THREADS);  // staging tiles free again
                     ptx::tc_fence_before();
                 }
+                ++blk;
             }
         }
         if (p.gbias != nullptr) {
+            // 16 warps x 3 slots x 64 columns of partial sums -> one fp32 atomic per column per CTA
+            float* red = reinterpret_cast<float*>(sPd);  // [16][3][64]
 #pragma unroll
             for (int s3 = 0; s3 < 3; ++s3) {
-                float* gb = p.gbias + (s3 * p.nh + h) * DH + 2 * lane;
-                atomicAdd(gb, bsum[s3][0]);
-                atomicAdd(gb + 1, bsum[s3][1]);
+                red[(e * 3 + s3) * 64 + 2 * lane] = bsum[s3][0];
+                red[(e * 3 + s3) * 64 + 2 * lane + 1] = bsum[s3][1];
+            }
+            named_bar_sync(1, BWD_SM_THREADS);
+            if (t < 192) {
+                float acc = 0.f;
+#pragma unroll
+                for (int w = 0; w < BWD_SM_WARPS; ++w) acc += red[w * 192 + t];
+                atomicAdd(p.gbias + ((t >> 6) * p.nh + h) * DH + (t & 63), acc);
             }
         }
     }
