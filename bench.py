@@ -238,7 +238,10 @@ def run_ours(args):
         achieved = tot_flop / (gemm_only_ms * 1e-3) / 1e12 if gemm_only_ms > 0 else 0.0
         step_ms = ms_dev / args.steps
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "gemm_tc_kernel (all tcgen05 GEMM launches of one step)", "launches": n_tc,
+                "traffic": 135.8e6 * args.batch / 64.0,  # dram__bytes_read+write per launch, mean of 12 launches, batch 64
+                "traffic_source": "profiles/r01_ncu_summary_v10_{fwd,bwd}.txt (ncu --set full); scaled linearly with batch",
+                "algorithmic_bytes_per_launch": 122.1e6 * args.batch / 64.0,
+                "kernel": "gemm_tc_kernel (all tcgen05 GEMM launches of one step)", "launches": n_tc,
                 "gemm_ms_per_step": gemm_only_ms, "gemm_gflop_per_step": tot_flop / 1e9,
                 "method": "CUDA-event time of a captured replay of the step's GEMM launches alone (same order/buffers/streams)",
                 "gemm_marginal_ms_per_step": step_ms - no_gemm_ms,
