@@ -84,6 +84,9 @@ struct Cfg {
     static constexpr int kBlocksPerWarp = kColBlocks >= 2 ? kColBlocks / 2 : 1;
 };
 
+__device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -468,20 +471,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     ptx::tma_store_commit();
                 }
                 store_pending = true;
-                if (p.colsum != nullptr && h == 1) {
+                if (p.colsum != nullptr) {
+                    // Column sums of the staged block: lane L owns columns 2L, 2L+1; each warp of the pair takes 16 of the
+                    // 32 rows with two independent accumulator pairs.  Measured alternatives (tools/gemm_shapes.py, us per
+                    // launch at batch 64): one warp / 32 rows / scalar atomics 94, same with red.v2 98, quadrant
+                    // pre-reduction through shared-memory atomics 107, this 83 (no column sums at all: 77) -- the cost was
+                    // the dependent FADD chain on one warp of the pair, not the reductions at L2.
                     const int nrows = min(32, p.M - row0);
-                    float s0 = 0.f, s1 = 0.f;
-#pragma unroll 8
-                    for (int r = 0; r < 32; ++r) {
+                    float s0 = 0.f, s1 = 0.f, u0 = 0.f, u1 = 0.f;
+#pragma unroll
+                    for (int rr = 0; rr < 16; rr += 2) {
+                        const int r = h * 16 + rr;
+                        const uint32_t w0 = *reinterpret_cast<const uint32_t*>(blkC + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4) + (lane & 3) * 4);
+                        const uint32_t w1 = *reinterpret_cast<const uint32_t*>(blkC + (r + 1) * 128 + ((((lane >> 2) ^ ((r + 1) & 7))) << 4) + (lane & 3) * 4);
                         if (r < nrows) {
-                            const uint32_t w = *reinterpret_cast<const uint32_t*>(blkC + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4) + (lane & 3) * 4);
-                            s0 += __uint_as_float(w << 16);
-                            s1 += __uint_as_float(w & 0xFFFF0000u);
+                            s0 += __uint_as_float(w0 << 16);
+                            s1 += __uint_as_float(w0 & 0xFFFF0000u);
+                        }
+                        if (r + 1 < nrows) {
+                            u0 += __uint_as_float(w1 << 16);
+                            u1 += __uint_as_float(w1 & 0xFFFF0000u);
                         }
                     }
                     const int c = colb + 2 * lane;
-                    if (c < p.N) atomicAdd(p.colsum + c, s0);
-                    if (c + 1 < p.N) atomicAdd(p.colsum + c + 1, s1);
+                    if (c + 1 < p.N) red_add_v2(p.colsum + c, s0 + u0, s1 + u1);  // one 8-byte reduction per lane
+                    else if (c < p.N) atomicAdd(p.colsum + c, s0 + u0);
                 }
                 ++nblk;
             }
