@@ -274,8 +274,7 @@ constexpr int B_SMEM = 1024 + B_MISC + 1024 + 128;
 
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                const __grid_constant__ CUtensorMap tmDQKV, const bf16* __restrict__ ctx, const bf16* __restrict__ dctx,
-                const AttnParams p) {
+                const __grid_constant__ CUtensorMap tmDQKV, const __grid_constant__ CUtensorMap tmO, const AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint8_t* sQ = smem + B_SQ;
@@ -316,12 +315,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 
     if (warp == 0) {
         if (lane == 0) {
-            ptx::mbar_expect_tx(&bars[0], 4 * 32768);
+            // O (the forward output) lands in the idle Pd region: delta = rowsum(dO * O) is computed from shared memory, so
+            // dO is read from HBM once and no thread-issued global load sits in the prologue
+            ptx::mbar_expect_tx(&bars[0], 5 * 32768);
             for (int r = 0; r < 2; ++r) {
+                ptx::tma_load_4d(sDO + r * 16384, &tmDO, &bars[0], 0, r * 128, h, b);
+                ptx::tma_load_4d(sPd + r * 16384, &tmO, &bars[0], 0, r * 128, h, b);
                 ptx::tma_load_4d(sQ + r * 16384, &tmQKV, &bars[0], 0, r * 128, h, b);
                 ptx::tma_load_4d(sK + r * 16384, &tmQKV, &bars[0], 0, r * 128, p.nh + h, b);
                 ptx::tma_load_4d(sV + r * 16384, &tmQKV, &bars[0], 0, r * 128, 2 * p.nh + h, b);
-                ptx::tma_load_4d(sDO + r * 16384, &tmDO, &bars[0], 0, r * 128, h, b);
             }
             ptx::mbar_wait(&bars[0], 0);
             ptx::tc_fence_after();
@@ -389,29 +391,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             if (t < p.S) mv = p.mask ? (1.0f - (float)p.mask[(long long)b * p.S + t]) * (-10000.0f * kLog2e) : 0.f;
             sMask[t] = mv;
         }
-        // delta_row = sum_d dO[row,d] * O[row,d] and L_row for this thread's row in each query tile.  The four threads
-        // sharing a row split the 64 columns; explicit 128-bit loads, all issued before the arithmetic.
+        // L_row and the dropout keep bits of every block this thread will process (4 words): global loads issued first,
+        // consumed after the tiles have landed, so that none sits on the per-block critical path
         float delta0 = 0.f, delta1 = 0.f, L0 = 0.f, L1 = 0.f;
-        // dropout keep bits of every block this thread will process (4 words), fetched now so that no global load sits
-        // on the per-block critical path
         uint32_t kbits[2][2];
         {
-            bf16x8 ov[2][2], dv[2][2];
             bool ok[2];
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int q = i * 128 + row;
-                ok[i] = (i < n_qt) && (q < p.S);
-                if (ok[i]) {
-                    const bf16* o = ctx + ((long long)b * p.S + q) * H + h * DH + q4 * 16;
-                    const bf16* d = dctx + ((long long)b * p.S + q) * H + h * DH + q4 * 16;
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        ov[i][c] = ld_stream8(o + c * 8);
-                        dv[i][c] = ld_stream8(d + c * 8);
-                    }
-                }
-            }
+            for (int i = 0; i < 2; ++i) ok[i] = (i < n_qt) && (i * 128 + row < p.S);
 #pragma unroll
             for (int j = 0; j < 2; ++j)
 #pragma unroll
@@ -424,22 +411,26 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                 }
             if (ok[0]) L0 = p.lse[(long long)(b * p.nh + h) * p.S + row];
             if (ok[1]) L1 = p.lse[(long long)(b * p.nh + h) * p.S + 128 + row];
+            // delta_row = sum_d dO[row,d] * O[row,d]: the four threads sharing a row split the 64 columns (two 16-byte
+            // chunks each) of the swizzled dO / O tiles
+            ptx::mbar_wait(&bars[0], 0);
             float part[2] = {0.f, 0.f};
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
-                if (ok[i]) {
+                if (i < n_qt) {
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
+                        const int off = i * 16384 + row * 128 + (((q4 * 2 + c) ^ (row & 7)) << 4);
                         float a[8], d8[8];
-                        unpack8(ov[i][c], a);
-                        unpack8(dv[i][c], d8);
+                        unpack8(*reinterpret_cast<const bf16x8*>(sPd + off), a);
+                        unpack8(*reinterpret_cast<const bf16x8*>(sDO + off), d8);
 #pragma unroll
                         for (int x = 0; x < 8; ++x) part[i] = fmaf(a[x], d8[x], part[i]);
                     }
                 }
             }
-            // exchange the four quarters of each row through shared memory (sPd is free until the first block)
-            float* ex = reinterpret_cast<float*>(sPd);
+            // exchange the four quarters of each row through shared memory (dS is free until the first block)
+            float* ex = reinterpret_cast<float*>(sDS);
             ex[(q4 * 2 + 0) * 128 + row] = part[0];
             ex[(q4 * 2 + 1) * 128 + row] = part[1];
             named_bar_sync(1, BWD_SM_THREADS);
@@ -520,6 +511,29 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                     // the previous block's accumulating products read Pd / dS from shared memory: they must have
                     // retired before these stores (S / dP of THIS block were issued ahead of them)
                     ptx::mbar_wait(&bars[3], (blk - 1) & 1);
+                    if (i == 0) {
+                        // ... and with them dK / dV of the previous key block are final.  Drained HERE, after this block's
+                        // arithmetic, so that the wait for those MMAs is already over (draining right behind the block
+                        // that produced them exposed ~2500 cycles of it, profiles/r01_attn_bwd_timeline_v11.txt); this
+                        // block's own accumulations, which restart dK / dV, are only issued after its arrive below.
+                        ptx::tc_fence_after();
+                        stage_acc(C_DK, sPd);
+                        stage_acc(C_DV, sDS);
+                        ptx::fence_proxy_async_smem();
+                        named_bar_sync(1, BWD_SM_THREADS);
+                        if (q4 == 0 && lane == 0) {
+                            ptx::tma_store_4d(&tmDQKV, sPd + quad * 4096, 0, (j - 1) * 128 + quad * 32, p.nh + h, b);
+                            ptx::tma_store_4d(&tmDQKV, sDS + quad * 4096, 0, (j - 1) * 128 + quad * 32, 2 * p.nh + h, b);
+                            ptx::tma_store_commit();
+                        }
+                        if (p.gbias != nullptr) {
+                            colsum_tile(sPd, (j - 1) * 128, bsum[1]);
+                            colsum_tile(sDS, (j - 1) * 128, bsum[2]);
+                        }
+                        if (q4 == 0 && lane == 0) ptx::tma_store_wait_read<0>();
+                        named_bar_sync(1, BWD_SM_THREADS);  // staging tiles free again
+                        ptx::tc_fence_before();
+                    }
                 }
                 {   // keys [kl, kl+32) -> key group kl/64, 16-byte chunks ((kl/32)&1)*4 .. +3 of row `row`
                     uint8_t* bp = sPd + (q4 >> 1) * 16384 + row * 128;
@@ -534,38 +548,31 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                 ptx::fence_proxy_async_smem();
                 ptx::tc_fence_before();
                 ptx::mbar_arrive(&bars[2]);
-                // drain finished accumulators while nothing else needs these threads
-                const bool last_i = (i == n_qt - 1);
-                const bool last_j = (j == n_kh - 1);
-                if (last_i || last_j) {
-                    ptx::mbar_wait(&bars[3], blk & 1);  // this block's MMAs (incl. the accumulations) have retired
+                if (j == n_kh - 1 && i == n_qt - 1) {
+                    // last block: everything that is still in TMEM -- dK / dV of this key block and every dQ tile
+                    ptx::mbar_wait(&bars[3], blk & 1);
                     ptx::tc_fence_after();
-                    // Pd / dS are free until the next block's stores: dK -> first 16 KB of Pd, dV -> first 16 KB of dS,
-                    // dQ -> second 16 KB of Pd; one barrier pair for all tiles of this block
-                    if (last_i) {
-                        stage_acc(C_DK, sPd);
-                        stage_acc(C_DV, sDS);
-                    }
-                    if (last_j) stage_acc(i == 0 ? C_DQ0 : C_DQ1, sPd + 16384);
+                    stage_acc(C_DK, sPd);
+                    stage_acc(C_DV, sDS);
+                    stage_acc(C_DQ0, sPd + 16384);
+                    if (n_qt > 1) stage_acc(C_DQ1, sDS + 16384);
                     ptx::fence_proxy_async_smem();
                     named_bar_sync(1, BWD_SM_THREADS);
                     if (q4 == 0 && lane == 0) {
-                        if (last_i) {
-                            ptx::tma_store_4d(&tmDQKV, sPd + quad * 4096, 0, j * 128 + quad * 32, p.nh + h, b);
-                            ptx::tma_store_4d(&tmDQKV, sDS + quad * 4096, 0, j * 128 + quad * 32, 2 * p.nh + h, b);
-                        }
-                        if (last_j) ptx::tma_store_4d(&tmDQKV, sPd + 16384 + quad * 4096, 0, i * 128 + quad * 32, h, b);
+                        ptx::tma_store_4d(&tmDQKV, sPd + quad * 4096, 0, j * 128 + quad * 32, p.nh + h, b);
+                        ptx::tma_store_4d(&tmDQKV, sDS + quad * 4096, 0, j * 128 + quad * 32, 2 * p.nh + h, b);
+                        ptx::tma_store_4d(&tmDQKV, sPd + 16384 + quad * 4096, 0, quad * 32, h, b);
+                        if (n_qt > 1) ptx::tma_store_4d(&tmDQKV, sDS + 16384 + quad * 4096, 0, 128 + quad * 32, h, b);
                         ptx::tma_store_commit();
                     }
                     if (p.gbias != nullptr) {
-                        if (last_i) {
-                            colsum_tile(sPd, j * 128, bsum[1]);
-                            colsum_tile(sDS, j * 128, bsum[2]);
-                        }
-                        if (last_j) colsum_tile(sPd + 16384, i * 128, bsum[0]);
+                        colsum_tile(sPd, j * 128, bsum[1]);
+                        colsum_tile(sDS, j * 128, bsum[2]);
+                        colsum_tile(sPd + 16384, 0, bsum[0]);
+                        if (n_qt > 1) colsum_tile(sDS + 16384, 128, bsum[0]);
                     }
                     if (q4 == 0 && lane == 0) ptx::tma_store_wait_read<0>();
-                    named_bar_sync(1, BWD_SM_THREADS);  // staging tiles free again
+                    named_bar_sync(1, BWD_SM_THREADS);  // the bias-sum scratch below reuses Pd
                     ptx::tc_fence_before();
                 }
                 ++blk;
@@ -677,10 +684,12 @@ extern "C" int polus_attention_bwd(const polus_bf16_t* qkv, const int32_t* mask,
     POLUS_REQUIRE(polus_attention_supported(S, dh), "polus_attention_bwd: needs head_dim 64 and S <= 256, S %% 32 == 0 (got S=%d dh=%d)", S, dh);
     POLUS_REQUIRE(p_drop == 0.f || keepbits != nullptr, "polus_attention_bwd: dropout needs the forward's keepbits");
     if (B == 0) return 0;
-    CUtensorMap tq, tdo, tdq;
+    CUtensorMap tq, tdo, tdq, to;
     int rc = head_map(&tq, qkv, B, S, 3 * nh, 128);
     if (rc) return rc;
     rc = head_map(&tdo, dctx, B, S, nh, 128);
+    if (rc) return rc;
+    rc = head_map(&to, ctx, B, S, nh, 128);
     if (rc) return rc;
     rc = head_map(&tdq, dqkv, B, S, 3 * nh, 32);
     if (rc) return rc;
@@ -690,7 +699,7 @@ extern "C" int polus_attention_bwd(const polus_bf16_t* qkv, const int32_t* mask,
         set = true;
     }
     AttnParams p = make_params(B, S, nh, p_drop, seed, site, d_step, mask, const_cast<float*>(lse), const_cast<uint32_t*>(keepbits), gbias_qkv);
-    POLUS_CHECK_CUDA(polus_launch_pdl(attn_bwd_kernel, dim3(B * nh), dim3(BWD_THREADS), B_SMEM, (cudaStream_t)stream, tq, tdo, tdq, (const bf16*)ctx, (const bf16*)dctx, p));
+    POLUS_CHECK_CUDA(polus_launch_pdl(attn_bwd_kernel, dim3(B * nh), dim3(BWD_THREADS), B_SMEM, (cudaStream_t)stream, tq, tdo, tdq, to, p));
     g_launch_count++;
     POLUS_LAUNCH_CHECK();
     return 0;
