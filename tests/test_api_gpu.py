@@ -176,3 +176,26 @@ def test_bert_large_dims_seq512_parity():
     from tests.parity import run_tiny_ner_parity
     r = run_tiny_ner_parity(steps=2, B=1, S=512, H=1024, nh=16, I=4096, L=1, vocab=1200)
     assert r["ok"], r
+
+
+def test_ner_sequential_metrics_on_device():
+    """§8f rank 1 (validation path): token-level MacroF1 / Accuracy over [B, S] label tensors -- confusion matrix built by
+    polus_confusion_matrix on the device, bit-exact against numpy; formulas of polus/ner/metrics.py:39-72."""
+    from polus_b200 import device
+    from polus_b200.ner.metrics import Accuracy, MacroF1Score
+    device.init(0)
+    rng = np.random.default_rng(5)
+    K = 4
+    f1, acc = MacroF1Score(num_classes=K), Accuracy(num_classes=K)
+    cm = np.zeros((K, K), np.int64)
+    for _ in range(3):
+        y = rng.integers(0, K, (16, 256)).astype(np.int32)
+        p = np.where(rng.random((16, 256)) < 0.7, y, rng.integers(0, K, (16, 256))).astype(np.int32)
+        f1.samples_from_batch((y, p))
+        acc.samples_from_batch((y, p))
+        np.add.at(cm, (y.reshape(-1), p.reshape(-1)), 1)
+    assert np.array_equal(f1.confusion_matrix, cm)
+    tp = np.diag(cm).astype(np.float64)
+    prec, rec = tp / cm.sum(-1), tp / cm.sum(-2)
+    assert f1.evaluate() == pytest.approx(float(np.mean(2 / (1 / rec + 1 / prec))), rel=1e-12)
+    assert acc.evaluate() == pytest.approx(float(tp.sum() / cm.sum()), rel=1e-12)

@@ -259,3 +259,47 @@ def test_mock_horovod_surface():
     assert hvd.DistributedGradientTape(t) is t
     assert hvd.broadcast_variables([1, 2], root_rank=0) is None
     assert hvd.allgather_object({"a": 1}) == [{"a": 1}]
+
+
+def test_decode_bio_round_trip_and_error_counts():
+    """§8f rank 1: BIO decoding (reference polus/ner/bio.py:115-188, with its loop-state bug fixed) inverts get_bio and
+    counts the two error classes the reference logs."""
+    from polus_b200.ner.bio import decode_bio, get_bio
+    spans = [(0, 3), (4, 9), (10, 12), (13, 20), (21, 25), (26, 30)]
+    ents = [(4, 12, "Chemical"), (21, 25, "Chemical")]
+    tags = get_bio(spans, ents)
+    assert tags == ["O", "B-Chemical", "I-Chemical", "O", "B-Chemical", "O"]
+    es, counts = decode_bio(tags, spans)
+    assert es == set(ents) and counts == {"tags": 6, "inside_tag_after_other_tag": 0, "inside_tag_with_different_entity_type": 0}
+    # I after O opens an entity; I of another type closes + reopens; the trailing entity is flushed
+    es, counts = decode_bio(["I-Chemical", "I-Gene", "O", "B-Chemical", "B-Chemical", "I-Chemical"], spans, allow_errors=True)
+    assert es == {(0, 3, "Chemical"), (4, 9, "Gene"), (13, 20, "Chemical"), (21, 30, "Chemical")}
+    assert counts["inside_tag_after_other_tag"] == 1 and counts["inside_tag_with_different_entity_type"] == 1
+    with pytest.raises(AssertionError):
+        decode_bio(["O", "I-Chemical"], spans[:2])
+
+
+def test_entity_f1_strict_matching_and_window_filter():
+    """Entity-level F1 (reference polus/ner/metrics.py:8-21 + ner/utils.py:231-308): strict span+type match, documents
+    assembled from windows in arrival order, positions with is_prediction == 0 ignored."""
+    from polus_b200.ner.metrics import EntityF1, eval_list_of_entity_sets, precision_recall_f1
+    from polus_b200.ner.utils import TAG2INT as T
+    O, B, I, P = T["O"], T["B-Chemical"], T["I-Chemical"], T["PAD"]
+    spans = np.array([[[0, 2], [3, 5], [6, 8], [9, 11]], [[6, 8], [9, 11], [12, 14], [0, 0]]])
+    batch = {"identifier": np.array(["doc1", "doc1"]), "spans": spans,
+             "tags_int": np.array([[B, I, O, B], [O, B, I, P]]),
+             "tags_int_pred": np.array([[B, I, O, B], [B, B, O, P]]),
+             "is_prediction": np.array([[1, 1, 1, 1], [0, 0, 1, 0]])}  # second window: only its third token is new
+    m = EntityF1()
+    m.samples_from_batch(batch)
+    r = m.evaluate_ner()
+    # gold: (0,5), (9,14)   pred: (0,5), (9,11)   -> tp 1, fp 1, fn 1
+    assert (r["tp"], r["fp"], r["fn"]) == (1, 1, 1) and r["f1"] == 0.5
+    assert precision_recall_f1(0, 0, 0)[2] != precision_recall_f1(0, 0, 0)[2]  # nan
+    assert precision_recall_f1(0, 0, 0, return_nan=False) == (0.0, 0.0, 0.0)
+    assert eval_list_of_entity_sets([{(0, 1, "A")}], [{(0, 1, "A"), (2, 3, "A")}])["precision"] == 0.5
+    # gold supplied as entity lists instead of gold tags
+    m2 = EntityF1(gold={"doc1": [(0, 5, "Chemical"), (9, 14, "Chemical")]})
+    del batch["tags_int"]
+    m2.samples_from_batch([batch])
+    assert m2.evaluate() == 0.5
