@@ -182,10 +182,19 @@ def run_ours(args):
         _lib.call("polus_event_elapsed_ms", e0, e1, C.byref(ms))
         return ms.value, _lib.call("polus_launch_count") - l0, float(last)
 
+    # bring the GPU to its steady operating point (power-capped clocks) before either timed region: the first seconds
+    # after start-up run at boost clocks, which made whichever region came first look 3-5 % faster than the other
+    t_heat = time.time()
+    while time.time() - t_heat < args.preheat_s:
+        for i in range(10):
+            last = trainer.train_step(*dev_batches[i % len(dev_batches)])
+        float(last)
+    dbg("pre-heat done")
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ms_dev, launches, loss_dev = timed(dev_batches)
     dbg("timed (resident) done")
     ms_e2e, _, loss_e2e = timed(batches)
+    h2d = trainer.last_h2d_bytes  # bytes the public API copied host -> device for ONE step of the e2e region
     dbg("timed (e2e) done")
     clocks = sampler.stop() if sampler else None
     if world > 1:
@@ -283,13 +292,13 @@ def run_ours(args):
     seqs = args.batch * world * args.steps
     value = seqs / (ms_dev * 1e-3)
     e2e_value = seqs / (ms_e2e * 1e-3)
-    h2d = trainer.last_h2d_bytes
     line = {"metric": "train_sequences_per_second", "value": value, "unit": "sequences/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"BERT-base (L12 H768 nh12 I3072) polus.ner token classification + CRF, seq {SEQ}, "
                                    f"batch {args.batch}/GPU, dropout 0.1, Adam+warmup",
                        "global_batch": args.batch * world, "seq_len": SEQ, "parallelism": f"dp{world}",
+                       "preheat_s": args.preheat_s,
                        "l2": "per-step working set (weights 0.2 GB bf16 + activations > 3 GB) exceeds the 126 MB L2; no flush needed",
                        "loss_last": loss_dev},
             "clocks": clocks,
@@ -315,6 +324,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="sequences per GPU per step (weak scaling: global batch = batch x N)")
     ap.add_argument("--ref-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--preheat-s", type=float, default=1.5, help="untimed steps run for this long before the timed regions")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

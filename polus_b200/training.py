@@ -113,36 +113,87 @@ def _leaf_dtype(x):
     return I32
 
 
+_STAGE_SLOTS = 3   # pinned / device staging ring of the input feed
+_copy_stream = [None]
+
+
+def _h2d_stream():
+    if _copy_stream[0] is None:
+        st = C.c_void_p()
+        _lib.call("polus_stream_create", C.byref(st), 0)
+        _copy_stream[0] = st.value
+    return _copy_stream[0]
+
+
+def _new_event():
+    ev = C.c_void_p()
+    _lib.call("polus_event_create", C.byref(ev))
+    return ev.value
+
+
 class _CompiledStep:
-    """One captured CUDA graph + its static input buffers (one per input signature)."""
+    """One captured CUDA graph + its static input buffers (one per input signature).
+
+    Input feed (host batches): the graph reads fixed device buffers.  Each step's numpy leaves are copied into one slot
+    of a ring of pinned host buffers, shipped by an async H2D copy on a dedicated copy stream into that slot's device
+    staging buffers -- overlapping the previous step's compute -- and moved into the graph's inputs by a device-to-device
+    copy on the compute stream right before the replay.  A slot is rewritten only after the event recorded behind its
+    D2D copy has completed, so the host can run ahead of the device without overwriting a batch still in flight."""
 
     def __init__(self, trainer, struct, leaves):
         self.struct = struct
         self.inputs = []   # device tensors the graph reads
-        self.staging = []  # pinned host arrays
+        self.host_leaf = []
         for x in leaves:
             dt = _leaf_dtype(x)
             shape = x.shape if isinstance(x, Tensor) else np.asarray(x).shape
             self.inputs.append(Tensor(shape, dt))
-            self.staging.append(None if isinstance(x, Tensor) else device.PinnedArray(shape, tensor._NP[dt]))
-        self.h2d_bytes = sum(t.nbytes for t, s in zip(self.inputs, self.staging) if s is not None)
+            self.host_leaf.append(not isinstance(x, Tensor))
+        self.staging = None    # [slot][leaf] pinned host arrays (created on the first host-fed step)
+        self.dev_stage = None  # [slot][leaf] device staging tensors
+        self.slot_done = [None] * _STAGE_SLOTS   # event behind the D2D copies that consumed the slot
+        self.slot_h2d = [None] * _STAGE_SLOTS    # event behind the slot's H2D copies (copy stream)
+        self.pos = 0
+        self.h2d_bytes = 0
         self.blocks = None
         self.graph = None
         self.loss = None
         self.trainer = trainer
 
+    def _ensure_staging(self):
+        if self.staging is None:
+            self.staging = [[device.PinnedArray(t.shape, tensor._NP[t.dtype]) for t in self.inputs] for _ in range(_STAGE_SLOTS)]
+            self.dev_stage = [[Tensor(t.shape, t.dtype) for t in self.inputs] for _ in range(_STAGE_SLOTS)]
+            for k in range(_STAGE_SLOTS):
+                self.slot_done[k], self.slot_h2d[k] = _new_event(), _new_event()
+            self._slot_used = [False] * _STAGE_SLOTS
+
     def feed(self, leaves):
         st = device.stream()
-        for i, (x, t, pin) in enumerate(zip(leaves, self.inputs, self.staging)):
-            if isinstance(x, Tensor):
-                if x.ptr != t.ptr:
-                    _lib.call("polus_memcpy_d2d", t.ptr, x.ptr, t.nbytes, st)
-            else:
-                if pin is None:
-                    pin = self.staging[i] = device.PinnedArray(t.shape, tensor._NP[t.dtype])
-                    self.h2d_bytes += t.nbytes
-                np.copyto(pin.array, np.asarray(x), casting="unsafe")
-                _lib.call("polus_memcpy_h2d", t.ptr, pin.ptr, t.nbytes, st)
+        host = [i for i, x in enumerate(leaves) if not isinstance(x, Tensor)]
+        for i, (x, t) in enumerate(zip(leaves, self.inputs)):
+            if isinstance(x, Tensor) and x.ptr != t.ptr:
+                _lib.call("polus_memcpy_d2d", t.ptr, x.ptr, t.nbytes, st)
+        self.h2d_bytes = 0
+        if not host:
+            return
+        self._ensure_staging()
+        k = self.pos
+        self.pos = (k + 1) % _STAGE_SLOTS
+        if self._slot_used[k]:
+            _lib.call("polus_event_sync", self.slot_done[k])  # the batch that used this slot has reached the graph inputs
+        self._slot_used[k] = True
+        cs = _h2d_stream()
+        for i in host:
+            pin, t = self.staging[k][i], self.inputs[i]
+            np.copyto(pin.array, np.asarray(leaves[i]), casting="unsafe")
+            _lib.call("polus_memcpy_h2d", self.dev_stage[k][i].ptr, pin.ptr, t.nbytes, cs)
+            self.h2d_bytes += t.nbytes
+        _lib.call("polus_event_record", self.slot_h2d[k], cs)
+        _lib.call("polus_stream_wait_event", st, self.slot_h2d[k])
+        for i in host:
+            _lib.call("polus_memcpy_d2d", self.inputs[i].ptr, self.dev_stage[k][i].ptr, self.inputs[i].nbytes, st)
+        _lib.call("polus_event_record", self.slot_done[k], st)
 
     def capture(self):
         st = device.stream()

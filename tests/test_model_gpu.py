@@ -144,3 +144,37 @@ def test_tutorial_classifier_macro_f1():
     trainer.train()
     f1 = val.get_metrics()["MacroF1Score"][-1]
     assert f1 > 0.9, f1
+
+
+def test_host_feed_ring_keeps_batches_apart_when_host_runs_ahead(monkeypatch):
+    """The input feed (training._CompiledStep.feed): pinned staging ring + copy stream.  Feeding 10 DIFFERENT host batches
+    without ever waiting for a loss must train on exactly the batches a fully synchronous loop trains on."""
+    from polus_b200 import ops, tensor
+    from polus_b200.models import BertConfig
+    from polus_b200.ner.models import BertNERModel
+    from polus_b200.optimizers import Adam
+    from polus_b200.training import ClassifierTrainer
+    from polus_b200.utils import set_random_seed
+    from tests.parity import make_batch
+
+    rng = np.random.default_rng(9)
+    batches = []
+    for _ in range(10):
+        ids, mask, tt, tags = make_batch(rng, 4, 64, 800, 4)
+        batches.append(({"input_ids": ids, "attention_mask": mask, "token_type_ids": tt}, np.eye(4, dtype=np.float32)[tags]))
+
+    def run(sync_every_step):
+        monkeypatch.setenv("POLUS_EAGER", "0")
+        tensor.reset_arena()
+        set_random_seed(11)
+        ops.set_step(0)
+        cfg = BertConfig(vocab_size=800, hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256,
+                         max_position_embeddings=64, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+        model = BertNERModel(cfg, output_classes=4, droupout_p=0.0)
+        tr = ClassifierTrainer(model, Adam(1e-3), model.loss)
+        losses = []
+        for x, y in batches:
+            l = tr.train_step(x, y)
+            losses.append(float(l) if sync_every_step else l)
+        return [float(l) for l in losses]
+    np.testing.assert_allclose(run(False), run(True), rtol=2e-3)
