@@ -184,11 +184,11 @@ def run_ours(args):
 
     # bring the GPU to its steady operating point (power-capped clocks) before either timed region: the first seconds
     # after start-up run at boost clocks, which made whichever region came first look 3-5 % faster than the other
-    t_heat = time.time()
-    while time.time() - t_heat < args.preheat_s:
-        for i in range(10):
-            last = trainer.train_step(*dev_batches[i % len(dev_batches)])
-        float(last)
+    # (a FIXED number of steps: every rank must issue the same sequence of collectives)
+    for i in range(args.preheat_steps):
+        last = trainer.train_step(*dev_batches[i % len(dev_batches)])
+        if i % 10 == 9:
+            float(last)
     dbg("pre-heat done")
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ms_dev, launches, loss_dev = timed(dev_batches)
@@ -298,7 +298,7 @@ def run_ours(args):
             "config": {"workload": f"BERT-base (L12 H768 nh12 I3072) polus.ner token classification + CRF, seq {SEQ}, "
                                    f"batch {args.batch}/GPU, dropout 0.1, Adam+warmup",
                        "global_batch": args.batch * world, "seq_len": SEQ, "parallelism": f"dp{world}",
-                       "preheat_s": args.preheat_s,
+                       "preheat_steps": args.preheat_steps,
                        "l2": "per-step working set (weights 0.2 GB bf16 + activations > 3 GB) exceeds the 126 MB L2; no flush needed",
                        "loss_last": loss_dev},
             "clocks": clocks,
@@ -324,7 +324,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="sequences per GPU per step (weak scaling: global batch = batch x N)")
     ap.add_argument("--ref-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--preheat-s", type=float, default=1.5, help="untimed steps run for this long before the timed regions")
+    ap.add_argument("--preheat-steps", type=int, default=100, help="untimed steps before the timed regions (~1.4 s at batch 64)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
