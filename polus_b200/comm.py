@@ -195,26 +195,14 @@ class _DistributedTape:
     def __init__(self, tape):
         self.tape = tape
 
-    def gradient(self, loss, weights):
-        tape = self.tape
-        buckets = plan_buckets(weights)
-        # a bucket is complete once backward has run the EARLIEST forward node that touches any of its params
-        first_use = {}
-        for idx, node in enumerate(tape.nodes):
-            for t in node.inputs:
-                if isinstance(t, Param) and id(t) not in first_use:
-                    first_use[id(t)] = idx
-        ready_at = []
-        for b in buckets:
-            uses = [first_use[id(p)] for p in b[3] if id(p) in first_use]
-            ready_at.append(min(uses) if uses else len(tape.nodes))
+    def gradient(self, loss, weights, on_bucket_ready=None):
         from . import ops
+        tape = self.tape
         comm_stream, main = _state["comm_stream"], device.stream()
-        pending = sorted(range(len(buckets)), key=lambda i: -ready_at[i])
         events = []
 
-        def launch(i):
-            ch, off, n, _ = buckets[i]
+        def launch(bucket):
+            ch, off, n, _ = bucket
             ev = C.c_void_p()
             _lib.call("polus_event_create", C.byref(ev))
             _lib.call("polus_event_record", ev, main)
@@ -222,13 +210,12 @@ class _DistributedTape:
             ops.side_join(comm_stream)  # weight gradients of this bucket issued on the background stream
             _lib.call("polus_comm_allreduce_f32", ch.g.ptr + off * 4, n, comm_stream)
             events.append(ev)
+            if on_bucket_ready is not None:
+                on_bucket_ready(ch, off, n, after=comm_stream)  # the update waits for the reduced bucket only
 
-        def before_node(idx):
-            while pending and ready_at[pending[0]] > idx:
-                launch(pending.pop(0))
+        before_node, flush = ops.bucket_schedule(tape.nodes, weights, launch)
         grads = ops.run_backward(tape.nodes, loss, before_node)
-        while pending:
-            launch(pending.pop(0))
+        flush()
         tape.nodes = []
         # join: the optimizer (main stream) must see every reduced bucket
         done = C.c_void_p()

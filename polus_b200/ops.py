@@ -88,12 +88,45 @@ class GradientTape:
     def stop_recording(self):
         return GradientTape._Pause(self)
 
-    def gradient(self, loss, weights):
+    def gradient(self, loss, weights, on_bucket_ready=None):
         """Back-propagate from a scalar loss.  Returns the gradient tensors of `weights` (views of the
-        gradient arena for Params)."""
-        grads = run_backward(self.nodes, loss)
+        gradient arena for Params).  on_bucket_ready(chunk, offset, n_elems): called during the sweep as soon as every
+        gradient of a contiguous ~64 MB span of the arena is final (the optimizer updates that span on a side stream
+        while backward continues, training.BaseTrainer._step_body)."""
+        before = None
+        if on_bucket_ready is not None:
+            before, flush = bucket_schedule(self.nodes, weights, lambda b: on_bucket_ready(b[0], b[1], b[2]))
+        grads = run_backward(self.nodes, loss, before)
+        if on_bucket_ready is not None:
+            flush()
         self.nodes = []
         return [w.grad if isinstance(w, Param) else _materialise(grads.get(id(w))) for w in weights]
+
+
+def bucket_schedule(nodes, weights, launch):
+    """(before_node, flush) for run_backward: `launch(bucket)` fires once backward has passed the EARLIEST forward node
+    that reads any parameter of the bucket, i.e. when all its gradients are final and its weights are no longer read."""
+    from . import comm
+    buckets = comm.plan_buckets(weights)
+    first_use = {}
+    for idx, node in enumerate(nodes):
+        for t in node.inputs:
+            if isinstance(t, Param) and id(t) not in first_use:
+                first_use[id(t)] = idx
+    ready_at = []
+    for b in buckets:
+        uses = [first_use[id(p)] for p in b[3] if id(p) in first_use]
+        ready_at.append(min(uses) if uses else len(nodes))
+    pending = sorted(range(len(buckets)), key=lambda i: -ready_at[i])
+
+    def before_node(idx):
+        while pending and ready_at[pending[0]] > idx:
+            launch(buckets[pending.pop(0)])
+
+    def flush():
+        while pending:
+            launch(buckets[pending.pop(0)])
+    return before_node, flush
 
 
 def _materialise(g):
@@ -216,6 +249,7 @@ def side_reset():
     """Called when a capture begins: events of an earlier capture may be reused."""
     _side["next"] = 0
     _side["dirty"] = False
+    _side["opt_dirty"] = False
 
 
 def side_fork():
@@ -229,6 +263,36 @@ def side_fork():
     _lib.call("polus_stream_wait_event", _side["stream"], ev)
     _side["dirty"] = True
     return _side["stream"]
+
+
+def opt_stream_after(*streams):
+    """Stream for early optimizer updates (training._step_body): it first observes everything issued so far on
+    `streams`.  Separate from the wgrad side stream so that an update waiting for its allreduce never blocks wgrads."""
+    if _side.get("opt") is None:
+        s = C.c_void_p()
+        _lib.call("polus_stream_create", C.byref(s), 2)
+        _side["opt"] = s.value
+    for st in streams:
+        if st is None:
+            continue
+        ev = _side_event()
+        _lib.call("polus_event_record", ev, st)
+        _lib.call("polus_stream_wait_event", _side["opt"], ev)
+    _side["opt_dirty"] = True
+    return _side["opt"]
+
+
+def opt_stream_join():
+    """Main stream waits for every early optimizer update."""
+    if _side.get("opt_dirty"):
+        ev = _side_event()
+        _lib.call("polus_event_record", ev, _side["opt"])
+        _lib.call("polus_stream_wait_event", device.stream(), ev)
+        _side["opt_dirty"] = False
+
+
+def side_stream_if_dirty():
+    return _side["stream"] if _side["dirty"] else None
 
 
 def side_join(stream=None):

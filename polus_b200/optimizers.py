@@ -76,6 +76,7 @@ class Adam:
         self._state = {}            # chunk id -> (m Buffer, v Buffer, decay Buffer|None)
         self._ranges_key = None
         self._ranges = None
+        self._early = []            # (chunk, off, n) spans already updated during this step's backward
 
     @property
     def lr(self):
@@ -132,19 +133,49 @@ class Adam:
                 out.append([ch, off, n])
         return out
 
+    def _launch(self, ch, off, n, increment, stream):
+        cfg = self._cfg()
+        m, v, dm, _ = self._chunk_state(ch)
+        _lib.call("polus_adam", ch.p.ptr + off * 4, ch.g.ptr + off * 4, m.ptr + off * 4, v.ptr + off * 4,
+                  ch.pb.ptr + off * 2, (dm.ptr + off) if dm is not None else None, n, C.byref(cfg), ops.step_counter(),
+                  1 if increment else 0, stream)
+
+    def apply_span_early(self, ch, off, n, after=None):
+        """Update one contiguous arena span while backward is still running (its gradients are final and, with `after`
+        = the collective stream, reduced).  Runs on the optimizer side stream: the HBM-bound update hides under the
+        tensor-bound GEMMs of the earlier layers instead of standing alone at the end of the step.  The step counter
+        (bias correction, LR schedule, dropout streams) is advanced by apply_gradients, after every span."""
+        if id(ch) not in self._state:
+            return False  # slots are created on the first (op-by-op) step, never inside a capture
+        stream = ops.opt_stream_after(after) if after is not None else ops.opt_stream_after(device.stream(), ops.side_stream_if_dirty())
+        self._launch(ch, off, n, False, stream)
+        self._early.append((id(ch), off, n))
+        return True
+
     def apply_gradients(self, grads_and_vars):
         weights = [w for g, w in grads_and_vars if g is not None]
         key = tuple(id(w) for w in weights)
         if key != self._ranges_key:
             self._ranges_key, self._ranges = key, self._contiguous_ranges(weights)
-        cfg = self._cfg()
-        step_ptr = ops.step_counter()
-        n_ranges = len(self._ranges)
-        for i, (ch, off, n) in enumerate(self._ranges):
-            m, v, dm, _ = self._chunk_state(ch)
-            _lib.call("polus_adam", ch.p.ptr + off * 4, ch.g.ptr + off * 4, m.ptr + off * 4, v.ptr + off * 4,
-                      ch.pb.ptr + off * 2, (dm.ptr + off) if dm is not None else None, n, C.byref(cfg), step_ptr,
-                      1 if i == n_ranges - 1 else 0, device.stream())
+        ops.opt_stream_join()
+        # spans the backward sweep already updated are cut out of the contiguous runs
+        todo = []
+        for ch, off, n in self._ranges:
+            cuts = sorted((o, m) for c, o, m in self._early if c == id(ch) and o >= off and o + m <= off + n)
+            pos = off
+            for o, m in cuts:
+                if o > pos:
+                    todo.append((ch, pos, o - pos))
+                pos = max(pos, o + m)
+            if pos < off + n:
+                todo.append((ch, pos, off + n - pos))
+        self._early = []
+        st = device.stream()
+        if not todo:
+            ch = self._ranges[0][0]
+            self._launch(ch, self._ranges[0][1], 0, True, st)  # nothing left: only advance the step counter
+        for i, (ch, off, n) in enumerate(todo):
+            self._launch(ch, off, n, i == len(todo) - 1, st)
 
 
 class AdamWeightDecay(Adam):

@@ -113,6 +113,7 @@ def _leaf_dtype(x):
     return I32
 
 
+_EARLY_UPDATE = os.environ.get("POLUS_EARLY_UPDATE", "1") != "0"
 _STAGE_SLOTS = 3   # pinned / device staging ring of the input feed
 _copy_stream = [None]
 
@@ -287,7 +288,14 @@ class BaseTrainer:
             if len(current) != len(self.trainable_weights):
                 self.trainable_weights = current
         tape = self.hvd.DistributedGradientTape(tape)
-        grads = tape.gradient(loss_value, self.trainable_weights)
+        # without a gradient post-processing hook nothing reads the full gradient list before the update, so each
+        # contiguous span of the arena is updated as soon as backward has finished with it (captured steps only)
+        early = None
+        if (self.post_process_grads is None and ops.side_active() and _EARLY_UPDATE
+                and hasattr(self.optimizer, "apply_span_early")):
+            early = self.optimizer.apply_span_early
+        grads = tape.gradient(loss_value, self.trainable_weights, on_bucket_ready=early) if early is not None \
+            else tape.gradient(loss_value, self.trainable_weights)
         if self.post_process_grads is not None:
             grads = self.post_process_grads(grads)
         self.optimizer.apply_gradients(zip(grads, self.trainable_weights))
