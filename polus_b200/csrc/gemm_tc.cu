@@ -180,7 +180,11 @@ __device__ __forceinline__ void stage_row_f32(uint8_t* block, int lane, const fl
     }
 }
 
-template <int BN, bool A_MN, bool B_MN, int CG, int EPI>
+// CL = CTAs per cluster: CG, or 4 (two CTA pairs stacked along M that compute the tiles (2mt, nt) and (2mt+1, nt) and SHARE
+// the B tile: each of the four CTAs fetches half of its pair's share and multicasts it to its counterpart in the other
+// pair, so a k-block costs every CTA 24 KB of L2 reads instead of 32 KB -- the 256x256 pair tile at ~1200 TFLOP/s reads
+// ~9.5 TB/s from L2, against a measured chip limit of ~6300 B/clk, B300_MICROARCH).
+template <int BN, bool A_MN, bool B_MN, int CG, int EPI, int CL>
 __global__ void __launch_bounds__(128 + 32 * EPI, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, const TcParams p) {
@@ -189,10 +193,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int BN_LOCAL = C::BN_LOCAL;
     constexpr int B_STAGE_BYTES = C::B_STAGE_BYTES;
     constexpr uint32_t kStageTx = (A_STAGE_BYTES + B_STAGE_BYTES) * CG;  // bytes landing on the leader's barrier
-    const uint32_t cta_rank = CG == 2 ? ptx::cluster_ctarank() : 0u;
+    static_assert(CL == CG || (CL == 4 && CG == 2), "cluster is one CTA, one pair, or two pairs");
+    constexpr int PP = CL / CG;  // CTA pairs (or single CTAs) per cluster
+    const uint32_t cluster_rank = CL > 1 ? ptx::cluster_ctarank() : 0u;
+    const uint32_t cta_rank = CG == 2 ? (cluster_rank & 1u) : 0u;  // position inside the pair
+    const int cpair = CG == 2 ? (int)(cluster_rank >> 1) : 0;  // which CTA pair of the cluster
     const bool is_leader = cta_rank == 0;
-    const int tile0 = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-    const int tile_step = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int tile0 = (int)(blockIdx.x / CL);
+    const int tile_step = (int)(gridDim.x / CL);
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -219,7 +227,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
             ptx::mbar_init(&full_bar[s], 1);
-            ptx::mbar_init(&empty_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], PP);  // one commit per pair whose tensor cores read (a multicast copy of) this slot
         }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(&tfull_bar[s], 1);
@@ -234,7 +242,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (CG == 2) ptx::cluster_sync();  // peer barriers initialised before any remote arrive / multicast commit
+    if (CL > 1) ptx::cluster_sync();  // peer barriers initialised before any remote arrive / multicast commit
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();  // operands / outputs of earlier kernels are touched only from here on
@@ -247,7 +255,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int g = r / per_group;
         const int gm = min(p.group_m, p.m_tiles - g * p.group_m);  // the last group may be narrower
         const int rr = r - g * per_group;
-        mt = g * p.group_m + rr % gm;
+        mt = (g * p.group_m + rr % gm) * PP + cpair;  // m_tiles counts cluster rows; this pair's 256-row tile inside it
         nt = rr / gm;
         sp = t % p.split_k;
         t /= p.split_k;
@@ -283,7 +291,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int g = 0; g < BM / 64; ++g)
                             load(a + g * (BK * 128), &tmA, &full_bar[stage], m0 + g * 64, kb * BK, b0, b1);
                     }
-                    if (!B_MN) {
+                    if (CL == 4) {
+                        // half of this CTA's B share (64 of its 128 tile columns), multicast to the same position of
+                        // the other pair; the other half arrives from there
+                        const uint16_t mask = (uint16_t)((1u << cta_rank) | (1u << (cta_rank + 2)));
+                        if (!B_MN) ptx::tma_load_4d_2sm_mc(b + cpair * 8192, &tmB, &full_bar[stage], mask, kb * BK, n0 + cpair * 64, b0, b1);
+                        else ptx::tma_load_4d_2sm_mc(b + cpair * (BK * 128), &tmB, &full_bar[stage], mask, n0 + cpair * 64, kb * BK, b0, b1);
+                    } else if (!B_MN) {
                         load(b, &tmB, &full_bar[stage], kb * BK, n0, b0, b1);
                     } else {
 #pragma unroll
@@ -331,7 +345,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         else ptx::umma_bf16(tmem_d, ad, bd, idesc, accum);
                     }
                     // smem slot reusable (in both CTAs of the pair) once these MMAs retire
-                    if (CG == 2) ptx::umma_commit_2sm(&empty_bar[stage]);
+                    if (CG == 2) ptx::umma_commit_2sm(&empty_bar[stage], (uint16_t)((1u << CL) - 1u));
                     else ptx::umma_commit(&empty_bar[stage]);
                     if (++stage == kStages) {
                         stage = 0;
@@ -339,7 +353,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
                 // accumulator complete -> epilogue warps of both CTAs
-                if (CG == 2) ptx::umma_commit_2sm(&tfull_bar[acc]);
+                if (CG == 2) ptx::umma_commit_2sm(&tfull_bar[acc], (uint16_t)(3u << (2 * cpair)));
                 else ptx::umma_commit(&tfull_bar[acc]);
                 if (++acc == 2) {
                     acc = 0;
@@ -502,7 +516,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                if (CG == 2) ptx::mbar_arrive_remote(&tempty_bar[acc], 0);
+                if (CG == 2) ptx::mbar_arrive_remote(&tempty_bar[acc], 2 * cpair);
                 else ptx::mbar_arrive(&tempty_bar[acc]);
             }
             if (++acc == 2) {
@@ -673,7 +687,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                if (CG == 2) ptx::mbar_arrive_remote(&tempty_bar[acc], 0);  // the leader's MMA thread waits on it
+                if (CG == 2) ptx::mbar_arrive_remote(&tempty_bar[acc], 2 * cpair);  // the pair leader's MMA thread waits on it
                 else ptx::mbar_arrive(&tempty_bar[acc]);
             }
             if (++acc == 2) {
@@ -686,7 +700,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     ptx::tc_fence_before();
     __syncthreads();
-    if (CG == 2) ptx::cluster_sync();  // the peer may still be reading our smem / arriving on our barriers
+    if (CL > 1) ptx::cluster_sync();  // the peers may still be reading our smem / arriving on our barriers
     if (warp == 2) {
         ptx::tc_fence_after();
         if (CG == 2) ptx::tmem_dealloc_2sm<C::kTmemCols>(tmem_base);
@@ -745,10 +759,10 @@ int make_map(CUtensorMap* map, const polus_operand_t& op, long long mn_len, long
     return encode_map(map, op.ptr, inner, rows, op.ld, batch0, op.bs0, batch1, op.bs1, op.mn_major ? BK : box_mn);
 }
 
-template <int BN, bool A_MN, bool B_MN, int CG, int EPI = 8>
+template <int BN, bool A_MN, bool B_MN, int CG, int EPI = 8, int CL = CG>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tc2,
            const TcParams& p_in, cudaStream_t st) {
-    auto kern = gemm_tc_kernel<BN, A_MN, B_MN, CG, EPI>;
+    auto kern = gemm_tc_kernel<BN, A_MN, B_MN, CG, EPI, CL>;
     using C = Cfg<BN, CG>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -758,18 +772,34 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
     TcParams p = p_in;
     p.n_stages = C::stages(p.stg_warp);
     POLUS_REQUIRE(p.n_stages >= 2, "polus_gemm_tc: operand ring needs at least two stages");
-    int groups = polus_num_sms() / CG;
-    if (p.num_tiles < groups) groups = p.num_tiles;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(groups * CG);
     cfg.blockDim = dim3(128 + 32 * EPI);
     cfg.dynamicSmemBytes = C::smem_bytes(p.stg_warp);
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.x = CL;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    int groups = polus_num_sms() / CL;
+    if (CL == 4) {
+        // four-CTA clusters must sit inside one GPC: not every SM can be part of one, and the persistent tile loop
+        // needs all its clusters resident at once
+        static int max_clusters = 0;
+        if (max_clusters == 0) {
+            cfg.gridDim = dim3(groups * CL);
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n > 0) max_clusters = n;
+            else max_clusters = groups;
+            cudaGetLastError();
+            if (getenv("POLUS_GEMM_DEBUG")) fprintf(stderr, "[polus_gemm_tc] 4-CTA clusters resident: %d (of %d wanted)\n", max_clusters, groups);
+        }
+        if (max_clusters < groups) groups = max_clusters;
+    }
+    if (p.num_tiles < groups) groups = p.num_tiles;
+    cfg.gridDim = dim3(groups * CL);
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
@@ -859,18 +889,28 @@ extern "C" int polus_gemm_tc(const polus_gemm_t* g, void* stream) {
         }
     }
 
+    // two-pair clusters sharing the B tile (see the kernel template): plain bf16-output GEMMs on 256-wide pair tiles
+    // with an even number of 256-row tiles.  EXPERIMENT, off by default (POLUS_GEMM_CL4=1): per SM it is ~12 % faster on
+    // the K-major-B shapes, but only 33 four-CTA clusters are resident on this part (132 of 148 SMs), so the launch as a
+    // whole ties (fwd_ffn2 54.2 vs 54.3 us, dgrad_ffn1 52.9 vs 53.1) and loses with MN-major B (fwd_qkv 56 vs 47 us).
+    // Worth it only together with a second kernel on the 16 SMs no cluster can use.
+    static const int cl4_env = getenv("POLUS_GEMM_CL4") ? atoi(getenv("POLUS_GEMM_CL4")) : 0;
+    const bool plain = g->c_dtype == POLUS_BF16 && g->act == POLUS_ACT_NONE && !g->C2 && !g->Emul;
+    const bool cl4 = cl4_env && CG == 2 && BN == 256 && plain && !g->A.mn_major && mt % 2 == 0 && split == 1;
+    const long long mt_cluster = cl4 ? mt / 2 : mt;
+
     TcParams p;
     p.M = g->M;
     p.N = g->N;
     p.K = g->K;
     p.batch0 = batch0;
-    p.m_tiles = (int)mt;
+    p.m_tiles = (int)mt_cluster;
     p.n_tiles = cdiv(g->N, BN);
     p.kb_total = kb_total;
     if (split > p.kb_total) split = p.kb_total;
     p.kb_per_split = cdiv(p.kb_total, split);
     p.split_k = cdiv(p.kb_total, p.kb_per_split);
-    p.num_tiles = (int)(mt * p.n_tiles * p.split_k * nb);
+    p.num_tiles = (int)(mt_cluster * p.n_tiles * p.split_k * nb);
     // Rasterisation: concurrently running tiles form (about) an 8 x 9 patch of the tile grid instead of a 74 x 1 column
     // strip, so each A row block and each B column block in flight is shared by 8-9 clusters (measured 1.05-1.15x).
     static const int group_env = getenv("POLUS_GEMM_GROUP_M") ? atoi(getenv("POLUS_GEMM_GROUP_M")) : 8;
@@ -894,7 +934,7 @@ extern "C" int polus_gemm_tc(const polus_gemm_t* g, void* stream) {
     CUtensorMap ta, tb, tc, tc2;
     int rc = make_map(&ta, g->A, g->M, g->K, batch0, batch1, BM);
     if (rc) return rc;
-    rc = make_map(&tb, g->B, g->N, g->K, batch0, batch1, BN / CG);
+    rc = make_map(&tb, g->B, g->N, g->K, batch0, batch1, cl4 ? BN / CG / 2 : BN / CG);
     if (rc) return rc;
     if (!p.c_f32) {  // bf16 outputs leave through TMA stores of 32-row x 64-column blocks
         rc = encode_map(&tc, g->C, g->N, g->M, g->ldc, batch0, g->cbs0, batch1, g->cbs1, 32);
@@ -917,6 +957,10 @@ extern "C" int polus_gemm_tc(const polus_gemm_t* g, void* stream) {
     if (CG == 2 && BN == 256 && !p.c_f32 && !g->A.mn_major && epi_env && (p.act != POLUS_ACT_NONE || p.has_emul || p.has_c2)) {
         if (g->B.mn_major) return launch<256, false, true, 2, 16>(ta, tb, tc, tc2, p, st);
         return launch<256, false, false, 2, 16>(ta, tb, tc, tc2, p, st);
+    }
+    if (cl4) {
+        if (g->B.mn_major) return launch<256, false, true, 2, 8, 4>(ta, tb, tc, tc2, p, st);
+        return launch<256, false, false, 2, 8, 4>(ta, tb, tc, tc2, p, st);
     }
     if (CG == 2) {
         if (BN == 128) return launch_major<128, 2>(g->A.mn_major, g->B.mn_major, ta, tb, tc, tc2, p, st);

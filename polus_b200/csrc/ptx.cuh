@@ -76,6 +76,18 @@ __device__ __forceinline__ void tma_load_4d_2sm(void* smem_dst, const CUtensorMa
         : "memory");
 }
 
+// 2-CTA + multicast: the box lands at the same CTA-relative offset in every CTA of `cta_mask`; each destination's bytes
+// complete on the barrier (same offset) of that destination's pair leader.
+__device__ __forceinline__ void tma_load_4d_2sm_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, uint16_t cta_mask,
+                                                   int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%4, %5, %6, %7}], [%2], %3;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "h"(cta_mask),
+        "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
 // TMA store: swizzled smem block -> global (rows/columns outside the tensor map are clipped)
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2, int c3) {
     asm volatile(
@@ -146,12 +158,12 @@ __device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, u
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// arrives (count 1) on the barrier at this smem offset in BOTH CTAs of the pair
-__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+// arrives (count 1) on the barrier at this smem offset in every CTA of `cta_mask` (default: both CTAs of a 2-CTA cluster)
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask = 3) {
     asm volatile(
         "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
             smem_u32(bar)),
-        "h"((uint16_t)3)
+        "h"(cta_mask)
         : "memory");
 }
 
