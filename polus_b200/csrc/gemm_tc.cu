@@ -896,7 +896,7 @@ extern "C" int polus_gemm_tc(const polus_gemm_t* g, void* stream) {
     // Worth it only together with a second kernel on the 16 SMs no cluster can use.
     static const int cl4_env = getenv("POLUS_GEMM_CL4") ? atoi(getenv("POLUS_GEMM_CL4")) : 0;
     const bool plain = g->c_dtype == POLUS_BF16 && g->act == POLUS_ACT_NONE && !g->C2 && !g->Emul;
-    const bool cl4 = cl4_env && CG == 2 && BN == 256 && plain && !g->A.mn_major && mt % 2 == 0 && split == 1;
+    const bool cl4 = cl4_env && CG == 2 && BN == 256 && plain && !g->A.mn_major && !g->B.mn_major && mt % 2 == 0 && split == 1;
     const long long mt_cluster = cl4 ? mt / 2 : mt;
 
     TcParams p;

@@ -9,7 +9,9 @@
 // shuffles; no shared memory on the forward path.  Parameter gradients use a deterministic two-stage
 // reduction (per-CTA partials in a workspace, then a column-sum kernel) instead of global atomics.
 #include "common.cuh"
+#include "ptx.cuh"
 #include <atomic>
+#include <stdlib.h>
 extern std::atomic<long long> g_launch_count;
 int polus_launch_colsum_reduce(const float* partial, int rows, int cols, float* out0, float* out1, int split, cudaStream_t st);
 
@@ -251,6 +253,163 @@ ln_res_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, con
                 reinterpret_cast<float4*>(r8)[0] = make_float4(src[0], src[1], src[2], src[3]);
                 reinterpret_cast<float4*>(r8)[1] = make_float4(src[4], src[5], src[6], src[7]);
             }
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < H; idx += blockDim.x) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) s += red[w * H + idx];
+            atomicAdd(out + idx, s);
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------ backward, rows prefetched by bulk copies
+// Same arithmetic as ln_res_bwd_kernel for H = 256 * NC.  ncu on that kernel: IPC 0.30 per scheduler, "long scoreboard"
+// the dominant stall, 16 resident warps (128 registers each hold the three column accumulators) -- every warp loads a
+// row, waits out the DRAM latency, computes, and only then asks for its next row.  Here each warp owns two shared-memory
+// row slots (dy | dy2 | z, 3 x 2H bytes); lane 0 posts the bulk copies of row k+1 before the warp starts on row k, so a
+// CTA keeps 2 x 8 rows in flight without a single extra register and the loads overlap the arithmetic.
+template <int NC>
+__global__ void __launch_bounds__(kWarps * 32, 2)
+ln_res_bwd_pf_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, const bf16* __restrict__ z, const float* __restrict__ mean_in,
+                     const float* __restrict__ rstd_in, const float* __restrict__ gamma, int M, DropCfg dc,
+                     const uint32_t* __restrict__ d_step, bf16* __restrict__ dx, bf16* __restrict__ dres,
+                     float* __restrict__ ggamma, float* __restrict__ gbeta, float* __restrict__ gbias,
+                     const uint8_t* __restrict__ keepbits) {
+    constexpr int H = NC * 256;
+    constexpr int ROWB = H * 2;  // bytes of one bf16 row
+    extern __shared__ __align__(128) uint8_t ln_smem[];
+    float* red = reinterpret_cast<float*>(ln_smem);            // [kWarps][H] reduction scratch
+    float* sg = red + kWarps * H;                               // gamma [H]
+    uint8_t* rows = reinterpret_cast<uint8_t*>(sg + H);         // [kWarps][2 slots][3][ROWB]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(rows + kWarps * 2 * 3 * ROWB);  // [kWarps][2]
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    constexpr int chunks = H >> 3;
+    pdl_trigger();
+    for (int i = threadIdx.x; i < (H >> 2); i += blockDim.x)
+        reinterpret_cast<float4*>(sg)[i] = __ldg(reinterpret_cast<const float4*>(gamma) + i);
+    if (lane == 0) {
+        ptx::mbar_init(&bars[warp * 2], 1);
+        ptx::mbar_init(&bars[warp * 2 + 1], 1);
+        ptx::fence_barrier_init();
+    }
+    float dg[NC][8], db[NC][8], dxs[NC][8];
+#pragma unroll
+    for (int i = 0; i < NC; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dg[i][j] = db[i][j] = dxs[i][j] = 0.f;
+    pdl_wait();
+    __syncthreads();
+    const uint32_t step = dc.thresh16 ? *d_step : 0u;
+    constexpr float inv_h = 1.0f / (float)H;
+    const int row_step = gridDim.x * kWarps;
+    const uint32_t tx = (dy2 != nullptr ? 3u : 2u) * ROWB;
+    uint8_t* my = rows + warp * (2 * 3 * ROWB);
+    auto post = [&](int row, int slot) {  // lane 0 only
+        uint8_t* dst = my + slot * (3 * ROWB);
+        uint64_t* bar = &bars[warp * 2 + slot];
+        ptx::mbar_expect_tx(bar, tx);
+        ptx::bulk_load(dst, dy + (long long)row * H, ROWB, bar);
+        ptx::bulk_load(dst + 2 * ROWB, z + (long long)row * H, ROWB, bar);
+        if (dy2 != nullptr) ptx::bulk_load(dst + ROWB, dy2 + (long long)row * H, ROWB, bar);
+    };
+    int row = blockIdx.x * kWarps + warp;
+    if (row < M && lane == 0) post(row, 0);
+    float rstd_n = 0.f, mean_n = 0.f;
+    if (row < M) {
+        rstd_n = rstd_in[row];
+        mean_n = mean_in[row];
+    }
+    for (int k = 0; row < M; row += row_step, ++k) {
+        const int slot = k & 1;
+        const int next = row + row_step;
+        const float rstd = rstd_n;
+        const float nmr = -mean_n * rstd;
+        ptx::fence_proxy_async_smem();  // the dy + dy2 sums written into the other slot (row k-1) vs the bulk copy about to overwrite it
+        __syncwarp();                   // every lane is done with that slot
+        if (next < M) {
+            if (lane == 0) post(next, slot ^ 1);
+            rstd_n = rstd_in[next];
+            mean_n = mean_in[next];
+        }
+        uint32_t kb[NC];
+        if (dc.thresh16 && keepbits != nullptr) {
+#pragma unroll
+            for (int i = 0; i < NC; ++i) kb[i] = keepbits[(long long)row * chunks + lane + 32 * i];
+        }
+        ptx::mbar_wait(&bars[warp * 2 + slot], (uint32_t)(k >> 1) & 1u);
+        uint8_t* src = my + slot * (3 * ROWB);
+        const long long base = (long long)row * H;
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            const int c = lane + 32 * i;
+            float dyv[8], zv[8];
+            unpack8(*reinterpret_cast<const bf16x8*>(src + c * 16), dyv);
+            unpack8(*reinterpret_cast<const bf16x8*>(src + 2 * ROWB + c * 16), zv);
+            if (dy2 != nullptr) {  // second contribution to d(y) (residual stream): bf16 sum, as the separate add kernel
+                float b2[8];       // produced, written back to the slot so that the second pass reads the same values
+                unpack8(*reinterpret_cast<const bf16x8*>(src + ROWB + c * 16), b2);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dyv[j] += b2[j];
+                const bf16x8 sum = pack8(dyv);
+                *reinterpret_cast<bf16x8*>(src + c * 16) = sum;
+                unpack8(sum, dyv);
+            }
+            const float4 g0 = reinterpret_cast<const float4*>(sg + c * 8)[0], g1 = reinterpret_cast<const float4*>(sg + c * 8)[1];
+            const float gam[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float xh = fmaf(zv[j], rstd, nmr);
+                const float g = dyv[j] * gam[j];
+                s1 += g;
+                s2 = fmaf(g, xh, s2);
+                dg[i][j] = fmaf(dyv[j], xh, dg[i][j]);
+                db[i][j] += dyv[j];
+            }
+        }
+        const float c1 = warp_sum(s1) * inv_h * rstd;
+        const float c2 = warp_sum(s2) * inv_h * rstd;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            const int c = lane + 32 * i;
+            float dyv[8], zv[8], dz[8];
+            unpack8(*reinterpret_cast<const bf16x8*>(src + c * 16), dyv);  // each lane re-reads the chunks it wrote
+            unpack8(*reinterpret_cast<const bf16x8*>(src + 2 * ROWB + c * 16), zv);
+            const float4 g0 = reinterpret_cast<const float4*>(sg + c * 8)[0], g1 = reinterpret_cast<const float4*>(sg + c * 8)[1];
+            const float gam[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float xh = fmaf(zv[j], rstd, nmr);
+                dz[j] = fmaf(-xh, c2, fmaf(dyv[j] * gam[j], rstd, -c1));
+            }
+            if (dres != nullptr && dres != dx) st_global16(dres + base + c * 8, pack8(dz));
+            if (dc.thresh16) {
+                if (keepbits != nullptr) dropout_apply8_bits(kb[i], dc.inv_keep, dz);
+                else dropout_apply8(dc.seed, dc.site, step, (unsigned long long)row * chunks + c, dc.thresh16, dc.inv_keep, dz);
+            }
+            st_global16(dx + base + c * 8, pack8(dz));
+            if (gbias != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dxs[i][j] += dz[j];
+            }
+        }
+    }
+    // CTA reduction of the parameter-gradient partials, one quantity at a time (red is [kWarps][H])
+#pragma unroll
+    for (int which = 0; which < 3; ++which) {
+        float* out = which == 0 ? ggamma : (which == 1 ? gbeta : gbias);
+        if (out == nullptr) continue;  // uniform
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            const int c = lane + 32 * i;
+            float* r8 = red + warp * H + c * 8;
+            const float* srcp = which == 0 ? dg[i] : (which == 1 ? db[i] : dxs[i]);
+            reinterpret_cast<float4*>(r8)[0] = make_float4(srcp[0], srcp[1], srcp[2], srcp[3]);
+            reinterpret_cast<float4*>(r8)[1] = make_float4(srcp[4], srcp[5], srcp[6], srcp[7]);
         }
         __syncthreads();
         for (int idx = threadIdx.x; idx < H; idx += blockDim.x) {
@@ -521,6 +680,24 @@ extern "C" int polus_ln_res_bwd(const polus_bf16_t* dy, const polus_bf16_t* dy2,
         if (smem > 48 * 1024) POLUS_CHECK_CUDA(cudaFuncSetAttribute(ln_res_bwd_kernel<NC_, FULL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         POLUS_CHECK_CUDA(polus_launch_pdl(ln_res_bwd_kernel<NC_, FULL_>, dim3(grid), dim3(kWarps * 32), smem, st, (const bf16*)dy, (const bf16*)dy2, (const bf16*)z, mean, rstd, gamma, M, H, dc, \
                                           d_step, (bf16*)dx, (bf16*)dres, ggamma, gbeta, gbias_x, keepbits));                  \
+    }
+    // rows prefetched through shared memory (H = 768: 101 KB per CTA, two CTAs per SM)
+    static const bool pf_env = !(getenv("POLUS_LN_PREFETCH") && atoi(getenv("POLUS_LN_PREFETCH")) == 0);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dy2) | reinterpret_cast<uintptr_t>(z)) & 15) == 0;
+    if (pf_env && aligned && (H == 768 || H == 512 || H == 256)) {
+        const size_t smem_pf = (size_t)(kWarps + 1) * H * sizeof(float) + (size_t)kWarps * 2 * 3 * H * 2 + kWarps * 2 * sizeof(uint64_t);
+#define LN_BWD_PF(NC_)                                                                                                          \
+    {                                                                                                                          \
+        static bool set = false;                                                                                               \
+        if (!set) { POLUS_CHECK_CUDA(cudaFuncSetAttribute(ln_res_bwd_pf_kernel<NC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pf)); set = true; } \
+        POLUS_CHECK_CUDA(polus_launch_pdl(ln_res_bwd_pf_kernel<NC_>, dim3(grid), dim3(kWarps * 32), smem_pf, st, (const bf16*)dy, (const bf16*)dy2, (const bf16*)z, mean, rstd, gamma, M, dc, \
+                                          d_step, (bf16*)dx, (bf16*)dres, ggamma, gbeta, gbias_x, keepbits));                  \
+    }
+        if (H == 768) LN_BWD_PF(3) else if (H == 512) LN_BWD_PF(2) else LN_BWD_PF(1)
+#undef LN_BWD_PF
+        g_launch_count++;
+        POLUS_LAUNCH_CHECK();
+        return 0;
     }
     if (H == 768) LN_BWD(3, true) else if (H == 1024) LN_BWD(4, true) else if (H == 256) LN_BWD(1, true) else if (H == 512) LN_BWD(2, true)
     else if (nc <= 1) LN_BWD(1, false) else if (nc == 2) LN_BWD(2, false) else if (nc == 3) LN_BWD(3, false) else if (nc == 4) LN_BWD(4, false) else LN_BWD(16, false)

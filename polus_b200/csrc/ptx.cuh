@@ -76,6 +76,13 @@ __device__ __forceinline__ void tma_load_4d_2sm(void* smem_dst, const CUtensorMa
         : "memory");
 }
 
+// 1-D bulk copy global -> shared (bytes and both addresses multiples of 16), completion on an mbarrier
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 // 2-CTA + multicast: the box lands at the same CTA-relative offset in every CTA of `cta_mask`; each destination's bytes
 // complete on the barrier (same offset) of that destination's pair leader.
 __device__ __forceinline__ void tma_load_4d_2sm_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, uint16_t cta_mask,
