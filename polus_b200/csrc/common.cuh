@@ -212,6 +212,49 @@ __device__ __forceinline__ void gelu_cdf_pdf(float x, float& cdf, float& pdf) {
     cdf = 0.5f + copysignf(r, x);
     pdf = e;
 }
+// ---- packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2 / FADD2): one issue slot for two lanes' worth of FMA-pipe work.
+// The FMA pipe itself is no faster (tools/ubench/alu.cu: 58.7 FFMA2/clk/SM vs 113 FFMA), but the GEMM epilogues that
+// evaluate GELU are bound by ISSUE slots shared with MUFU, ALU, shared-memory and TMEM instructions.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(reinterpret_cast<unsigned long long&>(d))
+        : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)), "l"(reinterpret_cast<unsigned long long&>(c)));
+    return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    float2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<unsigned long long&>(d))
+        : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+    return d;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    float2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<unsigned long long&>(d))
+        : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+    return d;
+}
+// gelu_cdf_pdf for two values at once: y = x Phi(x), d = Phi(x) + x phi(x).  Same formula and constants, so each lane's
+// result equals the scalar version's up to the fused-multiply rounding of the last two operations.
+__device__ __forceinline__ void gelu_fwd_grad2(float2 x, float2& y, float2& d) {
+    const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+    const float2 den = fma2(ax, make_float2(0.3275911f * 0.70710678118654752f, 0.3275911f * 0.70710678118654752f), make_float2(1.0f, 1.0f));
+    const float2 arg = fma2(mul2(x, x), make_float2(-0.7213475108146667f, -0.7213475108146667f), make_float2(-1.325748085975647f, -1.325748085975647f));
+    float2 t, e;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(den.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(den.y));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(arg.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(arg.y));
+    // the polynomial with all signs flipped, so that  r = 1/2 - poly t e  is one packed FMA
+    float2 np = fma2(t, make_float2(-1.3302744626998901f, -1.3302744626998901f), make_float2(1.8212559223175049f, 1.8212559223175049f));
+    np = fma2(t, np, make_float2(-1.781477928161621f, -1.781477928161621f));
+    np = fma2(t, np, make_float2(0.3565637767314911f, 0.3565637767314911f));
+    np = fma2(t, np, make_float2(-0.3193815350532532f, -0.3193815350532532f));
+    const float2 r = fma2(mul2(np, t), e, make_float2(0.5f, 0.5f));
+    const float2 cdf = add2(make_float2(0.5f, 0.5f), make_float2(copysignf(r.x, x.x), copysignf(r.y, x.y)));
+    y = mul2(x, cdf);
+    d = fma2(x, e, cdf);
+}
+
 // activations (polus_act_t)
 __device__ __forceinline__ float act_fwd(int act, float x) {
     switch (act) {

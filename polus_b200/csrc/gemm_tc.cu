@@ -153,13 +153,15 @@ __device__ __forceinline__ void stage8(uint8_t* block, int lane, int chunk, cons
 }
 // y = act(x), d = act'(x) for 8 values
 __device__ __forceinline__ void act_fwd_grad8(int act, float* v, float* d) {
-    if (act == POLUS_ACT_GELU) {  // the case that matters (warp-uniform branch)
+    if (act == POLUS_ACT_GELU) {  // the case that matters (warp-uniform branch): two values per instruction
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float cdf, pdf;
-            gelu_cdf_pdf(v[j], cdf, pdf);
-            d[j] = fmaf(v[j], pdf, cdf);
-            v[j] *= cdf;
+        for (int j = 0; j < 8; j += 2) {
+            float2 y2, d2;
+            gelu_fwd_grad2(make_float2(v[j], v[j + 1]), y2, d2);
+            v[j] = y2.x;
+            v[j + 1] = y2.y;
+            d[j] = d2.x;
+            d[j + 1] = d2.y;
         }
     } else {
 #pragma unroll
@@ -424,7 +426,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 named_bar_sync(bar_id, 64);
                 if (p.has_emul) ptx::mbar_wait(&emul_bar[pair], (uint32_t)nblk & 1u);
                 const int col0 = colb + h * 32;
-                if (col0 < p.N) {
+                if (col0 < p.N && p.has_c2 && p.c2_grad && p.N - col0 >= 32) {
+                    // activation + derivative (the FFN-up GEMM): 16 accumulator columns at a time, so that the 96
+                    // registers of this instantiation hold values, derivatives and the packed-pair temporaries
+#pragma unroll
+                    for (int sub = 0; sub < 2; ++sub) {
+                        float v[16];
+                        ptx::tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + cb * 64 + h * 32 + sub * 16, v);
+                        ptx::tmem_ld_wait();
+                        if (p.alpha != 1.0f) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] *= p.alpha;
+                        }
+                        if (add_bias) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + sub * 16) + j);
+                                v[4 * j] += bv.x;
+                                v[4 * j + 1] += bv.y;
+                                v[4 * j + 2] += bv.z;
+                                v[4 * j + 3] += bv.w;
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            float d8[8];
+                            act_fwd_grad8(p.act, v + 8 * j, d8);
+                            stage8(blkC2, lane, h * 4 + sub * 2 + j, d8);
+                            stage8(blkC, lane, h * 4 + sub * 2 + j, v + 8 * j);
+                        }
+                    }
+                } else if (col0 < p.N) {
                     float v[32];
                     ptx::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + cb * 64 + h * 32, v);
                     ptx::tmem_ld_wait();
