@@ -215,7 +215,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* tfull_bar = empty_bar + kMaxStages;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint64_t* emul_bar = tempty_bar + 2;  // [epilogue warp]: Emul tile landed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(emul_bar + kEpiWarps);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(emul_bar + 2 * kEpiWarps);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -235,7 +235,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ptx::mbar_init(&tfull_bar[s], 1);
             ptx::mbar_init(&tempty_bar[s], (EPI == 16 ? 16 : C::kEpiActive) * CG);  // one arrive per working epilogue warp of the group
         }
-        for (int s = 0; s < kEpiWarps; ++s) ptx::mbar_init(&emul_bar[s], 1);
+        for (int s = 0; s < 2 * kEpiWarps; ++s) ptx::mbar_init(&emul_bar[s], 1);
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
@@ -366,28 +366,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (EPI == 16 && warp >= 4) {
         // ------------------------------------------------------------ epilogue, 16 warps (bf16 outputs with per-element
         // math: activation + derivative, multiplier tile + column sums).  With 8 warps those epilogues ran at IPC 0.28 per
-        // scheduler -- two resident warps cannot cover MUFU / TMEM-load / shared-memory latency -- and paced the whole GEMM
-        // (profiles/r01_ncu_summary_v10_fwd.txt: tensor pipe 34 % active on the FFN-up GEMM).  Warps pair up on a block:
-        // warp (quad, cg, h) owns TMEM lanes 32*quad.. and the 32-column half h of 64-column block cg*kBPP + i; the pair
-        // shares one staging buffer (C | C2 or Emul) and one named barrier.
+        // scheduler -- two resident warps cannot cover MUFU / TMEM-load / shared-memory latency -- and paced the whole GEMM.
+        // Every warp works alone on 32-row x 32-column blocks (TMEM lanes 32*quad.., column chunks (e/4)*kCPW + i of the
+        // tile): its own 2 KB staging tile for C and 2 KB for C2 / the multiplier tile, 64-byte-swizzled, moved by TMA boxes
+        // of 32 x 32.  No barrier between warps: the first 16-warp version paired warps on 64-column blocks and spent 19 %
+        // of its samples in the pair's bar.sync (profiles/r01_ncu_summary_v13_emul.txt).
         const int e = warp - 4;
         const int quad = e & 3;
-        const int h = (e >> 2) & 1;
-        const int cg = e >> 3;
-        const int pair = quad + 4 * cg;
-        const int bar_id = 2 + pair;
-        constexpr int kBPP = (BN / 64) / 2 > 0 ? (BN / 64) / 2 : 1;  // 64-column blocks per pair per tile
-        uint8_t* blkC = sStage + pair * p.stg_warp;
-        uint8_t* blkC2 = blkC + STG_BLOCK;
+        const int csub = e >> 2;
+        constexpr int kCPW = (BN / 32) / 4 > 0 ? (BN / 32) / 4 : 1;  // 32-column chunks per warp per tile
+        const uint32_t sC = ptx::smem_u32(sStage) + (uint32_t)e * 4096u;  // [32 rows][64 B] C
+        const uint32_t sX = sC + 2048u;                                    // [32 rows][64 B] C2 or multiplier
+        const uint32_t swz = (uint32_t)((lane >> 1) & 3);                 // 64B swizzle: 16-byte chunk index ^ (row/2)%4
+        uint64_t* ebar = &emul_bar[e];
         int acc = 0;
         uint32_t acc_phase = 0;
         bool store_pending = false;
         int nblk = 0;
         auto blk_valid = [&](int t, int i) -> bool {
-            if (t >= p.num_tiles || i >= kBPP) return false;
+            if (t >= p.num_tiles || i >= kCPW) return false;
             int mt, nt, sp, b0, b1;
             decode(t, mt, nt, sp, b0, b1);
-            return nt * BN + (cg * kBPP + i) * 64 < p.N;
+            return nt * BN + (csub * kCPW + i) * 32 < p.N;
         };
         auto advance = [&](int& t, int& i) {
             ++i;
@@ -397,13 +397,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         };
         auto emul_issue = [&](int t, int i) {
-            if (h == 0 && lane == 0) {
+            if (lane == 0) {
                 int mt, nt, sp, b0, b1;
                 decode(t, mt, nt, sp, b0, b1);
-                ptx::mbar_expect_tx(&emul_bar[pair], STG_BLOCK);
-                ptx::tma_load_4d(blkC2, &tmC2, &emul_bar[pair], nt * BN + (cg * kBPP + i) * 64,
-                                 (mt * CG + (int)cta_rank) * BM + quad * 32, b0, b1);
+                ptx::mbar_expect_tx(ebar, 2048);
+                asm volatile(
+                    "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                    ::"r"(sX), "l"(reinterpret_cast<uint64_t>(&tmC2)), "r"(ptx::smem_u32(ebar)),
+                    "r"(nt * BN + (csub * kCPW + i) * 32), "r"((mt * CG + (int)cta_rank) * BM + quad * 32), "r"(b0), "r"(b1)
+                    : "memory");
             }
+        };
+        auto sts16 = [&](uint32_t tile, int chunk, const float* v8) {  // 8 values -> 16-byte chunk `chunk` of row `lane`
+            const bf16x8 q = pack8(v8);
+            const uint32_t* u = reinterpret_cast<const uint32_t*>(&q);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile + (uint32_t)lane * 64u + (((uint32_t)chunk ^ swz) << 4)),
+                         "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]) : "memory");
+        };
+        auto tma_store32 = [&](const CUtensorMap* map, uint32_t tile, int c0, int c1, int c2, int c3) {
+            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                         ::"l"(reinterpret_cast<uint64_t>(map)), "r"(tile), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
         };
         int pf_t = tile0, pf_i = -1;
         if (p.has_emul) {
@@ -418,21 +431,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int row0 = (mt * CG + (int)cta_rank) * BM + quad * 32;
             const bool add_bias = (p.bias != nullptr) && (sp == 0);
 #pragma unroll 1
-            for (int i = 0; i < kBPP; ++i) {
-                const int cb = cg * kBPP + i;
-                const int colb = nt * BN + cb * 64;
-                if (colb >= p.N) break;  // uniform for the pair
-                if (store_pending && h == 0 && lane == 0) ptx::tma_store_wait_read<0>();  // previous block's stores have read the buffer
-                named_bar_sync(bar_id, 64);
-                if (p.has_emul) ptx::mbar_wait(&emul_bar[pair], (uint32_t)nblk & 1u);
-                const int col0 = colb + h * 32;
-                if (col0 < p.N && p.has_c2 && p.c2_grad && p.N - col0 >= 32) {
-                    // activation + derivative (the FFN-up GEMM): 16 accumulator columns at a time, so that the 96
-                    // registers of this instantiation hold values, derivatives and the packed-pair temporaries
+            for (int i = 0; i < kCPW; ++i) {
+                const int cc = csub * kCPW + i;
+                const int col0 = nt * BN + cc * 32;
+                if (col0 >= p.N) break;  // warp-uniform
+                if (store_pending) {
+                    if (lane == 0) ptx::tma_store_wait_read<0>();  // the previous block's stores have read the tiles
+                    __syncwarp();
+                    store_pending = false;
+                }
+                const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + cc * 32;
+                const bool full32 = p.N - col0 >= 32;
+                if (p.has_c2 && p.c2_grad && full32) {
+                    // activation + derivative (the FFN-up GEMM): 16 accumulator columns at a time (96 registers)
 #pragma unroll
                     for (int sub = 0; sub < 2; ++sub) {
                         float v[16];
-                        ptx::tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + cb * 64 + h * 32 + sub * 16, v);
+                        ptx::tmem_ld16(tcol + sub * 16, v);
                         ptx::tmem_ld_wait();
                         if (p.alpha != 1.0f) {
 #pragma unroll
@@ -452,13 +467,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int j = 0; j < 2; ++j) {
                             float d8[8];
                             act_fwd_grad8(p.act, v + 8 * j, d8);
-                            stage8(blkC2, lane, h * 4 + sub * 2 + j, d8);
-                            stage8(blkC, lane, h * 4 + sub * 2 + j, v + 8 * j);
+                            sts16(sX, sub * 2 + j, d8);
+                            sts16(sC, sub * 2 + j, v + 8 * j);
                         }
                     }
-                } else if (col0 < p.N) {
+                } else {
                     float v[32];
-                    ptx::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + cb * 64 + h * 32, v);
+                    ptx::tmem_ld32(tcol, v);
                     ptx::tmem_ld_wait();
                     const int nvalid = min(32, p.N - col0);
                     if (p.alpha != 1.0f) {
@@ -466,7 +481,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
                     }
                     if (add_bias) {
-                        if (nvalid == 32) {
+                        if (full32) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
@@ -482,66 +497,51 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                     if (p.has_emul) {
+                        ptx::mbar_wait(ebar, (uint32_t)nblk & 1u);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
+                            bf16x8 q;
+                            uint32_t* u = reinterpret_cast<uint32_t*>(&q);
+                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3])
+                                         : "r"(sX + (uint32_t)lane * 64u + (((uint32_t)j ^ swz) << 4)));
                             float m8[8];
-                            unpack8(*reinterpret_cast<const bf16x8*>(blkC2 + lane * 128 + (((h * 4 + j) ^ (lane & 7)) << 4)), m8);
+                            unpack8(q, m8);
 #pragma unroll
                             for (int x = 0; x < 8; ++x) v[8 * j + x] *= m8[x];
                         }
-                        stage_row(blkC, lane, h, v);
-                    } else if (p.has_c2 && p.c2_grad) {
-                        // 8 values at a time: 96 registers per thread do not hold 32 results and 32 derivatives
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            float d8[8];
-                            act_fwd_grad8(p.act, v + 8 * j, d8);
-                            stage8(blkC2, lane, h * 4 + j, d8);
-                            stage8(blkC, lane, h * 4 + j, v + 8 * j);
-                        }
+                        __syncwarp();  // every lane has its multipliers: the tile may be refilled
+                        advance(pf_t, pf_i);
+                        if (pf_t < p.num_tiles) emul_issue(pf_t, pf_i);
                     } else {
-                        if (p.has_c2) stage_row(blkC2, lane, h, v);
+                        if (p.has_c2) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) sts16(sX, j, v + 8 * j);  // pre-activation copy
+                        }
                         apply_act(p.act, v);
-                        stage_row(blkC, lane, h, v);
                     }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) sts16(sC, j, v + 8 * j);
                 }
                 ptx::fence_proxy_async_smem();
-                named_bar_sync(bar_id, 64);  // both halves staged; both warps are done with the multiplier tile
-                if (p.has_emul) {
-                    advance(pf_t, pf_i);
-                    if (pf_t < p.num_tiles) emul_issue(pf_t, pf_i);
-                }
-                if (h == 0 && lane == 0) {
-                    ptx::tma_store_4d(&tmC, blkC, colb, row0, b0, b1);
-                    if (p.has_c2) ptx::tma_store_4d(&tmC2, blkC2, colb, row0, b0, b1);
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store32(&tmC, sC, col0, row0, b0, b1);  // rows >= M / columns >= N are clipped by the tensor map
+                    if (p.has_c2) tma_store32(&tmC2, sX, col0, row0, b0, b1);
                     ptx::tma_store_commit();
                 }
                 store_pending = true;
                 if (p.colsum != nullptr) {
-                    // Column sums of the staged block: lane L owns columns 2L, 2L+1; each warp of the pair takes 16 of the
-                    // 32 rows with two independent accumulator pairs.  Measured alternatives (tools/gemm_shapes.py, us per
-                    // launch at batch 64): one warp / 32 rows / scalar atomics 94, same with red.v2 98, quadrant
-                    // pre-reduction through shared-memory atomics 107, this 83 (no column sums at all: 77) -- the cost was
-                    // the dependent FADD chain on one warp of the pair, not the reductions at L2.
+                    // column sums of the staged (bf16-rounded) 32 x 32 block: lane L = column L, four independent chains
                     const int nrows = min(32, p.M - row0);
-                    float s0 = 0.f, s1 = 0.f, u0 = 0.f, u1 = 0.f;
+                    float s[4] = {0.f, 0.f, 0.f, 0.f};
+                    const uint32_t cb16 = (uint32_t)(lane >> 3), off = (uint32_t)(lane & 7) * 2u;
 #pragma unroll
-                    for (int rr = 0; rr < 16; rr += 2) {
-                        const int r = h * 16 + rr;
-                        const uint32_t w0 = *reinterpret_cast<const uint32_t*>(blkC + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4) + (lane & 3) * 4);
-                        const uint32_t w1 = *reinterpret_cast<const uint32_t*>(blkC + (r + 1) * 128 + ((((lane >> 2) ^ ((r + 1) & 7))) << 4) + (lane & 3) * 4);
-                        if (r < nrows) {
-                            s0 += __uint_as_float(w0 << 16);
-                            s1 += __uint_as_float(w0 & 0xFFFF0000u);
-                        }
-                        if (r + 1 < nrows) {
-                            u0 += __uint_as_float(w1 << 16);
-                            u1 += __uint_as_float(w1 & 0xFFFF0000u);
-                        }
+                    for (int r = 0; r < 32; ++r) {
+                        uint32_t w;
+                        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(w) : "r"(sC + (uint32_t)r * 64u + ((cb16 ^ (uint32_t)((r >> 1) & 3)) << 4) + off));
+                        if (r < nrows) s[r & 3] += __uint_as_float(w << 16);
                     }
-                    const int c = colb + 2 * lane;
-                    if (c + 1 < p.N) red_add_v2(p.colsum + c, s0 + u0, s1 + u1);  // one 8-byte reduction per lane
-                    else if (c < p.N) atomicAdd(p.colsum + c, s0 + u0);
+                    if (col0 + lane < p.N) atomicAdd(p.colsum + col0 + lane, (s[0] + s[1]) + (s[2] + s[3]));
                 }
                 ++nblk;
             }
@@ -556,7 +556,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 acc_phase ^= 1;
             }
         }
-        if (h == 0 && lane == 0) ptx::tma_store_wait_all();  // smem must outlive the bulk stores
+        if (lane == 0) ptx::tma_store_wait_all();  // smem must outlive the bulk stores
     } else if (EPI == 8 && warp >= 4 && (warp - 4) < C::kEpiActive) {
         // ------------------------------------------------------------ epilogue (TMEM lane = row)
         const int e = warp - 4;
@@ -760,7 +760,7 @@ EncodeTiledFn get_encode_fn() {
 
 // 4-D bf16 view (dim0 contiguous, rows, batch0, batch1); box = {64, box_rows, 1, 1}, 128-byte swizzle.
 int encode_map(CUtensorMap* map, const void* ptr, long long inner, long long rows, long long ld, int batch0,
-               long long bs0, int batch1, long long bs1, int box_rows, int esize = 2) {
+               long long bs0, int batch1, long long bs1, int box_rows, int esize = 2, int box_bytes = 128) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) {
         polus_set_error("cuTensorMapEncodeTiled entry point not found (driver too old?)");
@@ -768,14 +768,14 @@ int encode_map(CUtensorMap* map, const void* ptr, long long inner, long long row
     }
     cuuint64_t dims[4] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)batch0, (cuuint64_t)batch1};
     cuuint64_t strides[3];
-    cuuint32_t box[4] = {(cuuint32_t)(128 / esize), (cuuint32_t)box_rows, 1, 1};
+    cuuint32_t box[4] = {(cuuint32_t)(box_bytes / esize), (cuuint32_t)box_rows, 1, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     strides[0] = (cuuint64_t)ld * esize;
     strides[1] = (cuuint64_t)(batch0 > 1 ? bs0 * esize : rows * ld * esize);
     strides[2] = (cuuint64_t)(batch1 > 1 ? bs1 * esize : strides[1] * (cuuint64_t)batch0);
     CUresult r = enc(map, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, box_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         polus_set_error("cuTensorMapEncodeTiled failed (%d): ptr=%p inner=%lld rows=%lld ld=%lld b0=%d/%lld b1=%d/%lld",
                         (int)r, ptr, inner, rows, ld, batch0, bs0, batch1, bs1);
@@ -987,6 +987,15 @@ extern "C" int polus_gemm_tc(const polus_gemm_t* g, void* stream) {
     // the FFN-up forward GEMM and the dgrad GEMM that applies act' and sums the bias gradient)
     static const int epi_env = getenv("POLUS_GEMM_EPI16") ? atoi(getenv("POLUS_GEMM_EPI16")) : 1;
     if (CG == 2 && BN == 256 && !p.c_f32 && !g->A.mn_major && epi_env && (p.act != POLUS_ACT_NONE || p.has_emul || p.has_c2)) {
+        // 16 warps x (2 KB C + 2 KB C2 / multiplier), 32 x 32 TMA boxes with the 64-byte swizzle
+        p.stg_warp = 2 * STG_BLOCK;
+        rc = encode_map(&tc, g->C, g->N, g->M, g->ldc, batch0, g->cbs0, batch1, g->cbs1, 32, 2, 64);
+        if (rc) return rc;
+        tc2 = tc;
+        if (p.has_c2 || p.has_emul) {
+            rc = encode_map(&tc2, p.has_c2 ? g->C2 : const_cast<void*>(g->Emul), g->N, g->M, g->ldc, batch0, g->cbs0, batch1, g->cbs1, 32, 2, 64);
+            if (rc) return rc;
+        }
         if (g->B.mn_major) return launch<256, false, true, 2, 16>(ta, tb, tc, tc2, p, st);
         return launch<256, false, false, 2, 16>(ta, tb, tc, tc2, p, st);
     }

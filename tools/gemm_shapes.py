@@ -27,6 +27,8 @@ def op(ptr, ld, mn, bs0=0, bs1=0):
 
 def case(name, M_, N_, K_, A, B, ldc, c_dtype, b0=1, b1=1, cbs0=0, cbs1=0, acc=0, split=1, act=0, c2=False, use_bias=True, count=1,
          c2_kind=0, emul=False, colsum=True):
+    if os.environ.get("GEMM_ONLY") and os.environ["GEMM_ONLY"] not in name:
+        return 0.0
     g = _lib.Gemm()
     g.M, g.N, g.K, g.batch0, g.batch1 = M_, N_, K_, b0, b1
     g.A, g.B = A, B
