@@ -52,6 +52,20 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// barrier + OR-reduction of a predicate over the `nthreads` threads of named barrier `id`
+__device__ __forceinline__ bool named_bar_or(int id, int nthreads, bool pred) {
+    int r;
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        "setp.ne.s32 p, %1, 0;\n"
+        "bar.red.or.pred q, %2, %3, p;\n"
+        "selp.s32 %0, 1, 0, q;\n"
+        "}\n"
+        : "=r"(r) : "r"((int)pred), "r"(id), "r"(nthreads) : "memory");
+    return r != 0;
+}
+
 // ================================================================================================ forward
 // 288 threads: warp 0 = TMA + MMA issue, warps 1-8 = softmax (thread = (query row, key half)); 2 CTAs per SM.
 constexpr int FWD_THREADS = 288;
@@ -140,11 +154,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         const int row = quad * 32 + lane;        // row inside the tile (== TMEM lane)
         const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
         // additive key mask, staged once: (1 - m) * -10000 for real keys, -inf for keys beyond S
-        {
-            float mv = -INFINITY;
-            if (t < p.S) mv = p.mask ? (1.0f - (float)p.mask[(long long)b * p.S + t]) * -10000.0f : 0.f;
-            sMask[t] = mv;
-        }
+        float my_mask = -INFINITY;
+        if (t < p.S) my_mask = p.mask ? (1.0f - (float)p.mask[(long long)b * p.S + t]) * -10000.0f : 0.f;
+        sMask[t] = my_mask;
         // Dropout decisions of this thread's 128 probabilities, made (and written out for the backward kernel) while the
         // Q/K/V tiles are still in flight and the first MMA runs: 16 Philox blocks that used to sit between the two
         // softmax passes (attention_fwd p=0.1 vs p=0: +50 % time, profiles/r01_kernel_times_v9_b64.log).
@@ -172,7 +184,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                 }
             }
         }
-        named_bar_sync(1, 256);
+        // (barrier for sMask) + is any of the 256 key slots masked?  Sequences without padding take the branch that
+        // never reads the mask: two instructions per score fewer in each pass, and identical results (x * s + 0 == x * s)
+        const bool masked = named_bar_or(1, 256, my_mask != 0.f);
         ptx::mbar_wait(&bars[1], 0);
         ptx::tc_fence_after();
         const float sc = p.scale;
@@ -182,9 +196,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             float v[32];
             ptx::tmem_ld32(lane_addr + half * 128 + c * 32, v);
             ptx::tmem_ld_wait();
+            if (masked) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaf(v[j], sc, sMask[half * 128 + c * 32 + j]));
+                for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaf(v[j], sc, sMask[half * 128 + c * 32 + j]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) mx = fmaxf(mx, v[j]);
+            }
         }
+        if (!masked) mx *= sc;  // sc > 0: max(x_j * sc) == max(x_j) * sc, rounding included
         sRed[half * 128 + row] = mx;
         named_bar_sync(1, 256);
         mx = fmaxf(mx, sRed[(half ^ 1) * 128 + row]);  // keys beyond S are -inf, real keys finite: mx is finite
@@ -198,10 +218,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             ptx::tmem_ld32(lane_addr + half * 128 + c * 32, v);
             ptx::tmem_ld_wait();
             const int kc = half * 128 + c * 32;  // first key of this chunk
+            if (masked) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                v[j] = exp2f(fmaf(v[j], scl, fmaf(sMask[kc + j], kLog2e, -mxl)));
-                sum += v[j];
+                for (int j = 0; j < 32; ++j) {
+                    v[j] = exp2f(fmaf(v[j], scl, fmaf(sMask[kc + j], kLog2e, -mxl)));
+                    sum += v[j];
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    v[j] = exp2f(fmaf(v[j], scl, -mxl));
+                    sum += v[j];
+                }
             }
             if (p.thresh16) {
                 const uint32_t bits = kbits[c];
@@ -386,10 +414,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         const int q4 = e >> 2;            // keys [32*q4, +32) of the current 128-key block
         const int row = quad * 32 + lane;
         const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
+        float my_mask = 0.f;
         if (t < 256) {
-            float mv = -INFINITY;
-            if (t < p.S) mv = p.mask ? (1.0f - (float)p.mask[(long long)b * p.S + t]) * (-10000.0f * kLog2e) : 0.f;
-            sMask[t] = mv;
+            my_mask = -INFINITY;
+            if (t < p.S) my_mask = p.mask ? (1.0f - (float)p.mask[(long long)b * p.S + t]) * (-10000.0f * kLog2e) : 0.f;
+            sMask[t] = my_mask;
         }
         // L_row and the dropout keep bits of every block this thread will process (4 words): global loads issued first,
         // consumed after the tiles have landed, so that none sits on the per-block critical path
@@ -440,7 +469,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                 delta1 += ex[(qq * 2 + 1) * 128 + row];
             }
         }
-        named_bar_sync(1, BWD_SM_THREADS);
+        const bool masked = named_bar_or(1, BWD_SM_THREADS, my_mask != 0.f);  // (also the barrier behind the delta exchange)
         const float sc = p.scale;
         uint32_t ph1 = 0;
         int blk = 0;
@@ -495,9 +524,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                     ptx::tmem_ld16(lane_addr + C_S + kl + 16 * sub, s);
                     ptx::tmem_ld16(lane_addr + C_DP + kl + 16 * sub, dp);
                     ptx::tmem_ld_wait();
+                    if (masked) {
+#pragma unroll
+                        for (int x = 0; x < 16; ++x) s[x] = fmaf(s[x], scl, sMask[kc + 16 * sub + x]) - Ll;  // sMask holds mask * log2(e)
+                    } else {  // no padded key in this sequence: the mask is never read
+#pragma unroll
+                        for (int x = 0; x < 16; ++x) s[x] = fmaf(s[x], scl, -Ll);
+                    }
 #pragma unroll
                     for (int x = 0; x < 16; ++x) {
-                        const float pr = exp2f(fmaf(s[x], scl, sMask[kc + 16 * sub + x]) - Ll);  // sMask holds mask * log2(e)
+                        const float pr = exp2f(s[x]);
                         const float m = ((bits >> (16 * sub + x)) & 1u) ? p.inv_keep : 0.f;      // dropout multiplier
                         s[x] = pr * m;                                                           // dropped probability (for dV)
                         dp[x] = (pr * sc) * fmaf(dp[x], m, -dl);                                 // dS = P (dP - delta) / sqrt(dh)
