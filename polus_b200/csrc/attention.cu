@@ -77,8 +77,11 @@ constexpr int F_SMEM = 1024 + F_MISC + 1024 + 1024 + 64;
 
 __global__ void __launch_bounds__(FWD_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO, const AttnParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    // 1024-byte alignment (128B-swizzle atoms) comes from the declaration, which also keeps the pointer in the shared
+    // address space for the compiler: LDS / STS instead of generic LD / ST on every staging access
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;
+    if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
     uint8_t* sQ = smem + F_SQ;
     uint8_t* sK = smem + F_SK;
     uint8_t* sV = smem + F_SV;
@@ -303,8 +306,11 @@ constexpr int B_SMEM = 1024 + B_MISC + 1024 + 128;
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                 const __grid_constant__ CUtensorMap tmDQKV, const __grid_constant__ CUtensorMap tmO, const AttnParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    // 1024-byte alignment (128B-swizzle atoms) comes from the declaration, which also keeps the pointer in the shared
+    // address space for the compiler: LDS / STS instead of generic LD / ST on every staging access
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;
+    if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
     uint8_t* sQ = smem + B_SQ;
     uint8_t* sK = smem + B_SK;
     uint8_t* sV = smem + B_SV;

@@ -204,9 +204,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int tile0 = (int)(blockIdx.x / CL);
     const int tile_step = (int)(gridDim.x / CL);
 
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                               ~static_cast<uintptr_t>(1023));
+    // 1024-byte alignment (128B-swizzle atoms) comes from the declaration, which also keeps the pointer in the shared
+    // address space for the compiler (LDS / STS instead of generic LD / ST in the staging code)
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;
+    if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
     uint8_t* sA = smem;
     uint8_t* sB = smem + kStages * A_STAGE_BYTES;
     uint8_t* sStage = smem + kStages * (A_STAGE_BYTES + B_STAGE_BYTES);  // 1024-aligned (stage sizes are multiples of 4 KB)
