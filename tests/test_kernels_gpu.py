@@ -474,7 +474,8 @@ def test_skinny_linear_fwd_bwd(dev, M, K, N, act, xdt):
 
 
 @pytest.mark.parametrize("B,nh,S,p,use_mask", [(2, 2, 64, 0.0, True), (1, 3, 256, 0.1, True), (2, 2, 128, 0.0, False),
-                                               (1, 2, 192, 0.1, True), (3, 1, 32, 0.0, True), (2, 2, 96, 0.1, False)])
+                                               (1, 2, 192, 0.1, True), (3, 1, 32, 0.0, True), (2, 2, 96, 0.1, False),
+                                               (2, 2, 224, 0.1, True), (1, 2, 160, 0.0, False), (1, 1, 256, 0.1, False)])
 def test_fused_attention_fwd_bwd(dev, B, nh, S, p, use_mask):
     """Fused attention (scores/probabilities in TMEM/smem) vs the oracle with the device's own dropout masks, and vs
     the unfused GEMM+softmax path (same Philox counters => same masks)."""
