@@ -322,10 +322,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="sequences per GPU per step (weak scaling: global batch = batch x N)")
+    ap.add_argument("--batch", type=int, default=128, help="sequences per GPU per step (weak scaling: global batch = batch x N)")
     ap.add_argument("--ref-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--preheat-steps", type=int, default=100, help="untimed steps before the timed regions (~1.4 s at batch 64)")
+    ap.add_argument("--preheat-steps", type=int, default=100, help="untimed steps before the timed regions (~2.4 s at batch 128)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
