@@ -1,4 +1,4 @@
-// Fused multi-head self-attention for S <= 256, head_dim = 64 (BERT-base/large heads), forward and backward.
+// Fused multi-head self-attention for S <= 512, head_dim = 64 (BERT-base/large heads), forward and backward.
 // The S x S score / probability tensors never leave the SM: scores live in TMEM, probabilities go through shared
 // memory straight into the second tcgen05.mma.  Replaces, per layer, three batched GEMM launches + the softmax
 // kernel in forward and five launches in backward (the unfused path of ops.attention, kept for longer sequences),
@@ -14,7 +14,8 @@
 //                     (K-major A operand).  After the second MMA: O * (1/sum) -> bf16 -> smem -> TMA store into
 //                     ctx [B,S,H].  Saves L = max + log(sum) per row for backward.
 //
-// Backward, one CTA per (batch, head): blocks (query tile i, key half j) of 128x128.
+// Backward, one CTA per (batch, head, 256-query half): blocks (query tile i, key block j) of 128x128; K / V stream
+// through two 128-key stages; with two halves (S > 256) dK / dV partial sums are reduce-added in bf16 by the TMA unit.
 //   TMEM: S_ij 0..127 | dP_ij 128..255 | dQ_0 256..319 | dK_j 320..383 | dV_j 384..447 | dQ_1 448..511.
 //   smem: Q, K, V, dO (32 KB each), Pd_ij and dS_ij (32 KB each; ONE copy of dS serves both dQ += dS K (K-major A)
 //   and dK += dS^T Q (MN-major A): the two canonical layouts coincide byte for byte).
@@ -67,28 +68,36 @@ __device__ __forceinline__ bool named_bar_or(int id, int nthreads, bool pred) {
 }
 
 // ================================================================================================ forward
-// 288 threads: warp 0 = TMA + MMA issue, warps 1-8 = softmax (thread = (query row, key half)); 2 CTAs per SM.
-constexpr int FWD_THREADS = 288;
-constexpr int F_SQ = 0;                    // 16 KB  Q tile                       } P (64 KB) overlays Q, K and the
-constexpr int F_SK = 16384;                // 32 KB  K                            } 16 KB pad once S = Q K^T retired;
-constexpr int F_SV = 65536;                // 32 KB  V                              O staging reuses the first 16 KB
-constexpr int F_MISC = F_SV + 32768;       // mask [256] f32 | red [2][128] f32 | barriers
-constexpr int F_SMEM = 1024 + F_MISC + 1024 + 1024 + 64;
+// NSEG = number of 128-key segments the kernel covers: 2 for S <= 256 (288 threads, 2 CTAs per SM), 4 for S <= 512
+// (544 threads, one CTA per SM: the 128 x 512 score tile fills the SM's 512 TMEM columns).
+// warp 0 = TMA + MMA issue, warps 1..4*NSEG = softmax (thread = (query row, 128-key segment)).
+template <int NSEG> struct FwdCfg {
+    static constexpr int THREADS = 32 + 128 * NSEG;
+    static constexpr int SM_THREADS = 128 * NSEG;
+    static constexpr int SQ = 0;                      // 16 KB  Q tile                  } P (NSEG x 32 KB) overlays Q, K and
+    static constexpr int SK = 16384;                  // NSEG x 16 KB  K                } the pad behind them once S = Q K^T
+    static constexpr int SV = NSEG * 32768;           // NSEG x 16 KB  V                  retired; O staging reuses 16 KB of it
+    static constexpr int MISC = SV + NSEG * 16384;    // mask [128 NSEG] f32 | red [NSEG][128] f32 | barriers
+    static constexpr int SMEM = 1024 + MISC + NSEG * 1024 + 64;
+};
 
-__global__ void __launch_bounds__(FWD_THREADS, 2)
+template <int NSEG>
+__global__ void __launch_bounds__(FwdCfg<NSEG>::THREADS, NSEG == 2 ? 2 : 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO, const AttnParams p) {
+    using Cfg = FwdCfg<NSEG>;
+    constexpr int SMT = Cfg::SM_THREADS;
     // 1024-byte alignment (128B-swizzle atoms) comes from the declaration, which also keeps the pointer in the shared
     // address space for the compiler: LDS / STS instead of generic LD / ST on every staging access
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw;
     if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
-    uint8_t* sQ = smem + F_SQ;
-    uint8_t* sK = smem + F_SK;
-    uint8_t* sV = smem + F_SV;
+    uint8_t* sQ = smem + Cfg::SQ;
+    uint8_t* sK = smem + Cfg::SK;
+    uint8_t* sV = smem + Cfg::SV;
     uint8_t* sP = smem;  // overlay
-    float* sMask = reinterpret_cast<float*>(smem + F_MISC);
-    float* sRed = reinterpret_cast<float*>(smem + F_MISC + 1024);        // [2 halves][128 rows]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + F_MISC + 2048);  // 0 load, 1 S ready, 2 P ready, 3 O ready
+    float* sMask = reinterpret_cast<float*>(smem + Cfg::MISC);
+    float* sRed = reinterpret_cast<float*>(smem + Cfg::MISC + NSEG * 512);        // [NSEG segments][128 rows]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::MISC + NSEG * 1024);  // 0 load, 1 S ready, 2 P ready, 3 O ready
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -104,11 +113,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         ptx::prefetch_tensormap(&tmO);
         ptx::mbar_init(&bars[0], 1);
         ptx::mbar_init(&bars[1], 1);
-        ptx::mbar_init(&bars[2], 256);
+        ptx::mbar_init(&bars[2], SMT);
         ptx::mbar_init(&bars[3], 1);
         ptx::fence_barrier_init();
     }
-    if (warp == 0) ptx::tmem_alloc<256>(tmem_slot);
+    if (warp == 0) ptx::tmem_alloc<128 * NSEG>(tmem_slot);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -117,43 +126,47 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 
     if (warp == 0) {
         if (lane == 0) {
-            ptx::mbar_expect_tx(&bars[0], 16384 + 32768 + 32768);
+            ptx::mbar_expect_tx(&bars[0], 16384 + NSEG * 32768);
             ptx::tma_load_4d(sQ, &tmQKV, &bars[0], 0, q0, h, b);
-            ptx::tma_load_4d(sK, &tmQKV, &bars[0], 0, 0, p.nh + h, b);
-            ptx::tma_load_4d(sK + 16384, &tmQKV, &bars[0], 0, 128, p.nh + h, b);
-            ptx::tma_load_4d(sV, &tmQKV, &bars[0], 0, 0, 2 * p.nh + h, b);
-            ptx::tma_load_4d(sV + 16384, &tmQKV, &bars[0], 0, 128, 2 * p.nh + h, b);
+#pragma unroll
+            for (int g = 0; g < NSEG; ++g) {
+                ptx::tma_load_4d(sK + g * 16384, &tmQKV, &bars[0], 0, g * 128, p.nh + h, b);
+                ptx::tma_load_4d(sV + g * 16384, &tmQKV, &bars[0], 0, g * 128, 2 * p.nh + h, b);
+            }
             ptx::mbar_wait(&bars[0], 0);
             ptx::tc_fence_after();
-            {   // S = Q K^T : A = Q (K-major), B = K (K-major), M128 N256, K = 64 in 4 steps
+            {   // S = Q K^T : A = Q (K-major), B = K (K-major), M128 N256 per 256 keys, K = 64 in 4 steps
                 constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, 256, 0, 0);
                 const uint64_t base = ptx::umma_desc_base(16, 1024);
                 const uint32_t a = ptx::smem_u32(sQ), bb = ptx::smem_u32(sK);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    ptx::umma_bf16(tmem, ptx::umma_desc(base, a + k * 32), ptx::umma_desc(base, bb + k * 32), idesc, k > 0);
+                for (int g = 0; g < NSEG / 2; ++g)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        ptx::umma_bf16(tmem + g * 256, ptx::umma_desc(base, a + k * 32), ptx::umma_desc(base, bb + g * 32768 + k * 32),
+                                       idesc, k > 0);
                 ptx::umma_commit(&bars[1]);
             }
             ptx::mbar_wait(&bars[2], 0);
             ptx::tc_fence_after();
-            {   // O = P V : A = P (K-major, 4 k-blocks of 64 keys), B = V ([key][d] => MN-major), M128 N64 K256 -> cols 0..63
+            {   // O = P V : A = P (K-major, 2 NSEG k-blocks of 64 keys), B = V ([key][d] => MN-major), M128 N64 K(128 NSEG) -> cols 0..63
                 constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, 64, 0, 1);
                 const uint64_t abase = ptx::umma_desc_base(16, 1024);
                 const uint64_t bbase = ptx::umma_desc_base(64 * 128, 1024);
                 const uint32_t a = ptx::smem_u32(sP), bb = ptx::smem_u32(sV);
 #pragma unroll
-                for (int k = 0; k < 16; ++k)
+                for (int k = 0; k < 8 * NSEG; ++k)
                     ptx::umma_bf16(tmem, ptx::umma_desc(abase, a + (k >> 2) * 16384 + (k & 3) * 32),
                                    ptx::umma_desc(bbase, bb + k * 2048), idesc, k > 0);
                 ptx::umma_commit(&bars[3]);
             }
         }
     } else {
-        // ---------------------------------------------------------------- softmax / epilogue: thread = (row, key half)
-        const int t = threadIdx.x - 32;          // 0..255
-        const int e = warp - 1;                  // 0..7
+        // ---------------------------------------------------------------- softmax / epilogue: thread = (row, key segment)
+        const int t = threadIdx.x - 32;          // 0..128 NSEG - 1
+        const int e = warp - 1;                  // 0..4 NSEG - 1
         const int quad = warp & 3;               // TMEM lane quadrant this warp may access
-        const int half = e >> 2;                 // keys [128*half, 128*half + 128)
+        const int half = e >> 2;                 // key segment: keys [128*half, 128*half + 128)
         const int row = quad * 32 + lane;        // row inside the tile (== TMEM lane)
         const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
         // additive key mask, staged once: (1 - m) * -10000 for real keys, -inf for keys beyond S
@@ -187,9 +200,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                 }
             }
         }
-        // (barrier for sMask) + is any of the 256 key slots masked?  Sequences without padding take the branch that
+        // (barrier for sMask) + is any of the 128 NSEG key slots masked?  Sequences without padding take the branch that
         // never reads the mask: two instructions per score fewer in each pass, and identical results (x * s + 0 == x * s)
-        const bool masked = named_bar_or(1, 256, my_mask != 0.f);
+        const bool masked = named_bar_or(1, SMT, my_mask != 0.f);
         ptx::mbar_wait(&bars[1], 0);
         ptx::tc_fence_after();
         const float sc = p.scale;
@@ -209,9 +222,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         }
         if (!masked) mx *= sc;  // sc > 0: max(x_j * sc) == max(x_j) * sc, rounding included
         sRed[half * 128 + row] = mx;
-        named_bar_sync(1, 256);
-        mx = fmaxf(mx, sRed[(half ^ 1) * 128 + row]);  // keys beyond S are -inf, real keys finite: mx is finite
-        named_bar_sync(1, 256);                        // sRed is reused for the sums below
+        named_bar_sync(1, SMT);
+#pragma unroll
+        for (int g = 1; g < NSEG; ++g) mx = fmaxf(mx, sRed[((half + g) % NSEG) * 128 + row]);  // keys beyond S are -inf, real keys finite: mx is finite
+        named_bar_sync(1, SMT);                        // sRed is reused for the sums below
         float sum = 0.f;
         const float mxl = mx * kLog2e;
         const float scl = sc * kLog2e;
@@ -251,27 +265,35 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         ptx::fence_proxy_async_smem();
         ptx::tc_fence_before();
         ptx::mbar_arrive(&bars[2]);
-        named_bar_sync(1, 256);
-        sum += sRed[(half ^ 1) * 128 + row];
+        named_bar_sync(1, SMT);
+        if (NSEG == 2) {
+            sum += sRed[(half ^ 1) * 128 + row];
+        } else {  // the same order in every thread of the row: identical 1/sum across the row's O columns
+            sum = 0.f;
+#pragma unroll
+            for (int g = 0; g < NSEG; ++g) sum += sRed[g * 128 + row];
+        }
         if (qvalid && half == 0) p.lse[grow] = mx + logf(sum);
         const float inv = 1.0f / sum;
         ptx::mbar_wait(&bars[3], 0);
         ptx::tc_fence_after();
-        {   // O columns [32*half, +32) of this row -> staging tile [128 rows][128 B] at the start of the P region
-            float v[32];
-            ptx::tmem_ld32(lane_addr + half * 32, v);
+        {   // O columns [OC*half, +OC) of this row -> staging tile [128 rows][128 B] at the start of the P region
+            constexpr int OC = 64 / NSEG;
+            float v[OC];
+            if (NSEG == 2) ptx::tmem_ld32(lane_addr + half * OC, v);
+            else ptx::tmem_ld16(lane_addr + half * OC, v);
             ptx::tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= inv;
+            for (int j = 0; j < OC; ++j) v[j] *= inv;
             uint8_t* stg = smem + row * 128;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int chunk = (half * 4 + j) ^ (row & 7);
+            for (int j = 0; j < OC / 8; ++j) {
+                const int chunk = (half * (OC / 8) + j) ^ (row & 7);
                 *reinterpret_cast<bf16x8*>(stg + chunk * 16) = pack8(v + 8 * j);
             }
         }
         ptx::fence_proxy_async_smem();
-        named_bar_sync(1, 256);
+        named_bar_sync(1, SMT);
         if (half == 0 && lane == 0) {
             ptx::tma_store_4d(&tmO, smem + quad * 4096, 0, q0 + quad * 32, h, b);  // rows >= S clipped
             ptx::tma_store_commit();
@@ -282,7 +304,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     __syncthreads();
     if (warp == 0) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc<256>(tmem);
+        ptx::tmem_dealloc<128 * NSEG>(tmem);
     }
 }
 
@@ -295,14 +317,16 @@ constexpr int BWD_SM_WARPS = 16;
 constexpr int BWD_SM_THREADS = BWD_SM_WARPS * 32;
 constexpr int BWD_THREADS = 32 + BWD_SM_THREADS;
 constexpr int B_SQ = 0;                   // 32 KB: Q rows 0..255
-constexpr int B_SK = B_SQ + 32768;
-constexpr int B_SV = B_SK + 32768;
+constexpr int B_SK = B_SQ + 32768;        // 32 KB: two 128-key stages of K (key block j lives in stage j & 1)
+constexpr int B_SV = B_SK + 32768;        // 32 KB: the same for V
 constexpr int B_SDO = B_SV + 32768;
 constexpr int B_SPD = B_SDO + 32768;      // 32 KB: Pd_ij  [2 key groups][128 q][64 keys]; also the drain staging tile
 constexpr int B_SDS = B_SPD + 32768;      // 32 KB: dS_ij  same layout
-constexpr int B_MISC = B_SDS + 32768;     // mask [256] floats, barriers
-constexpr int B_SMEM = 1024 + B_MISC + 1024 + 128;
+constexpr int B_MISC = B_SDS + 32768;     // mask [512] floats, barriers
+constexpr int B_SMEM = 1024 + B_MISC + 2048 + 128;
 
+// NKB = key blocks the instantiation can walk: 2 (S <= 256, the whole head in one CTA) or 4 (S <= 512)
+template <int NKB>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                 const __grid_constant__ CUtensorMap tmDQKV, const __grid_constant__ CUtensorMap tmO, const AttnParams p) {
@@ -318,15 +342,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     uint8_t* sPd = smem + B_SPD;
     uint8_t* sDS = smem + B_SDS;
     float* sMask = reinterpret_cast<float*>(smem + B_MISC);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_MISC + 1024);  // 0 load, 1 S/dP ready, 2 Pd/dS ready, 3 block MMAs done
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+    // 0 load, 1 S/dP ready, 2 Pd/dS ready, 3 block MMAs done, 4/5 K,V stage 0/1 reloaded (S > 256 only)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_MISC + 2048);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int h = blockIdx.x % p.nh;
-    const int b = blockIdx.x / p.nh;
-    const int H = p.nh * DH;
-    const int n_qt = (p.S + 127) / 128;   // query tiles (1 or 2)
-    const int n_kh = n_qt;                // 128-key blocks
+    // one CTA per (batch, head, 256-query half): S <= 256 has one half and the CTA owns the whole head; for S <= 512 the
+    // two halves of a head each walk all key blocks and their dK / dV partial sums meet in global memory (bf16 TMA
+    // reduce-add into a zeroed dqkv, see polus_attention_bwd)
+    const int n_half = (p.S + 255) / 256;
+    const int qh = blockIdx.x % n_half;
+    const int h = (blockIdx.x / n_half) % p.nh;
+    const int b = blockIdx.x / (n_half * p.nh);
+    const int qbase = qh * 256;                          // first query row of this CTA
+    const int n_qt = min(2, (p.S - qbase + 127) / 128);  // query tiles of this CTA (1 or 2)
+    const int n_kh = (p.S + 127) / 128;                  // 128-key blocks (1..4)
+    const bool partial_kv = n_half > 1;
 
     pdl_trigger();
     if (threadIdx.x == 0) {
@@ -337,6 +368,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         ptx::mbar_init(&bars[1], 1);
         ptx::mbar_init(&bars[2], BWD_SM_THREADS);
         ptx::mbar_init(&bars[3], 1);
+        ptx::mbar_init(&bars[4], 1);
+        ptx::mbar_init(&bars[5], 1);
         ptx::fence_barrier_init();
     }
     if (warp == 0) ptx::tmem_alloc<512>(tmem_slot);
@@ -353,9 +386,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             // dO is read from HBM once and no thread-issued global load sits in the prologue
             ptx::mbar_expect_tx(&bars[0], 5 * 32768);
             for (int r = 0; r < 2; ++r) {
-                ptx::tma_load_4d(sDO + r * 16384, &tmDO, &bars[0], 0, r * 128, h, b);
-                ptx::tma_load_4d(sPd + r * 16384, &tmO, &bars[0], 0, r * 128, h, b);
-                ptx::tma_load_4d(sQ + r * 16384, &tmQKV, &bars[0], 0, r * 128, h, b);
+                ptx::tma_load_4d(sDO + r * 16384, &tmDO, &bars[0], 0, qbase + r * 128, h, b);
+                ptx::tma_load_4d(sPd + r * 16384, &tmO, &bars[0], 0, qbase + r * 128, h, b);
+                ptx::tma_load_4d(sQ + r * 16384, &tmQKV, &bars[0], 0, qbase + r * 128, h, b);
                 ptx::tma_load_4d(sK + r * 16384, &tmQKV, &bars[0], 0, r * 128, p.nh + h, b);
                 ptx::tma_load_4d(sV + r * 16384, &tmQKV, &bars[0], 0, r * 128, 2 * p.nh + h, b);
             }
@@ -372,11 +405,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     ptx::umma_bf16(tmem + C_S, ptx::umma_desc(kbase, aQ + i * 16384 + k * 32),
-                                   ptx::umma_desc(kbase, aK + j * 16384 + k * 32), idesc, k > 0);
+                                   ptx::umma_desc(kbase, aK + (j & 1) * 16384 + k * 32), idesc, k > 0);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     ptx::umma_bf16(tmem + C_DP, ptx::umma_desc(kbase, aDO + i * 16384 + k * 32),
-                                   ptx::umma_desc(kbase, aV + j * 16384 + k * 32), idesc, k > 0);
+                                   ptx::umma_desc(kbase, aV + (j & 1) * 16384 + k * 32), idesc, k > 0);
                 ptx::umma_commit(&bars[1]);
             };
             issue_scores(0, 0);
@@ -386,11 +419,30 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                 // Pd_ij / dS_ij are in shared memory and every softmax thread has read S_ij / dP_ij out of TMEM
                 ptx::mbar_wait(&bars[2], ph2);
                 ph2 ^= 1;
+                if (blk > 0) {
+                    // (the softmax threads waited for the previous block's products before they stored: already complete)
+                    ptx::mbar_wait(&bars[3], (blk - 1) & 1);
+                    // that block was the last reader of its key block's K / V stage: refill it with key block jr + 2
+                    const int jr = (blk - 1) / n_qt;
+                    if (NKB > 2 && (blk - 1) % n_qt == n_qt - 1 && jr + 2 < n_kh) {
+                        uint64_t* lb = &bars[4 + (jr & 1)];
+                        ptx::mbar_expect_tx(lb, 32768);
+                        ptx::tma_load_4d(sK + (jr & 1) * 16384, &tmQKV, lb, 0, (jr + 2) * 128, p.nh + h, b);
+                        ptx::tma_load_4d(sV + (jr & 1) * 16384, &tmQKV, lb, 0, (jr + 2) * 128, 2 * p.nh + h, b);
+                    }
+                }
                 ptx::tc_fence_after();
                 // the NEXT block's scores first: they only need the S / dP columns, so the softmax threads can start on
                 // them while the three accumulating products of this block are still running (they wait for bars[3] of
                 // this block only before overwriting Pd / dS)
-                if (blk + 1 < n_blk) issue_scores((blk + 1) % n_qt, (blk + 1) / n_qt);
+                if (blk + 1 < n_blk) {
+                    const int ni = (blk + 1) % n_qt, nj = (blk + 1) / n_qt;
+                    if (NKB > 2 && ni == 0 && nj >= 2) {  // first use of a refilled stage
+                        ptx::mbar_wait(&bars[4 + (nj & 1)], ((nj >> 1) - 1) & 1);
+                        ptx::tc_fence_after();
+                    }
+                    issue_scores(ni, nj);
+                }
                 {   // dV_j += Pd_ij^T dO_i ; dK_j += dS_ij^T Q_i   (A MN-major over keys, B MN-major over d; M128 N64 K128)
                     constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, 64, 1, 1);
 #pragma unroll
@@ -408,7 +460,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 #pragma unroll
                     for (int k = 0; k < 8; ++k)
                         ptx::umma_bf16(tmem + cdq, ptx::umma_desc(kbase, aDS + (k >> 2) * 16384 + (k & 3) * 32),
-                                       ptx::umma_desc(mn1, aK + j * 16384 + k * 2048), idesc, (j > 0 || k > 0));
+                                       ptx::umma_desc(mn1, aK + (j & 1) * 16384 + k * 2048), idesc, (j > 0 || k > 0));
                 }
                 ptx::umma_commit(&bars[3]);
             }
@@ -420,32 +472,30 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         const int q4 = e >> 2;            // keys [32*q4, +32) of the current 128-key block
         const int row = quad * 32 + lane;
         const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
-        float my_mask = 0.f;
-        if (t < 256) {
-            my_mask = -INFINITY;
-            if (t < p.S) my_mask = p.mask ? (1.0f - (float)p.mask[(long long)b * p.S + t]) * (-10000.0f * kLog2e) : 0.f;
-            sMask[t] = my_mask;
-        }
+        float my_mask = -INFINITY;  // thread t stages key t (512 slots)
+        if (t < p.S) my_mask = p.mask ? (1.0f - (float)p.mask[(long long)b * p.S + t]) * (-10000.0f * kLog2e) : 0.f;
+        sMask[t] = my_mask;
+        if (t >= n_kh * 128) my_mask = 0.f;  // slots of key blocks that are never visited do not count as "masked"
         // L_row and the dropout keep bits of every block this thread will process (4 words): global loads issued first,
         // consumed after the tiles have landed, so that none sits on the per-block critical path
         float delta0 = 0.f, delta1 = 0.f, L0 = 0.f, L1 = 0.f;
-        uint32_t kbits[2][2];
+        uint32_t kbits[NKB][2];
         {
             bool ok[2];
 #pragma unroll
-            for (int i = 0; i < 2; ++i) ok[i] = (i < n_qt) && (i * 128 + row < p.S);
+            for (int i = 0; i < 2; ++i) ok[i] = (i < n_qt) && (qbase + i * 128 + row < p.S);
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
+            for (int j = 0; j < NKB; ++j)
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
-                    const int q = i * 128 + row, kc = j * 128 + q4 * 32;
+                    const int q = qbase + i * 128 + row, kc = j * 128 + q4 * 32;
                     uint32_t bits = 0xFFFFFFFFu;
                     if (p.thresh16 && i < n_qt && j < n_kh && q < p.S && kc < p.S)
                         bits = p.keepbits[((long long)(b * p.nh + h) * p.S + q) * (p.S >> 5) + (kc >> 5)];
                     kbits[j][i] = bits;
                 }
-            if (ok[0]) L0 = p.lse[(long long)(b * p.nh + h) * p.S + row];
-            if (ok[1]) L1 = p.lse[(long long)(b * p.nh + h) * p.S + 128 + row];
+            if (ok[0]) L0 = p.lse[(long long)(b * p.nh + h) * p.S + qbase + row];
+            if (ok[1]) L1 = p.lse[(long long)(b * p.nh + h) * p.S + qbase + 128 + row];
             // delta_row = sum_d dO[row,d] * O[row,d]: the four threads sharing a row split the 64 columns (two 16-byte
             // chunks each) of the swizzled dO / O tiles
             ptx::mbar_wait(&bars[0], 0);
@@ -495,7 +545,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             }
         };
         auto colsum_tile = [&](const uint8_t* tile, int row0, float* bs) {
-            const int nrows = min(128, p.S - row0);
+            const int nrows = min(128, p.S - row0);  // (may be <= 0 for a tile beyond S: nothing is added)
 #pragma unroll
             for (int rr = 0; rr < 8; ++rr) {
                 const int r = e * 8 + rr;
@@ -507,7 +557,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             }
         };
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < NKB; ++j) {
             if (j >= n_kh) break;
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
@@ -515,7 +565,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                 ptx::mbar_wait(&bars[1], ph1);
                 ph1 ^= 1;
                 ptx::tc_fence_after();
-                const int q = i * 128 + row;
+                const int q = qbase + i * 128 + row;
                 const bool qvalid = q < p.S;
                 const float Ll = qvalid ? (i == 0 ? L0 : L1) * kLog2e : INFINITY;  // rows beyond S: p = exp2(-inf) = 0
                 const float dl = i == 0 ? delta0 : delta1;
@@ -564,8 +614,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                         ptx::fence_proxy_async_smem();
                         named_bar_sync(1, BWD_SM_THREADS);
                         if (q4 == 0 && lane == 0) {
-                            ptx::tma_store_4d(&tmDQKV, sPd + quad * 4096, 0, (j - 1) * 128 + quad * 32, p.nh + h, b);
-                            ptx::tma_store_4d(&tmDQKV, sDS + quad * 4096, 0, (j - 1) * 128 + quad * 32, 2 * p.nh + h, b);
+                            if (partial_kv) {
+                                ptx::tma_reduce_add_4d(&tmDQKV, sPd + quad * 4096, 0, (j - 1) * 128 + quad * 32, p.nh + h, b);
+                                ptx::tma_reduce_add_4d(&tmDQKV, sDS + quad * 4096, 0, (j - 1) * 128 + quad * 32, 2 * p.nh + h, b);
+                            } else {
+                                ptx::tma_store_4d(&tmDQKV, sPd + quad * 4096, 0, (j - 1) * 128 + quad * 32, p.nh + h, b);
+                                ptx::tma_store_4d(&tmDQKV, sDS + quad * 4096, 0, (j - 1) * 128 + quad * 32, 2 * p.nh + h, b);
+                            }
                             ptx::tma_store_commit();
                         }
                         if (p.gbias != nullptr) {
@@ -601,17 +656,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                     ptx::fence_proxy_async_smem();
                     named_bar_sync(1, BWD_SM_THREADS);
                     if (q4 == 0 && lane == 0) {
-                        ptx::tma_store_4d(&tmDQKV, sPd + quad * 4096, 0, j * 128 + quad * 32, p.nh + h, b);
-                        ptx::tma_store_4d(&tmDQKV, sDS + quad * 4096, 0, j * 128 + quad * 32, 2 * p.nh + h, b);
-                        ptx::tma_store_4d(&tmDQKV, sPd + 16384 + quad * 4096, 0, quad * 32, h, b);
-                        if (n_qt > 1) ptx::tma_store_4d(&tmDQKV, sDS + 16384 + quad * 4096, 0, 128 + quad * 32, h, b);
+                        if (partial_kv) {
+                            ptx::tma_reduce_add_4d(&tmDQKV, sPd + quad * 4096, 0, j * 128 + quad * 32, p.nh + h, b);
+                            ptx::tma_reduce_add_4d(&tmDQKV, sDS + quad * 4096, 0, j * 128 + quad * 32, 2 * p.nh + h, b);
+                        } else {
+                            ptx::tma_store_4d(&tmDQKV, sPd + quad * 4096, 0, j * 128 + quad * 32, p.nh + h, b);
+                            ptx::tma_store_4d(&tmDQKV, sDS + quad * 4096, 0, j * 128 + quad * 32, 2 * p.nh + h, b);
+                        }
+                        ptx::tma_store_4d(&tmDQKV, sPd + 16384 + quad * 4096, 0, qbase + quad * 32, h, b);
+                        if (n_qt > 1) ptx::tma_store_4d(&tmDQKV, sDS + 16384 + quad * 4096, 0, qbase + 128 + quad * 32, h, b);
                         ptx::tma_store_commit();
                     }
                     if (p.gbias != nullptr) {
                         colsum_tile(sPd, j * 128, bsum[1]);
                         colsum_tile(sDS, j * 128, bsum[2]);
-                        colsum_tile(sPd + 16384, 0, bsum[0]);
-                        if (n_qt > 1) colsum_tile(sDS + 16384, 128, bsum[0]);
+                        colsum_tile(sPd + 16384, qbase, bsum[0]);
+                        if (n_qt > 1) colsum_tile(sDS + 16384, qbase + 128, bsum[0]);
                     }
                     if (q4 == 0 && lane == 0) ptx::tma_store_wait_read<0>();
                     named_bar_sync(1, BWD_SM_THREADS);  // the bias-sum scratch below reuses Pd
@@ -692,13 +752,13 @@ AttnParams make_params(int B, int S, int nh, float p_drop, uint64_t seed, uint32
 
 }  // namespace
 
-extern "C" int polus_attention_supported(int S, int dh) { return (dh == DH && S >= 32 && S <= 256 && S % 32 == 0) ? 1 : 0; }
+extern "C" int polus_attention_supported(int S, int dh) { return (dh == DH && S >= 32 && S <= 512 && S % 32 == 0) ? 1 : 0; }
 extern "C" size_t polus_attention_keepbits_words(int B, int S, int nh) { return (size_t)B * nh * S * (S / 32); }
 
 extern "C" int polus_attention_fwd(const polus_bf16_t* qkv, const int32_t* mask, int B, int S, int nh, int dh, float p_drop,
                                    uint64_t seed, uint32_t site, const uint32_t* d_step, polus_bf16_t* ctx, float* lse,
                                    uint32_t* keepbits, void* stream) {
-    POLUS_REQUIRE(polus_attention_supported(S, dh), "polus_attention_fwd: needs head_dim 64 and S <= 256, S %% 32 == 0 (got S=%d dh=%d)", S, dh);
+    POLUS_REQUIRE(polus_attention_supported(S, dh), "polus_attention_fwd: needs head_dim 64 and S <= 512, S %% 32 == 0 (got S=%d dh=%d)", S, dh);
     POLUS_REQUIRE(p_drop == 0.f || (d_step != nullptr && keepbits != nullptr), "polus_attention_fwd: dropout needs d_step and keepbits");
     if (B == 0) return 0;
     CUtensorMap tq, to;
@@ -708,12 +768,16 @@ extern "C" int polus_attention_fwd(const polus_bf16_t* qkv, const int32_t* mask,
     if (rc) return rc;
     static bool set = false;
     if (!set) {
-        POLUS_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
+        POLUS_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdCfg<2>::SMEM));
+        POLUS_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdCfg<4>::SMEM));
         set = true;
     }
     AttnParams p = make_params(B, S, nh, p_drop, seed, site, d_step, mask, lse, keepbits);
     const int q_tiles = (S + 127) / 128;
-    POLUS_CHECK_CUDA(polus_launch_pdl(attn_fwd_kernel, dim3(B * nh * q_tiles), dim3(FWD_THREADS), F_SMEM, (cudaStream_t)stream, tq, to, p));
+    if (S <= 256)
+        POLUS_CHECK_CUDA(polus_launch_pdl(attn_fwd_kernel<2>, dim3(B * nh * q_tiles), dim3(FwdCfg<2>::THREADS), FwdCfg<2>::SMEM, (cudaStream_t)stream, tq, to, p));
+    else
+        POLUS_CHECK_CUDA(polus_launch_pdl(attn_fwd_kernel<4>, dim3(B * nh * q_tiles), dim3(FwdCfg<4>::THREADS), FwdCfg<4>::SMEM, (cudaStream_t)stream, tq, to, p));
     g_launch_count++;
     POLUS_LAUNCH_CHECK();
     return 0;
@@ -723,7 +787,7 @@ extern "C" int polus_attention_bwd(const polus_bf16_t* qkv, const int32_t* mask,
                                    const polus_bf16_t* dctx, const float* lse, int B, int S, int nh, int dh, float p_drop,
                                    uint64_t seed, uint32_t site, const uint32_t* d_step, const uint32_t* keepbits,
                                    polus_bf16_t* dqkv, float* gbias_qkv, void* stream) {
-    POLUS_REQUIRE(polus_attention_supported(S, dh), "polus_attention_bwd: needs head_dim 64 and S <= 256, S %% 32 == 0 (got S=%d dh=%d)", S, dh);
+    POLUS_REQUIRE(polus_attention_supported(S, dh), "polus_attention_bwd: needs head_dim 64 and S <= 512, S %% 32 == 0 (got S=%d dh=%d)", S, dh);
     POLUS_REQUIRE(p_drop == 0.f || keepbits != nullptr, "polus_attention_bwd: dropout needs the forward's keepbits");
     if (B == 0) return 0;
     CUtensorMap tq, tdo, tdq, to;
@@ -737,11 +801,22 @@ extern "C" int polus_attention_bwd(const polus_bf16_t* qkv, const int32_t* mask,
     if (rc) return rc;
     static bool set = false;
     if (!set) {
-        POLUS_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
+        POLUS_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
+        POLUS_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
         set = true;
     }
     AttnParams p = make_params(B, S, nh, p_drop, seed, site, d_step, mask, const_cast<float*>(lse), const_cast<uint32_t*>(keepbits), gbias_qkv);
-    POLUS_CHECK_CUDA(polus_launch_pdl(attn_bwd_kernel, dim3(B * nh), dim3(BWD_THREADS), B_SMEM, (cudaStream_t)stream, tq, tdo, tdq, to, p));
+    const int n_half = (S + 255) / 256;
+    if (n_half > 1) {
+        // two CTAs per head (one per 256-query half) add their dK / dV partial sums into dqkv with bf16 TMA reduce-adds:
+        // the K and V column blocks [H, 3H) of every row start from zero (the dQ block is stored, not accumulated)
+        const size_t H2 = (size_t)nh * DH * sizeof(polus_bf16_t);
+        POLUS_CHECK_CUDA(cudaMemset2DAsync(reinterpret_cast<uint8_t*>(dqkv) + H2, 3 * H2, 0, 2 * H2, (size_t)B * S, (cudaStream_t)stream));
+        attn_bwd_kernel<4><<<dim3(B * nh * n_half), dim3(BWD_THREADS), B_SMEM, (cudaStream_t)stream>>>(tq, tdo, tdq, to, p);
+        POLUS_CHECK_CUDA(cudaGetLastError());
+    } else {
+        POLUS_CHECK_CUDA(polus_launch_pdl(attn_bwd_kernel<2>, dim3(B * nh), dim3(BWD_THREADS), B_SMEM, (cudaStream_t)stream, tq, tdo, tdq, to, p));
+    }
     g_launch_count++;
     POLUS_LAUNCH_CHECK();
     return 0;

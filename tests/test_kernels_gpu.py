@@ -475,7 +475,11 @@ def test_skinny_linear_fwd_bwd(dev, M, K, N, act, xdt):
 
 @pytest.mark.parametrize("B,nh,S,p,use_mask", [(2, 2, 64, 0.0, True), (1, 3, 256, 0.1, True), (2, 2, 128, 0.0, False),
                                                (1, 2, 192, 0.1, True), (3, 1, 32, 0.0, True), (2, 2, 96, 0.1, False),
-                                               (2, 2, 224, 0.1, True), (1, 2, 160, 0.0, False), (1, 1, 256, 0.1, False)])
+                                               (2, 2, 224, 0.1, True), (1, 2, 160, 0.0, False), (1, 1, 256, 0.1, False),
+                                               # S > 256: four key segments forward; two query halves per head backward
+                                               # (K / V stages refilled, dK / dV partial sums reduce-added by the TMA unit)
+                                               (2, 2, 512, 0.1, True), (1, 3, 512, 0.0, False), (2, 1, 384, 0.1, True),
+                                               (1, 2, 288, 0.0, True), (1, 2, 448, 0.1, False), (3, 2, 320, 0.1, True)])
 def test_fused_attention_fwd_bwd(dev, B, nh, S, p, use_mask):
     """Fused attention (scores/probabilities in TMEM/smem) vs the oracle with the device's own dropout masks, and vs
     the unfused GEMM+softmax path (same Philox counters => same masks)."""
@@ -513,7 +517,13 @@ def test_fused_attention_fwd_bwd(dev, B, nh, S, p, use_mask):
         ops.FUSED_ATTENTION = True
     # the fused backward also accumulates the QKV bias gradient = column sums of the dqkv it stored
     gb_ref = dq_f.astype(np.float64).reshape(-1, 3 * H).sum(0)
-    np.testing.assert_allclose(bias.grad.numpy(), gb_ref, rtol=1e-4, atol=1e-4 * (np.abs(gb_ref).max() + 1))
+    if S <= 256:
+        np.testing.assert_allclose(bias.grad.numpy(), gb_ref, rtol=1e-4, atol=1e-4 * (np.abs(gb_ref).max() + 1))
+    else:
+        # two CTAs per head: the bias sums add each half's bf16 partial dK / dV, the stored tensor holds the bf16 sum of
+        # the two partials -- they differ by that final rounding (<= 2^-9 |x| per element, worst case over the column)
+        bound = 2.0 ** -9 * np.abs(dq_f.astype(np.float64)).reshape(-1, 3 * H).sum(0) + 1e-4 * (np.abs(gb_ref).max() + 1)
+        assert np.all(np.abs(bias.grad.numpy() - gb_ref) <= bound)
     # oracle (float64) with the same dropout mask (site 1 of this step)
     q, k, v = [qkv[..., i * H:(i + 1) * H].reshape(B, S, nh, dh).transpose(0, 2, 1, 3).astype(np.float64) for i in range(3)]
     sc = q @ k.transpose(0, 1, 3, 2) / 8.0 + (R.attention_mask_additive(mask) if use_mask else 0.0)
