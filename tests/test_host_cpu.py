@@ -1,6 +1,7 @@
 """Host-side logic of the polus-shaped API (no GPU): utils/core/data/schedulers/labels/callbacks/bucket plan.
 Several cases mirror the reference's own unit tests (tests/test_utils.py, tests/test_core.py, tests/test_data.py)."""
 import json
+import os
 
 import numpy as np
 import pytest
@@ -303,3 +304,141 @@ def test_entity_f1_strict_matching_and_window_filter():
     del batch["tags_int"]
     m2.samples_from_batch([batch])
     assert m2.evaluate() == 0.5
+
+
+# ------------------------------------------------------------------ cached loaders (reference tests/test_data.py:68-345)
+def _count_gen(n, text="dummy"):
+    def source_gen():
+        for i in range(n):
+            yield {"id": i, "text": text}
+    return source_gen
+
+
+def _walk(dl):
+    ordered, n, sample = True, 0, None
+    for sample in dl:
+        ordered = ordered and sample["id"] == n
+        n += 1
+    return ordered, n, sample
+
+
+def test_cached_dataloader_chunk_format_and_order(tmp_path):
+    """Chunk files `<base>_NNNN.part` = pickled lists of <= chunk samples; `.index` = JSON with files / cache_chunk_size /
+    n_samples (reference data.py:266-320): a reader that knows only that format recovers the samples."""
+    import pickle
+    from polus_b200.data import CachedDataLoader
+    dl = CachedDataLoader(_count_gen(1000), cache_chunk_size=256, cache_folder=str(tmp_path))
+    ordered, n, last = _walk(dl)
+    assert ordered and n == 1000 and dl.get_n_samples() == 1000 and last == {"id": 999, "text": "dummy"}
+    assert dl.cache_base_name == "_chunk256_source_gen"
+    files = sorted(os.listdir(tmp_path))
+    assert files == ["_chunk256_source_gen.index"] + [f"_chunk256_source_gen_{k:04}.part" for k in range(4)]
+    with open(dl.cache_index_path) as f:
+        index = json.load(f)
+    assert set(index) == {"files", "cache_chunk_size", "n_samples"} and index["n_samples"] == 1000 and index["cache_chunk_size"] == 256
+    sizes = []
+    for path in index["files"]:
+        with open(path, "rb") as f:
+            sizes.append(len(pickle.load(f)))
+    assert sizes == [256, 256, 256, 232]
+    # a second loader over the same generator name finds the cache and never calls the generator
+    def source_gen():
+        raise AssertionError("the cache should have been used")
+        yield
+    again = CachedDataLoader(source_gen, cache_chunk_size=256, cache_folder=str(tmp_path))
+    assert _walk(again)[:2] == (True, 1000)
+    # through the dataset verbs the trainer consumes
+    ids = [int(s["id"]) for s in dl.to_tfDataset()]
+    assert ids == list(range(1000))
+    dl.clean()
+    assert os.listdir(tmp_path) == []
+
+
+def test_cached_dataloader_reads_a_cache_written_in_the_reference_layout(tmp_path):
+    """Files laid out by hand exactly as the reference writes them are opened with from_cached_index."""
+    import pickle
+    from polus_b200.data import CachedDataLoader
+    files = []
+    for k in range(3):
+        path = str(tmp_path / f"x__chunk4_g_{k:04}.part")
+        with open(path, "wb") as f:
+            pickle.dump([{"id": 4 * k + i} for i in range(4 if k < 2 else 1)], f)
+        files.append(path)
+    index_path = str(tmp_path / "x__chunk4_g.index")
+    with open(index_path, "w") as f:
+        json.dump({"files": files, "cache_chunk_size": 4, "n_samples": 9}, f)
+    dl = CachedDataLoader.from_cached_index(index_path)
+    assert _walk(dl)[:2] == (True, 9) and dl.cache_chunk_size == 4 and dl.cache_index_path == index_path
+
+
+def test_cached_dataloader_with_lookup_and_conversion(tmp_path):
+    from polus_b200.data import CachedDataLoader, CachedDataLoaderwLookup
+    data = {"a": 1, "b": 2, "c": 3}
+    dl = CachedDataLoaderwLookup(_count_gen(1000), lookup_data=data, cache_chunk_size=256, cache_folder=str(tmp_path / "a"))
+    assert _walk(dl)[:2] == (True, 1000) and dl.get_lookup_data()["c"] == 3
+    files = os.listdir(tmp_path / "a")
+    assert f"{dl.cache_base_name}.index" in files and f"{dl.cache_base_name}.lookup" in files
+    assert all(os.path.basename(p) in files for p in dl.cache_index["files"])
+    with pytest.raises(ValueError):
+        CachedDataLoaderwLookup(_count_gen(3), cache_folder=str(tmp_path / "a"))
+    # CachedDataLoader -> add_lookup_data -> CachedDataLoaderwLookup over the same chunks
+    plain = CachedDataLoader(_count_gen(1000), cache_chunk_size=256, cache_folder=str(tmp_path / "b"))
+    conv = plain.add_lookup_data(data)
+    assert isinstance(conv, CachedDataLoaderwLookup) and _walk(conv)[:2] == (True, 1000) and conv.get_lookup_data() == data
+    base = os.path.splitext(os.path.basename(conv.cache_index_path))[0]
+    assert {f"{base}.index", f"{base}.lookup"} <= set(os.listdir(tmp_path / "b"))
+    conv.clean()
+    assert os.listdir(tmp_path / "b") == []
+
+
+def test_cached_dataloader_pre_shuffle_merge_and_reopen(tmp_path):
+    from polus_b200.data import CachedDataLoader, CachedDataLoaderwLookup
+    import random
+    random.seed(0)
+    def new_gen():
+        for s in _count_gen(1000)():
+            s["new_entry"] = s["id"] * 2
+            yield s
+    dl = CachedDataLoader(new_gen, cache_chunk_size=16, cache_folder=str(tmp_path))
+    assert _walk(dl)[:2] == (True, 1000)
+    dl.pre_shuffle()
+    ordered, n, _ = _walk(dl)
+    assert not ordered and n == 1000
+    seen = [s["id"] for s in dl]
+    assert sorted(seen) == list(range(1000))
+    # chunk-level shuffle: inside every chunk of 16 the samples stay consecutive
+    assert all(seen[k - 1] == v - 1 for k, v in enumerate(seen) if v % 16 != 0)
+    # merge of three caches with different lengths
+    def named(n, text, name):
+        g = _count_gen(n, text)
+        g.__name__ = name
+        return g
+    parts = [CachedDataLoader(named(n, t, f"gen_{t}"), cache_chunk_size=64, cache_folder=str(tmp_path))
+             for n, t in ((1000, "dummy"), (500, "dummy2"), (721, "dummy3"))]
+    merged = CachedDataLoader.merge(*parts).pre_shuffle()
+    ordered, n, _ = _walk(merged)
+    assert not ordered and n == 2221 and merged.get_n_samples() == 2221 and merged.cache_chunk_size == 64
+    assert {s["text"] for s in merged} == {"dummy", "dummy2", "dummy3"}
+    # reopen from the index path alone
+    again = CachedDataLoader.from_cached_index(parts[0].cache_index_path).pre_shuffle()
+    ordered, n, last = _walk(again)
+    assert not ordered and n == 1000 and last["text"] == "dummy"
+    # merged lookups concatenate
+    la = parts[1].add_lookup_data(["x", "y"])
+    lb = parts[2].add_lookup_data(["z"])
+    both = CachedDataLoaderwLookup.merge(la, lb)
+    assert both.get_lookup_data() == ["x", "y", "z"] and both.get_n_samples() == 1221 and _walk(both)[1] == 1221
+    # deep_copy: a second index over the same chunks
+    parts[0].deep_copy(suffix="v2")
+    assert parts[0].cache_index_path.endswith("_chunk64_gen_dummy_v2.index") and os.path.exists(parts[0].cache_index_path)
+
+
+def test_cached_dataloader_cleans_up_when_the_generator_fails(tmp_path):
+    from polus_b200.data import CachedDataLoader
+    def bad_gen():
+        for i in range(40):
+            yield {"id": i}
+        raise RuntimeError("source failed")
+    with pytest.raises(RuntimeError):
+        CachedDataLoader(bad_gen, cache_chunk_size=16, cache_folder=str(tmp_path))
+    assert os.listdir(tmp_path) == []
