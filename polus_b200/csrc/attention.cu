@@ -322,8 +322,9 @@ constexpr int B_SV = B_SK + 32768;        // 32 KB: the same for V
 constexpr int B_SDO = B_SV + 32768;
 constexpr int B_SPD = B_SDO + 32768;      // 32 KB: Pd_ij  [2 key groups][128 q][64 keys]; also the drain staging tile
 constexpr int B_SDS = B_SPD + 32768;      // 32 KB: dS_ij  same layout
-constexpr int B_MISC = B_SDS + 32768;     // mask [512] floats, barriers
-constexpr int B_SMEM = 1024 + B_MISC + 2048 + 128;
+constexpr int B_SO1 = B_SDS + 32768;      // 16 KB: O rows 128..255 (O rows 0..127 land in the Pd region, idle until block 0 stores)
+constexpr int B_MISC = B_SO1 + 16384;     // mask [512] floats | delta exchange [2 tiles][4 quarters][128 rows] floats | barriers
+constexpr int B_SMEM = 1024 + B_MISC + 2048 + 4096 + 128;
 
 // NKB = key blocks the instantiation can walk: 2 (S <= 256, the whole head in one CTA) or 4 (S <= 512)
 template <int NKB>
@@ -342,9 +343,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     uint8_t* sPd = smem + B_SPD;
     uint8_t* sDS = smem + B_SDS;
     float* sMask = reinterpret_cast<float*>(smem + B_MISC);
-    // 0 load, 1 S/dP ready, 2 Pd/dS ready, 3 block MMAs done, 4/5 K,V stage 0/1 reloaded (S > 256 only)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_MISC + 2048);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+    uint8_t* sO1 = smem + B_SO1;
+    float* sEx = reinterpret_cast<float*>(smem + B_MISC + 2048);
+    // 0 first load group, 1 S/dP ready, 2 Pd/dS ready, 3 block MMAs done, 4/5 K,V stage 0/1 reloaded (S > 256 only),
+    // 6 second query tile loaded (Q, dO, O rows 128..255), 7 second key block loaded (K, V rows 128..255)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_MISC + 2048 + 4096);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // one CTA per (batch, head, 256-query half): S <= 256 has one half and the CTA owns the whole head; for S <= 512 the
@@ -370,6 +374,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         ptx::mbar_init(&bars[3], 1);
         ptx::mbar_init(&bars[4], 1);
         ptx::mbar_init(&bars[5], 1);
+        ptx::mbar_init(&bars[6], 1);
+        ptx::mbar_init(&bars[7], 1);
         ptx::fence_barrier_init();
     }
     if (warp == 0) ptx::tmem_alloc<512>(tmem_slot);
@@ -382,15 +388,27 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 
     if (warp == 0) {
         if (lane == 0) {
-            // O (the forward output) lands in the idle Pd region: delta = rowsum(dO * O) is computed from shared memory, so
-            // dO is read from HBM once and no thread-issued global load sits in the prologue
-            ptx::mbar_expect_tx(&bars[0], 5 * 32768);
-            for (int r = 0; r < 2; ++r) {
-                ptx::tma_load_4d(sDO + r * 16384, &tmDO, &bars[0], 0, qbase + r * 128, h, b);
-                ptx::tma_load_4d(sPd + r * 16384, &tmO, &bars[0], 0, qbase + r * 128, h, b);
-                ptx::tma_load_4d(sQ + r * 16384, &tmQKV, &bars[0], 0, qbase + r * 128, h, b);
-                ptx::tma_load_4d(sK + r * 16384, &tmQKV, &bars[0], 0, r * 128, p.nh + h, b);
-                ptx::tma_load_4d(sV + r * 16384, &tmQKV, &bars[0], 0, r * 128, 2 * p.nh + h, b);
+            // O (the forward output) comes through TMA as well: delta = rowsum(dO * O) is computed from shared memory, so dO is
+            // read from HBM once and no thread-issued global load sits in the prologue.  Three load groups, in the order of
+            // first use: block (0,0) starts when the first 80 KB have landed; the second query tile and the second key block
+            // (another 80 KB) arrive under its arithmetic (every CTA of a wave starts at the same time: the prologue is
+            // bandwidth-bound, profiles/r01_attn_bwd_timeline_v11.txt)
+            ptx::mbar_expect_tx(&bars[0], 5 * 16384);
+            ptx::tma_load_4d(sQ, &tmQKV, &bars[0], 0, qbase, h, b);
+            ptx::tma_load_4d(sK, &tmQKV, &bars[0], 0, 0, p.nh + h, b);
+            ptx::tma_load_4d(sDO, &tmDO, &bars[0], 0, qbase, h, b);
+            ptx::tma_load_4d(sV, &tmQKV, &bars[0], 0, 0, 2 * p.nh + h, b);
+            ptx::tma_load_4d(sPd, &tmO, &bars[0], 0, qbase, h, b);
+            if (n_qt > 1) {
+                ptx::mbar_expect_tx(&bars[6], 3 * 16384);
+                ptx::tma_load_4d(sQ + 16384, &tmQKV, &bars[6], 0, qbase + 128, h, b);
+                ptx::tma_load_4d(sDO + 16384, &tmDO, &bars[6], 0, qbase + 128, h, b);
+                ptx::tma_load_4d(sO1, &tmO, &bars[6], 0, qbase + 128, h, b);
+            }
+            if (n_kh > 1) {
+                ptx::mbar_expect_tx(&bars[7], 2 * 16384);
+                ptx::tma_load_4d(sK + 16384, &tmQKV, &bars[7], 0, 128, p.nh + h, b);
+                ptx::tma_load_4d(sV + 16384, &tmQKV, &bars[7], 0, 128, 2 * p.nh + h, b);
             }
             ptx::mbar_wait(&bars[0], 0);
             ptx::tc_fence_after();
@@ -439,6 +457,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                     const int ni = (blk + 1) % n_qt, nj = (blk + 1) / n_qt;
                     if (NKB > 2 && ni == 0 && nj >= 2) {  // first use of a refilled stage
                         ptx::mbar_wait(&bars[4 + (nj & 1)], ((nj >> 1) - 1) & 1);
+                        ptx::tc_fence_after();
+                    }
+                    if (ni == 1 && nj == 0) {  // first use of the second query tile
+                        ptx::mbar_wait(&bars[6], 0);
+                        ptx::tc_fence_after();
+                    }
+                    if (ni == 0 && nj == 1) {  // first use of the second key block
+                        ptx::mbar_wait(&bars[7], 0);
                         ptx::tc_fence_after();
                     }
                     issue_scores(ni, nj);
@@ -496,36 +522,32 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                 }
             if (ok[0]) L0 = p.lse[(long long)(b * p.nh + h) * p.S + qbase + row];
             if (ok[1]) L1 = p.lse[(long long)(b * p.nh + h) * p.S + qbase + 128 + row];
-            // delta_row = sum_d dO[row,d] * O[row,d]: the four threads sharing a row split the 64 columns (two 16-byte
-            // chunks each) of the swizzled dO / O tiles
             ptx::mbar_wait(&bars[0], 0);
-            float part[2] = {0.f, 0.f};
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                if (i < n_qt) {
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const int off = i * 16384 + row * 128 + (((q4 * 2 + c) ^ (row & 7)) << 4);
-                        float a[8], d8[8];
-                        unpack8(*reinterpret_cast<const bf16x8*>(sPd + off), a);
-                        unpack8(*reinterpret_cast<const bf16x8*>(sDO + off), d8);
-#pragma unroll
-                        for (int x = 0; x < 8; ++x) part[i] = fmaf(a[x], d8[x], part[i]);
-                    }
-                }
-            }
-            // exchange the four quarters of each row through shared memory (dS is free until the first block)
-            float* ex = reinterpret_cast<float*>(sDS);
-            ex[(q4 * 2 + 0) * 128 + row] = part[0];
-            ex[(q4 * 2 + 1) * 128 + row] = part[1];
-            named_bar_sync(1, BWD_SM_THREADS);
-#pragma unroll
-            for (int qq = 0; qq < 4; ++qq) {
-                delta0 += ex[(qq * 2 + 0) * 128 + row];
-                delta1 += ex[(qq * 2 + 1) * 128 + row];
-            }
         }
-        const bool masked = named_bar_or(1, BWD_SM_THREADS, my_mask != 0.f);  // (also the barrier behind the delta exchange)
+        // delta_row = sum_d dO[row,d] * O[row,d]: the four threads sharing a row split the 64 columns (two 16-byte chunks
+        // each) of the swizzled dO / O tiles and exchange their quarters through shared memory
+        auto delta_part = [&](const uint8_t* o_tile, const uint8_t* do_tile, int i) {
+            float part = 0.f;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int off = row * 128 + (((q4 * 2 + c) ^ (row & 7)) << 4);
+                float a[8], d8[8];
+                unpack8(*reinterpret_cast<const bf16x8*>(o_tile + off), a);
+                unpack8(*reinterpret_cast<const bf16x8*>(do_tile + off), d8);
+#pragma unroll
+                for (int x = 0; x < 8; ++x) part = fmaf(a[x], d8[x], part);
+            }
+            sEx[(i * 4 + q4) * 128 + row] = part;
+        };
+        auto delta_sum = [&](int i) {
+            float d = 0.f;
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) d += sEx[(i * 4 + qq) * 128 + row];
+            return d;
+        };
+        delta_part(sPd, sDO, 0);
+        const bool masked = named_bar_or(1, BWD_SM_THREADS, my_mask != 0.f);  // (also the barrier behind sMask and the delta exchange)
+        delta0 = delta_sum(0);
         const float sc = p.scale;
         uint32_t ph1 = 0;
         int blk = 0;
@@ -645,6 +667,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                 ptx::fence_proxy_async_smem();
                 ptx::tc_fence_before();
                 ptx::mbar_arrive(&bars[2]);
+                if (j == 0 && i == 0 && n_qt > 1) {
+                    // delta of the second query tile, in the shadow of the hand-off to the MMA thread (its tiles were
+                    // loaded behind block 0's)
+                    ptx::mbar_wait(&bars[6], 0);
+                    delta_part(sO1, sDO + 16384, 1);
+                    named_bar_sync(1, BWD_SM_THREADS);
+                    delta1 = delta_sum(1);
+                }
                 if (j == n_kh - 1 && i == n_qt - 1) {
                     // last block: everything that is still in TMEM -- dK / dV of this key block and every dQ tile
                     ptx::mbar_wait(&bars[3], blk & 1);
