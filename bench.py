@@ -247,10 +247,10 @@ def run_ours(args):
         achieved = tot_flop / (gemm_only_ms * 1e-3) / 1e12 if gemm_only_ms > 0 else 0.0
         step_ms = ms_dev / args.steps
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": 104.3e6 * args.batch / 64.0,  # dram__bytes_read+write per launch, mean of 12 launches, batch 64
-                "traffic_source": "profiles/r01_ncu_summary_v13_{fwd,bwd}.txt (ncu --set full); scaled linearly with batch",
-                "tensor_pipe_active_pct": 57.2,  # sm__pipe_tensor_cycles_active, time-weighted over the same 12 launches
-                "algorithmic_bytes_per_launch": 122.1e6 * args.batch / 64.0,
+                "traffic": 222.7e6 * args.batch / 128.0,  # dram__bytes_read+write per launch, mean of 12 launches, batch 128
+                "traffic_source": "profiles/r01_ncu_summary_v16_gemm_{fwd,bwd}.txt (ncu --set full, batch 128); scaled linearly with batch",
+                "tensor_pipe_active_pct": 65.5,  # sm__pipe_tensor_cycles_active, time-weighted over the same 12 launches
+                "algorithmic_bytes_per_launch": 244.2e6 * args.batch / 128.0,
                 "kernel": "gemm_tc_kernel (all tcgen05 GEMM launches of one step)", "launches": n_tc,
                 "gemm_ms_per_step": gemm_only_ms, "gemm_gflop_per_step": tot_flop / 1e9,
                 "method": "CUDA-event time of a captured replay of the step's GEMM launches alone (same order/buffers/streams)",
