@@ -185,11 +185,11 @@ int polus_softmax_bwd(polus_bf16_t* d_p_inout, polus_bf16_t* d_dpd_inout, int B,
                       float scale, float p_drop, uint64_t seed, uint32_t site,
                       const uint32_t* d_step, void* stream);
 
-/* Fused self-attention core for head_dim 64, S <= 256 (S % 8 == 0) on the packed projection qkv [B,S,3*nh*64]
+/* Fused self-attention core for head_dim 64, S <= 512 (S % 32 == 0) on the packed projection qkv [B,S,3*nh*64]
  * (q|k|v column blocks): ctx = dropout(softmax(QK^T/8 + (1-mask)*-10000)) V, scores/probabilities kept in
  * TMEM/shared memory.  Saves lse [B,nh,S] (row log-sum-exp) for the backward, which recomputes P.
  * Replaces HF TFBertSelfAttention's matmul/softmax/dropout/matmul and their gradients (polus/models.py:175-213). */
-int polus_attention_supported(int S, int head_dim);           /* head_dim 64, 32 <= S <= 256, S % 32 == 0 */
+int polus_attention_supported(int S, int head_dim);           /* head_dim 64, 32 <= S <= 512, S % 32 == 0 */
 size_t polus_attention_keepbits_words(int B, int S, int nh);   /* uint32 words of the dropout keep-bit buffer */
 int polus_attention_fwd(const polus_bf16_t* d_qkv, const int32_t* d_mask, int B, int S, int nh, int head_dim,
                         float p_drop, uint64_t seed, uint32_t site, const uint32_t* d_step, polus_bf16_t* d_ctx,
