@@ -71,9 +71,12 @@ struct TcParams {
 template <int BN, int CG>
 struct Cfg {
     static constexpr int BN_LOCAL = BN / CG;  // rows of the B tile this CTA stages
-    static constexpr int B_STAGE_BYTES = BN_LOCAL * BK * 2;
+    // MN-major B arrives in 64-column groups (one 128-byte swizzle atom wide): a 96-column share (BN = 192 on a pair)
+    // fetches two full groups and the MMA reads the first 96 columns; the slot size is the same for both majors
+    static constexpr int B_GROUPS = (BN_LOCAL + 63) / 64;
+    static constexpr int B_STAGE_BYTES = (BN_LOCAL < 64 ? BN_LOCAL : B_GROUPS * 64) * BK * 2;
     static constexpr int kStageBytes = A_STAGE_BYTES + B_STAGE_BYTES;
-    static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+    static constexpr int kTmemCols = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
     static int stages(int stg_warp) {
         const int n = (kSmemTotal - 1024 - kEpiWarps * stg_warp - kBarBytes) / kStageBytes;
         return n > kMaxStages ? kMaxStages : n;
@@ -81,7 +84,7 @@ struct Cfg {
     static int smem_bytes(int stg_warp) { return 1024 + stages(stg_warp) * kStageBytes + kEpiWarps * stg_warp + kBarBytes; }
     static constexpr int kColBlocks = BN / 64;                       // 64-column blocks per tile
     static constexpr int kEpiActive = kColBlocks >= 2 ? 8 : 4;        // epilogue warps that do work
-    static constexpr int kBlocksPerWarp = kColBlocks >= 2 ? kColBlocks / 2 : 1;
+    static constexpr int kBlocksPerWarp = kColBlocks >= 2 ? (kColBlocks + 1) / 2 : 1;  // (BN = 192: 2 + 1 blocks)
 };
 
 __device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
@@ -194,7 +197,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int kStages = p.n_stages;
     constexpr int BN_LOCAL = C::BN_LOCAL;
     constexpr int B_STAGE_BYTES = C::B_STAGE_BYTES;
-    constexpr uint32_t kStageTx = (A_STAGE_BYTES + B_STAGE_BYTES) * CG;  // bytes landing on the leader's barrier
+    // bytes landing on the leader's barrier per k-block (K-major B boxes hold exactly BN_LOCAL rows)
+    constexpr uint32_t kStageTx = (A_STAGE_BYTES + (B_MN ? B_STAGE_BYTES : BN_LOCAL * BK * 2)) * CG;
     static_assert(CL == CG || (CL == 4 && CG == 2), "cluster is one CTA, one pair, or two pairs");
     constexpr int PP = CL / CG;  // CTA pairs (or single CTAs) per cluster
     const uint32_t cluster_rank = CL > 1 ? ptx::cluster_ctarank() : 0u;
@@ -305,7 +309,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         load(b, &tmB, &full_bar[stage], kb * BK, n0, b0, b1);
                     } else {
 #pragma unroll
-                        for (int g = 0; g < BN_LOCAL / 64; ++g)
+                        for (int g = 0; g < C::B_GROUPS; ++g)
                             load(b + g * (BK * 128), &tmB, &full_bar[stage], n0 + g * 64, kb * BK, b0, b1);
                     }
                     if (++stage == kStages) {
@@ -575,7 +579,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (t >= p.num_tiles || i >= C::kBlocksPerWarp) return false;
             int mt, nt, sp, b0, b1;
             decode(t, mt, nt, sp, b0, b1);
-            return nt * BN + (half * C::kBlocksPerWarp + i) * 64 < p.N;
+            return half * C::kBlocksPerWarp + i < C::kColBlocks && nt * BN + (half * C::kBlocksPerWarp + i) * 64 < p.N;
         };
         auto advance = [&](int& t, int& i) {
             ++i;
@@ -610,7 +614,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int i = 0; i < C::kBlocksPerWarp; ++i) {
                 const int cb = half * C::kBlocksPerWarp + i;
                 const int colb = nt * BN + cb * 64;
-                if (colb >= p.N) break;  // warp-uniform
+                if (cb >= C::kColBlocks || colb >= p.N) break;  // warp-uniform
                 uint8_t* blkC = stg;
                 uint8_t* blkC2 = stg + STG_BLOCK;
                 if (stores_in_flight) {
@@ -908,6 +912,19 @@ extern "C" int polus_gemm_tc(const polus_gemm_t* g, void* stream) {
     else {
         const long long ctas256 = mt * cdiv(g->N, 256) * nb * split * CG;
         BN = ctas256 >= sms ? 256 : 128;
+        // 192-wide pair tiles (POLUS_GEMM_BN192=1, off by default): N = 768 outputs at 32768 rows are 384 tiles of 256 columns
+        // = 5.2 waves on 74 pairs, but 512 tiles of 192 = 6.9 waves.  MEASURED SLOWER (batch 128: fwd_ffn2 100.5 -> 114.3 us,
+        // dgrad_ffn1 99.9 -> 113.1, dgrad_qkv 78.2 -> 88.1, profiles/r01_gemm_shapes_v17_b128_bn{256,192}.log): the A tile is
+        // reused over 192 instead of 256 columns and the pair becomes operand-bandwidth bound, which costs more than the
+        // partly filled sixth wave.  Kept as a tested instantiation for shapes / parts where the balance differs.
+        const char* bn192_s = getenv("POLUS_GEMM_BN192");
+        const int bn192_env = bn192_s ? atoi(bn192_s) : 0;
+        const bool plain_epi = g->act == POLUS_ACT_NONE && g->C2 == nullptr && g->Emul == nullptr;
+        if (bn192_env && BN == 256 && CG == 2 && plain_epi && g->N % 192 == 0) {
+            const long long w256 = cdiv(mt * cdiv(g->N, 256) * nb * split, groups) * 256;
+            const long long w192 = cdiv(mt * cdiv(g->N, 192) * nb * split, groups) * 192;
+            if (w192 * 100 <= w256 * 95) BN = 192;
+        }
     }
     if (g->split_k == 0 && g->accumulate && g->act == POLUS_ACT_NONE && g->C2 == nullptr) {
         const long long tiles = mt * cdiv(g->N, BN) * nb;
@@ -1007,6 +1024,7 @@ extern "C" int polus_gemm_tc(const polus_gemm_t* g, void* stream) {
     }
     if (CG == 2) {
         if (BN == 128) return launch_major<128, 2>(g->A.mn_major, g->B.mn_major, ta, tb, tc, tc2, p, st);
+        if (BN == 192) return launch_major<192, 2>(g->A.mn_major, g->B.mn_major, ta, tb, tc, tc2, p, st);
         return launch_major<256, 2>(g->A.mn_major, g->B.mn_major, ta, tb, tc, tc2, p, st);
     }
     if (BN == 64) return launch_major<64, 1>(g->A.mn_major, g->B.mn_major, ta, tb, tc, tc2, p, st);

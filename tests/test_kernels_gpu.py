@@ -398,6 +398,45 @@ def test_gemm_tc_vs_checker_and_host(dev):
         np.testing.assert_allclose(r_t.numpy(), host, rtol=1e-4, atol=1e-4 * np.abs(host).max())
 
 
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn,f32", [(32768, 768, 192, 0, 0, 0), (32768, 768, 136, 0, 1, 0), (32700, 576, 200, 0, 0, 1),
+                                                  (32768, 768, 64, 1, 1, 0), (32768, 576, 128, 1, 0, 0), (32768, 768, 3072, 0, 1, 0)])
+def test_gemm_tc_192_wide_pair_tiles(dev, M, N, K, a_mn, b_mn, f32):
+    """192-column pair tiles (opt-in, POLUS_GEMM_BN192=1; the wave cost model picks them for N = 768 / 576 at 32768 rows:
+    6.9 instead of 5.2 waves -- measured slower than 256-wide tiles, so off by default): both operand majors (an MN-major B share of 96 columns is fetched as two 64-column groups), bias, bf16 and
+    fp32 outputs, ragged M and K, column sums -- against numpy fp64."""
+    from polus_b200 import _lib
+    from polus_b200.tensor import BF16, F32, Tensor
+    rng = np.random.default_rng(M + N + K + a_mn)
+    A = dev.bf16_round(rng.standard_normal((K, M) if a_mn else (M, K)).astype(np.float32))
+    B = dev.bf16_round(rng.standard_normal((K, N) if b_mn else (N, K)).astype(np.float32) * 0.1)
+    bias = rng.standard_normal(N).astype(np.float32)
+    a_t, b_t, bias_t = Tensor.from_numpy(A, BF16), Tensor.from_numpy(B, BF16), Tensor.from_numpy(bias, F32)
+    c_t = Tensor((M, N), F32 if f32 else BF16)
+    cs_t = Tensor.from_numpy(np.zeros(N, np.float32), F32)
+    g = _lib.Gemm()
+    g.M, g.N, g.K, g.batch0, g.batch1 = M, N, K, 1, 1
+    g.A = _lib.Operand(a_t.ptr, M if a_mn else K, 0, 0, a_mn, _lib.BF16)
+    g.B = _lib.Operand(b_t.ptr, N if b_mn else K, 0, 0, b_mn, _lib.BF16)
+    g.C, g.ldc, g.c_dtype, g.bias, g.alpha, g.act = c_t.ptr, N, (_lib.F32 if f32 else _lib.BF16), bias_t.ptr, 1.0, 0
+    g.accumulate, g.split_k = 0, 1
+    if not f32:
+        g.colsum = cs_t.ptr
+    import os
+    os.environ["POLUS_GEMM_BN192"] = "1"
+    try:
+        _lib.call("polus_gemm_tc", C.byref(g), st())
+    finally:
+        del os.environ["POLUS_GEMM_BN192"]
+    host = (A.T if a_mn else A).astype(np.float64) @ (B if b_mn else B.T).astype(np.float64) + bias
+    out = c_t.numpy().astype(np.float64)
+    scale = np.abs(host).max()
+    if f32:
+        np.testing.assert_allclose(out, host, rtol=1e-4, atol=1e-4 * scale)
+    else:
+        np.testing.assert_allclose(out, host, rtol=1e-2, atol=1e-2 * scale)
+        np.testing.assert_allclose(cs_t.numpy(), out.sum(0), rtol=1e-4, atol=1e-4 * np.abs(out).sum(0).max())
+
+
 @pytest.mark.parametrize("M,N,K,cg", [(512, 768, 256, 2), (300, 200, 136, 2), (8192, 3072, 768, 2), (128, 320, 64, 1), (77, 72, 520, 1)])
 def test_gemm_tc_fused_activation_backward(dev, M, N, K, cg):
     """The two epilogue modes that replace GeluGrad + BiasAddGrad (polus_gemm_t.c2_kind / Emul / colsum):
