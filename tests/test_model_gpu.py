@@ -178,3 +178,82 @@ def test_host_feed_ring_keeps_batches_apart_when_host_runs_ahead(monkeypatch):
             losses.append(float(l) if sync_every_step else l)
         return [float(l) for l in losses]
     np.testing.assert_allclose(run(False), run(True), rtol=2e-3)
+
+
+def test_full_size_bert_base_ner_properties():
+    """BASELINE config 2 at its FULL size (BERT-base: 12 layers, H=768, 12 heads, I=3072, vocab 30522; S=256, K=4), checked
+    through size-independent properties, because the numpy oracle cannot run 110 M parameters in test time:
+      * Viterbi paths and the CRF negative log-likelihood are recomputed by the oracle FROM THE DEVICE'S OWN EMISSIONS:
+        paths bit-exact (north_star), loss to fp32 tolerance;
+      * the loss is a batch mean: loss(batch) == mean(loss(first half), loss(second half)) with dropout off;
+      * inference is deterministic and independent of the other rows of the batch (row i alone == row i in the batch);
+      * padded key positions do not influence real tokens: changing input_ids under attention_mask == 0 leaves the
+        emissions of the real tokens unchanged;
+      * five Adam steps through the captured-graph trainer on one fixed batch lower the loss."""
+    from oracle import numpy_ref as R
+    from polus_b200 import device, ops, tensor
+    from polus_b200.models import BertConfig
+    from polus_b200.ner.models import BertNERModel
+    from polus_b200.optimizers import Adam
+    from polus_b200.training import ClassifierTrainer
+    from polus_b200.utils import set_random_seed
+    from tests.parity import make_batch
+    device.init(0)
+    tensor.reset_arena()
+    set_random_seed(123)
+    ops.set_step(0)
+    cfg = BertConfig(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)  # BERT-base defaults otherwise
+    K, B, S = 4, 8, 256
+    model = BertNERModel(cfg, output_classes=K, hidden_space=128, droupout_p=0.0)
+    rng = np.random.default_rng(123)
+    ids, mask, tt, tags = make_batch(rng, B, S, cfg.vocab_size, K)
+    x = {"input_ids": ids, "attention_mask": mask, "token_type_ids": tt}
+    y = np.eye(K, dtype=np.float32)[tags]
+    model(**x, training=False)
+    # SURVEY §8: 109,581,204 = HF BertModel (109,482,240) + NER head + CRF; the pooler Dense (768*768 + 768) gets no gradient
+    # on this path (polus/models.py:216 bypasses it) and is not instantiated here
+    assert sum(int(np.prod(w.shape)) for w in model.trainable_weights) == 109_581_204 - (768 * 768 + 768)
+    # spread the emissions (random-init heads give nearly flat ones: every path would tie)
+    out_kernel0, trans0 = model.out.kernel.numpy().copy(), model.crf.transitions.numpy().copy()
+    model.out.kernel.assign(out_kernel0 * 30.0)
+    model.crf.transitions.assign(rng.standard_normal((K, K)).astype(np.float32))
+
+    emis32 = model.emissions(**x, training=False).numpy().astype(np.float32)
+    emis = emis32.astype(np.float64)
+    assert np.isfinite(emis).all() and emis.std() > 0.05
+    trans32 = model.crf.transitions.numpy().astype(np.float32)
+    trans = trans32.astype(np.float64)
+    lens = np.full(B, S)  # polus/layers.py:74-76: the layer decodes every row at full length
+    # Viterbi: bit-exact given identical emissions (fp32 sums in the same order on both sides, ties -> lowest index)
+    paths_dev = model.inference(x).numpy()
+    paths_ref, _ = R.crf_decode(emis32, lens, trans32)
+    assert paths_dev.shape == (B, S) and np.array_equal(paths_dev.astype(np.int64), np.asarray(paths_ref).astype(np.int64))
+    assert len(np.unique(paths_dev)) > 1
+    # CRF loss from the same emissions
+    loss_dev = float(model.loss(tensor.Tensor.from_numpy(y, tensor.F32), model.crf(model.emissions(**x, training=True), training=True)))
+    loss_ref = float(np.mean(-R.crf_log_likelihood(emis, tags, lens, trans)))
+    assert abs(loss_dev - loss_ref) <= 2e-3 * abs(loss_ref), (loss_dev, loss_ref)
+
+    def loss_of(sl):
+        xs = {k: v[sl] for k, v in x.items()}
+        e = model.emissions(**xs, training=True)
+        return float(model.loss(tensor.Tensor.from_numpy(y[sl], tensor.F32), model.crf(e, training=True)))
+    whole, h0, h1 = loss_of(slice(0, B)), loss_of(slice(0, B // 2)), loss_of(slice(B // 2, B))
+    assert abs(whole - 0.5 * (h0 + h1)) <= 1e-4 * abs(whole), (whole, h0, h1)
+
+    # rows are independent; inference is deterministic
+    e_row = model.emissions(**{k: v[3:4] for k, v in x.items()}, training=False).numpy()
+    e_all = model.emissions(**x, training=False).numpy()
+    assert np.array_equal(e_all, model.emissions(**x, training=False).numpy())
+    np.testing.assert_allclose(e_row[0], e_all[3], atol=2e-2, rtol=2e-2)  # (batch 1 and batch 8 take different GEMM tile paths)
+    # tokens under the padding mask are invisible to the real ones
+    ids2 = ids.copy()
+    ids2[mask == 0] = rng.integers(0, cfg.vocab_size, size=int((mask == 0).sum()))
+    e_pad = model.emissions(input_ids=ids2, attention_mask=mask, token_type_ids=tt, training=False).numpy()
+    assert np.array_equal(e_pad[mask == 1], e_all[mask == 1])
+
+    model.out.kernel.assign(out_kernel0)  # back to the initial head for the optimisation check
+    model.crf.transitions.assign(trans0)
+    trainer = ClassifierTrainer(model, Adam(2e-5), model.loss)
+    losses = [float(trainer.train_step(x, y)) for _ in range(5)]
+    assert np.isfinite(losses).all() and losses[-1] < losses[0], losses
