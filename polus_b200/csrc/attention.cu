@@ -49,6 +49,14 @@ struct AttnParams {
     float* gbias;          // backward: [3H] bias gradient of the QKV projection += column sums of dqkv; may be null
 };
 
+// 2^x as ONE MUFU.EX2.  exp2f() costs four issue slots per value -- compare against -126, pre-scale by 0.5, MUFU, square --
+// to return denormal results; here x <= 0 always and a probability below 2^-126 is 0 in the bf16 P tile anyway.
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -238,13 +246,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             if (masked) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    v[j] = exp2f(fmaf(v[j], scl, fmaf(sMask[kc + j], kLog2e, -mxl)));
+                    v[j] = fast_exp2(fmaf(v[j], scl, fmaf(sMask[kc + j], kLog2e, -mxl)));
                     sum += v[j];
                 }
             } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    v[j] = exp2f(fmaf(v[j], scl, -mxl));
+                    v[j] = fast_exp2(fmaf(v[j], scl, -mxl));
                     sum += v[j];
                 }
             }
@@ -611,7 +619,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                     }
 #pragma unroll
                     for (int x = 0; x < 16; ++x) {
-                        const float pr = exp2f(s[x]);
+                        const float pr = fast_exp2(s[x]);
                         const float m = ((bits >> (16 * sub + x)) & 1u) ? p.inv_keep : 0.f;      // dropout multiplier
                         s[x] = pr * m;                                                           // dropped probability (for dV)
                         dp[x] = (pr * sc) * fmaf(dp[x], m, -dl);                                 // dS = P (dP - delta) / sqrt(dh)
