@@ -5,14 +5,15 @@
 // i.e. the TF ops behind HF TFBertSelfAttention: matmul(q,k^T)/sqrt(dh) + (1-mask)*-10000 (polus/models.py:175-195)
 // -> softmax -> dropout -> matmul(p, v), and their gradients.
 //
-// Forward, one CTA per (batch, head, 128-query tile), 160 threads:
-//   warp 0 / lane 0 : TMA loads of Q [128x64], K [256x64], V [256x64] from the packed [B,S,3H] projection (4-D
-//                     tensor map (dh, s, slot, b), slot = {q,k,v} x head); tcgen05.mma  S = Q K^T (M128 N256 K64) into
-//                     TMEM cols 0..255; later O = P V (M128 N64 K256) into cols 256..319.
-//   warps 1-4       : thread = query row.  Two passes over the TMEM row: max, then e = exp(x - max) (sum kept in fp32),
-//                     dropout with the same Philox counters as the unfused softmax kernel, bf16 e -> 128B-swizzled smem
-//                     (K-major A operand).  After the second MMA: O * (1/sum) -> bf16 -> smem -> TMA store into
-//                     ctx [B,S,H].  Saves L = max + log(sum) per row for backward.
+// Forward, one CTA per (batch, head, 128-query tile), 32 + 128 NSEG threads (NSEG = 2 for S <= 256, 4 for S <= 512):
+//   warp 0 / lane 0 : TMA loads of Q [128x64], K and V [128 NSEG x 64] from the packed [B,S,3H] projection (4-D tensor
+//                     map (dh, s, slot, b), slot = {q,k,v} x head); tcgen05.mma  S = Q K^T (M128 N256 K64 per 256 keys)
+//                     into TMEM cols 0..128 NSEG-1; later O = P V (M128 N64 K = 128 NSEG) into cols 0..63.
+//   other warps     : thread = (query row, 128-key segment).  Two passes over its TMEM columns: max, then
+//                     e = 2^((x - max) log2 e) (sum kept in fp32), dropout with the same Philox counters as the unfused
+//                     softmax kernel (decisions made, and written out for the backward, while the tiles are in flight),
+//                     bf16 e -> 128B-swizzled smem (K-major A operand) over the dead Q / K tiles.  After the second MMA:
+//                     O * (1/(1-p)) / sum -> bf16 -> smem -> TMA store into ctx [B,S,H].  Saves L = max + log(sum).
 //
 // Backward, one CTA per (batch, head, 256-query half): blocks (query tile i, key block j) of 128x128; K / V stream
 // through two 128-key stages; with two halves (S > 256) dK / dV partial sums are reduce-added in bf16 by the TMA unit.
@@ -259,7 +260,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             if (p.thresh16) {
                 const uint32_t bits = kbits[c];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? v[j] * p.inv_keep : 0.f;
+                for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? v[j] : 0.f;  // (the 1/(1-p) factor rides on 1/sum below)
             }
             // keys [kc, kc+32) -> k-block kc/64, 16-byte chunks ((kc/32)&1)*4 .. +3 of row `row`
             uint8_t* blk = sP + (kc >> 6) * 16384 + row * 128;
@@ -282,7 +283,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             for (int g = 0; g < NSEG; ++g) sum += sRed[g * 128 + row];
         }
         if (qvalid && half == 0) p.lse[grow] = mx + logf(sum);
-        const float inv = 1.0f / sum;
+        const float inv = p.inv_keep / sum;  // O = (keep o e) V * (1/(1-p)) / sum: one multiply per output instead of one per score
         ptx::mbar_wait(&bars[3], 0);
         ptx::tc_fence_after();
         {   // O columns [OC*half, +OC) of this row -> staging tile [128 rows][128 B] at the start of the P region

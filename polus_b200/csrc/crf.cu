@@ -26,7 +26,7 @@ namespace {
 //   beta-tilde_t[i] = r_t[i] / d_t, r_t[i] = sum_j E[i][j] w_{t+1}[j],  w_t[j] = exp(x_t[j] - m_t) * beta-tilde_t[j]
 //   gamma_t[j]  = alpha-hat_t[j] beta-tilde_t[j] / g_t,                g_t = sum_j alpha-hat_t[j] beta-tilde_t[j]
 //   xi_t[i][j]  = alpha-hat_t[i] E[i][j] w_{t+1}[j] / (d_t g_t)        (pair marginal of t -> t+1)
-// Shared memory: E [K][K], A [K][K], G [K][K], ah [T][K], w [T][K], bt [T][K], d [T].
+// Shared memory: E [K][K], A [K][K], G [K][K], ah [T][K], ex [T][K] (ex_t[j] = exp(x_t[j] - m_t)), bt [T][K], d [T], c [T].
 // reductions over the first kp lanes only (kp = power of two >= K): log2(kp) shuffles instead of 5 on the
 // sequential critical path (K = 4 tags => 2)
 __device__ __forceinline__ float kmax(float v, int kp) {
@@ -51,7 +51,8 @@ crf_nll_kernel(const float* __restrict__ emis, const int32_t* __restrict__ tags,
     float* sW = sAh + (size_t)T * K;  // [T][K]
     float* sBt = sW + (size_t)T * K;  // [T][K]
     float* sD = sBt + (size_t)T * K;  // [T]
-    __shared__ float s_logZ, s_score;
+    float* sC = sD + T;               // [T] forward normalisers c_t
+    __shared__ float s_logZ, s_score, s_msum[2];
     const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float amax = -INFINITY;
@@ -83,26 +84,46 @@ crf_nll_kernel(const float* __restrict__ emis, const int32_t* __restrict__ tags,
         if (tid == 0 && nll_out) nll_out[b] = 0.f;
         return;
     }
+    // ---------------- parallel over t: everything that does not depend on the recurrences.  ex_t[j] = exp(x_t[j] - m_t)
+    // goes to sW, sum_t m_t is reduced over the CTA: the exp / max / log work of a time step (~60 dependent instructions
+    // in one warp, the loop ran at ~1100 cycles per step) leaves the two sequential loops, which keep K FMAs, the
+    // normalising sum and one reciprocal per step.
+    {
+        float msum = 0.f;
+        for (int t = tid; t < len; t += 64) {
+            float m = -INFINITY;
+            for (int j = 0; j < K; ++j) m = fmaxf(m, x[t * K + j]);
+            for (int j = 0; j < K; ++j) sW[t * K + j] = expf(x[t * K + j] - m);
+            msum += m;
+        }
+        msum = warp_sum(msum);
+        if (lane == 0) s_msum[warp] = msum;
+    }
+    __syncthreads();
     if (warp == 0) {
         // ---------------- forward recursion + gold path score
-        float xv = act ? x[lane] : -INFINITY;
-        float m = kmax(xv, kp);
-        float u = act ? expf(xv - m) : 0.f;
+        float u = act ? sW[lane] : 0.f;
         float c = ksum(u, kp);
-        float ah = u / c;
-        float logZ = m + logf(c);
+        float ah = u * __frcp_rn(c);
         if (act) sAh[lane] = ah;
+        if (lane == 0) sC[0] = c;
+        float exn = (act && 1 < len) ? sW[K + lane] : 0.f;  // next step's factor, loaded one step ahead
         for (int t = 1; t < len; ++t) {
-            xv = act ? x[t * K + lane] : -INFINITY;  // issued early: independent of the recurrence
+            const float ex = exn;
+            exn = (act && t + 1 < len) ? sW[(t + 1) * K + lane] : 0.f;
             float s = 0.f;
             for (int i = 0; i < K; ++i) s = fmaf(__shfl_sync(0xffffffffu, ah, i), act ? sE[i * K + lane] : 0.f, s);
-            m = kmax(xv, kp);
-            u = act ? s * expf(xv - m) : 0.f;
+            u = s * ex;
             c = ksum(u, kp);
-            ah = u / c;
-            logZ += m + logf(c) + amax;
+            ah = u * __frcp_rn(c);
             if (act) sAh[t * K + lane] = ah;
+            if (lane == 0) sC[t] = c;
         }
+        __syncwarp();
+        // logZ = sum_t (m_t + log c_t) + (len - 1) max A, the logs taken in parallel
+        float lz = 0.f;
+        for (int t = lane; t < len; t += 32) lz += logf(sC[t]);
+        lz = warp_sum(lz);
         float sc = 0.f;
         for (int t = lane; t < len; t += 32) {
             const int yt = min(max(y[t], 0), K - 1);
@@ -111,26 +132,23 @@ crf_nll_kernel(const float* __restrict__ emis, const int32_t* __restrict__ tags,
         }
         sc = warp_sum(sc);
         if (lane == 0) {
-            s_logZ = logZ;
+            s_logZ = lz + (s_msum[0] + s_msum[1]) + (float)(len - 1) * amax;
             s_score = sc;
         }
     } else {
-        // ---------------- backward recursion
+        // ---------------- backward recursion (sW keeps ex_t; w_t[j] = ex_t[j] * beta-tilde_t[j] is rebuilt where it is used)
         float bt = act ? 1.0f : 0.f;  // beta-tilde_{len-1} (any positive constant: marginals renormalise)
+        float exn = act ? sW[(len - 1) * K + lane] : 0.f;
         for (int t = len - 1; t >= 0; --t) {
-            const float xv = act ? x[t * K + lane] : -INFINITY;
-            const float m = kmax(xv, kp);
-            const float wv = act ? expf(xv - m) * bt : 0.f;  // w_t[j]
-            if (act) {
-                sBt[t * K + lane] = bt;
-                sW[t * K + lane] = wv;
-            }
+            const float wv = exn * bt;  // w_t[j]
+            exn = (act && t > 0) ? sW[(t - 1) * K + lane] : 0.f;
+            if (act) sBt[t * K + lane] = bt;
             if (t > 0) {
                 float r = 0.f;  // r_{t-1}[i = lane]
                 for (int j = 0; j < K; ++j) r = fmaf(act ? sE[lane * K + j] : 0.f, __shfl_sync(0xffffffffu, wv, j), r);
                 const float d = ksum(r, kp);
                 if (lane == 0) sD[t - 1] = d;
-                bt = r / d;
+                bt = r * __frcp_rn(d);
             }
         }
     }
@@ -161,7 +179,7 @@ crf_nll_kernel(const float* __restrict__ emis, const int32_t* __restrict__ tags,
             const int i = pidx / K, j = pidx % K;
             const float e = sE[pidx];
             float acc = 0.f;
-            for (int t = 0; t + 1 < len; ++t) acc = fmaf(sAh[t * K + i] * sW[(t + 1) * K + j], sD[t], acc);
+            for (int t = 0; t + 1 < len; ++t) acc = fmaf(sAh[t * K + i] * (sW[(t + 1) * K + j] * sBt[(t + 1) * K + j]), sD[t], acc);
             sG[pidx] = acc * e;
         }
         __syncthreads();
@@ -274,7 +292,7 @@ extern "C" int polus_crf_nll(const float* emis, const int32_t* tags, const int32
     POLUS_REQUIRE(K >= 1 && K <= 32, "polus_crf_nll: K must be in [1,32] (got %d)", K);
     POLUS_REQUIRE(gemis != nullptr, "polus_crf_nll: gemis is required");
     POLUS_REQUIRE(T >= 1, "polus_crf_nll: T must be >= 1");
-    const size_t smem = ((size_t)3 * K * K + (size_t)3 * T * K + T) * sizeof(float);
+    const size_t smem = ((size_t)3 * K * K + (size_t)3 * T * K + 2 * (size_t)T) * sizeof(float);
     POLUS_REQUIRE(smem <= 200 * 1024, "polus_crf_nll: T*K = %d too large for the shared-memory forward-backward tables", T * K);
     if (B == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;

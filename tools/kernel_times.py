@@ -104,3 +104,13 @@ us = timeit(lambda k: _lib.call("polus_act_bwd_colsum", dy[k].ptr, dd[k].ptr, M,
 report("act_bwd_colsum (dy * stored act')", us, M * I * 6)
 us = timeit(lambda k: _lib.call("polus_act_bwd_colsum", dy[k].ptr, dd[k].ptr, M, I, _lib.ACT["gelu"], dz[k].ptr, gbias.ptr, None, st))
 report("act_bwd_colsum (gelu' recomputed)", us, M * I * 6)
+
+# CRF negative log-likelihood + gradients (latency-bound: T sequential steps per sequence, one CTA of two warps each)
+K = 4
+em = [Tensor.from_numpy(rng.standard_normal((B, S, K)).astype(np.float32), F32) for _ in range(NSETS)]
+tg = Tensor.from_numpy(rng.integers(1, K, (B, S)).astype(np.int32), I32)
+tr = Tensor.from_numpy(rng.standard_normal((K, K)).astype(np.float32), F32)
+nll, loss, ge, gt = Tensor((B,), F32), Tensor((), F32, zero=True), Tensor((B, S, K), F32), Tensor((K, K), F32, zero=True)
+us = timeit(lambda k: _lib.call("polus_crf_nll", em[k].ptr, tg.ptr, None, tr.ptr, None, B, S, K, nll.ptr, loss.ptr, ge.ptr, gt.ptr, st))
+print(json.dumps({"kernel": "crf_nll (fwd+bwd recursions, K=4)", "batch": B, "us": round(us, 2), "steps": S,
+                  "cycles_per_step_at_1.8GHz": round(us * 1800 / S)}), flush=True)
