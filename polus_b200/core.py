@@ -1,4 +1,5 @@
 """polus.core (reference polus/core.py:34-142), TF-free."""
+import logging
 import os
 
 import numpy as np
@@ -51,3 +52,11 @@ def execute_if(condition_var, error_message="", on=True):
                 print(error_message)
         return function_wrapper
     return decorator
+
+
+class BaseLogger:
+    """Base of the classes that log through the package logger.  polus/ner/utils.py:1 imports this name from polus.core,
+    which does not define it at the surveyed HEAD (the import fails there); this is the evident intent."""
+
+    def __init__(self):
+        self.logger = logging.getLogger("polus")

@@ -8,14 +8,12 @@
   `tags_int_pred`, `is_prediction` plus the gold `tags_int` (or a gold entity list) keyed by a document identifier --
   and applies the same BIO decoding (polus_b200.ner.bio.decode_bio).
 """
-import math
-
 import numpy as np
 
 from ..metrics import IConfusionMatrixTF, IMetric, _divide_no_nan
 from ..tensor import Tensor
 from .bio import decode_bio
-from .utils import INT2TAG
+from .utils import INT2TAG, eval_list_of_entity_sets, precision_recall_f1  # noqa: F401  (re-exported)
 
 
 class ISequentialConfusionMatrixTF(IConfusionMatrixTF):
@@ -45,29 +43,6 @@ class Accuracy(ISequentialConfusionMatrixTF):
         m = self.confusion_matrix.astype(np.float64)
         with np.errstate(divide="ignore", invalid="ignore"):
             return float(np.trace(m) / m.sum())
-
-
-def precision_recall_f1(tp, fp, fn, return_nan=True):
-    """polus/ner/utils.py:231-248: each ratio is nan (or 0) when its denominator is empty; f1 = tp / (tp + (fp + fn)/2)."""
-    bad = math.nan if return_nan else 0.0
-    precision = tp / (tp + fp) if tp + fp != 0 else bad
-    recall = tp / (tp + fn) if tp + fn != 0 else bad
-    f1 = tp / (tp + 0.5 * (fp + fn)) if tp + 0.5 * (fp + fn) != 0 else bad
-    return precision, recall, f1
-
-
-def eval_list_of_entity_sets(true, pred, return_nan=True):
-    """Strict evaluation (polus/ner/utils.py:269-308): TP = |true ∩ pred| per document, summed."""
-    assert isinstance(true, list) and isinstance(pred, list) and len(true) == len(pred)
-    results = {"tp": 0, "fp": 0, "fn": 0}
-    for t_es, p_es in zip(true, pred):
-        t_es, p_es = set(t_es), set(p_es)
-        tp = len(t_es & p_es)
-        results["tp"] += tp
-        results["fp"] += len(p_es) - tp
-        results["fn"] += len(t_es) - tp
-    results["precision"], results["recall"], results["f1"] = precision_recall_f1(results["tp"], results["fp"], results["fn"], return_nan)
-    return results
 
 
 def _host(x):

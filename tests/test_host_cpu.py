@@ -462,3 +462,63 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["e2e"] == {"value": d["value"], "unit": "sequences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     silent = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
     assert silent.returncode == 0 and silent.stdout.strip() == ""
+
+
+def test_bioc_sequence_decoder_flow_and_strict_evaluation():
+    """polus/ner/utils.py: samples_from_batch (is_prediction filtering, windows of one document concatenated) -> decode
+    (BIO error counters) -> strict entity-level evaluation; precision_recall_f1 / empty_results conventions."""
+    import math
+    from polus_b200.ner.utils import BioCSequenceDecoder, TAG2INT, empty_results, eval_list_of_entity_sets, precision_recall_f1
+    assert precision_recall_f1(3, 1, 2) == (0.75, 0.6, 3 / 4.5)
+    assert all(math.isnan(v) for v in precision_recall_f1(0, 0, 0)) and precision_recall_f1(0, 0, 0, return_nan=False) == (0.0, 0.0, 0.0)
+    assert empty_results() == {"tp": 0, "fp": 0, "fn": 0, "precision": 0.0, "recall": 0.0, "f1": 0.0}
+    assert empty_results(counts=False) == {"precision": 0.0, "recall": 0.0, "f1": 0.0}
+    r = eval_list_of_entity_sets([{(0, 4, "Chemical"), (10, 15, "Chemical")}, set()], [{(0, 4, "Chemical"), (11, 15, "Chemical")}, {(1, 2, "Chemical")}])
+    assert (r["tp"], r["fp"], r["fn"]) == (1, 2, 1) and r["f1"] == 1 / 2.5
+
+    text = "aspirin and sodium chloride here"
+    spans = [(0, 7), (8, 11), (12, 18), (19, 27), (28, 32)]
+    gold = {"corpusA": {"train": {"doc1": {"text": text, "es": [(0, 7, "Chemical"), (12, 27, "Chemical")]},
+                                  "doc2": {"text": "water", "es": [(0, 5, "Chemical")]}}}}
+    dec = BioCSequenceDecoder(gold)
+    O, B, I, PAD = TAG2INT["O"], TAG2INT["B-Chemical"], TAG2INT["I-Chemical"], TAG2INT["PAD"]
+    pad = (0, 0)
+    # doc1 arrives as two overlapping windows of 4 tokens: the overlap token is predicted by the first window only
+    batch1 = {"corpus": np.array([b"corpusA", b"corpusA"]), "group": np.array([b"train", b"train"]),
+              "identifier": np.array([b"doc1", b"doc1"]),
+              "spans": np.array([[spans[0], spans[1], spans[2], pad], [spans[2], spans[3], spans[4], pad]]),
+              "tags_int_pred": np.array([[B, O, B, PAD], [O, I, O, PAD]], np.int32),
+              "is_prediction": np.array([[1, 1, 1, 0], [0, 1, 1, 0]], np.int32)}
+    batch2 = {"corpus": np.array([b"corpusA"]), "group": np.array([b"train"]), "identifier": np.array([b"doc2"]),
+              "spans": np.array([[(0, 5), pad, pad, pad]]), "tags_int_pred": np.array([[I, PAD, PAD, PAD]], np.int32),
+              "is_prediction": np.array([[1, 0, 0, 0]], np.int32)}
+    dec.samples_from_batch(batch1)
+    dec.samples_from_batch([batch2])
+    assert dec.documents_dict["corpusA"]["train"]["doc1"]["tags"] == ["B-Chemical", "O", "B-Chemical", "I-Chemical", "O"]
+    counts = dec.decode()
+    assert counts == {"tags": 6, "inside_tag_after_other_tag": 1, "inside_tag_with_different_entity_type": 0}
+    assert dec.documents_dict["corpusA"]["train"]["doc1"]["es"] == {(0, 7, "Chemical"), (12, 27, "Chemical")}
+    res = dec._evaluate_ner()
+    assert (res["tp"], res["fp"], res["fn"]) == (3, 0, 0) and res["f1"] == 1.0 and dec.documents_dict == {}
+    # one call from a giant batch, with a miss
+    batch1["tags_int_pred"] = np.array([[B, O, O, PAD], [O, O, O, PAD]], np.int32)
+    res = dec.evaluate_ner_from_sample([batch1, batch2])
+    assert (res["tp"], res["fp"], res["fn"]) == (2, 0, 1)
+    with pytest.raises(NotImplementedError):
+        dec.get_collections()
+
+    # corpus objects that iterate like the reference's Corpus / Collection / Document
+    class Doc:
+        def __init__(self, text, es):
+            self._t, self._es = text, es
+        def text(self):
+            return self._t
+        def get_entity_set(self):
+            return self._es
+    class Corpus:
+        def __str__(self):
+            return "corpusB"
+        def __iter__(self):
+            return iter([("test", [("d", Doc("water", {(0, 5, "Chemical")}))])])
+    dec2 = BioCSequenceDecoder([Corpus()])
+    assert dec2.documents == {"corpusB": {"test": {"d": {"text": "water", "es": {(0, 5, "Chemical")}}}}}
