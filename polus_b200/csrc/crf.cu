@@ -217,6 +217,208 @@ crf_nll_kernel(const float* __restrict__ emis, const int32_t* __restrict__ tags,
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K = 4 (the polus.ner tag set), one sequence per LANE.  In crf_nll_kernel lane j owns tag j, so every time step walks
+// a chain of warp shuffles (K broadcasts of alpha-hat, log2 K butterfly steps for the normaliser): ~690 cycles per step
+// in ncu for ~35 instructions (profiles/r01_ncu_summary_v18_attn_crf_b128.txt).  Here a lane carries the whole K-vector
+// of ONE sequence in registers: a step is 16 FMAs, 3 adds, one reciprocal and 4 multiplies with no cross-lane traffic
+// (dependency chain ~75 cycles).  A CTA of 256 threads owns SEQ sequences: lane q of warp 0 runs the forward recursion
+// of sequence q, lane q of warp 1 the backward one, concurrently; the exp / max / log work, the gradients and the
+// gold-path scores are computed by all eight warps in parallel phases around them.  Same formulas (scaled
+// forward-backward, see the top of this file) and the same outputs as crf_nll_kernel.
+// Shared memory per sequence: ex [T][4] (+4 pad), alpha-hat [T][4] (+4), beta-tilde [T][4] (+4), m [T] (+1), c [T] (+1),
+// d [T] (+1): the pads put the rows of consecutive sequences on different banks for the per-lane row walks.
+template <int SEQ>
+__global__ void __launch_bounds__(256)
+crf_nll_lanes_kernel(const float* __restrict__ emis, const int32_t* __restrict__ tags, const int32_t* __restrict__ lens,
+                     const float* __restrict__ trans, const float* __restrict__ weights, int B, int T,
+                     float* __restrict__ nll_out, float* __restrict__ loss, float* __restrict__ gemis,
+                     float* __restrict__ gtrans) {
+    constexpr int K = 4;
+    extern __shared__ __align__(16) float sm[];
+    const int RS = T * K + K;  // row stride of the [T][4] tables (floats)
+    const int CS = T + 1;      // row stride of the [T] tables
+    float* sE = sm;                       // [4][4] exp(A - max A)
+    float* sA = sE + 16;                  // [4][4] A
+    float* sG = sA + 16;                  // [4][4] transition-gradient accumulator of this CTA
+    float* sEX = sG + 16;                 // [SEQ][RS]
+    float* sAH = sEX + (size_t)SEQ * RS;  // [SEQ][RS]
+    float* sBT = sAH + (size_t)SEQ * RS;  // [SEQ][RS]
+    float* sM = sBT + (size_t)SEQ * RS;   // [SEQ][CS]
+    float* sC = sM + (size_t)SEQ * CS;    // [SEQ][CS]
+    float* sD = sC + (size_t)SEQ * CS;    // [SEQ][CS]
+    __shared__ int s_len[SEQ];
+    __shared__ float s_gscale[SEQ];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b0 = blockIdx.x * SEQ;
+
+    float amax = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) amax = fmaxf(amax, trans[i]);
+    if (tid < 16) {
+        sA[tid] = trans[tid];
+        sE[tid] = expf(trans[tid] - amax);
+        sG[tid] = 0.f;
+    }
+    if (tid < SEQ) {
+        const int b = b0 + tid;
+        int len = 0;
+        float gs = 0.f;
+        if (b < B) {
+            len = lens ? lens[b] : T;
+            len = len < 0 ? 0 : (len > T ? T : len);
+            gs = (weights ? weights[b] : 1.0f) / (float)B;
+        }
+        s_len[tid] = len;
+        s_gscale[tid] = gs;
+    }
+    __syncthreads();
+
+    // ---------------- phase A (all threads, one (sequence, t) pair at a time): m_t = max_j x_t[j], ex_t[j] = exp(x_t[j] - m_t)
+    for (int it = tid; it < SEQ * T; it += 256) {
+        const int q = it / T, t = it - q * T;
+        if (t < s_len[q]) {
+            const float4 xv = *reinterpret_cast<const float4*>(emis + ((long long)(b0 + q) * T + t) * K);
+            const float m = fmaxf(fmaxf(xv.x, xv.y), fmaxf(xv.z, xv.w));
+            *reinterpret_cast<float4*>(sEX + (size_t)q * RS + t * K) = make_float4(expf(xv.x - m), expf(xv.y - m), expf(xv.z - m), expf(xv.w - m));
+            sM[q * CS + t] = m;
+        }
+    }
+    __syncthreads();
+
+    // ---------------- phase B: the two recursions, one sequence per lane
+    if (warp == 0 && lane < SEQ && s_len[lane] > 0) {
+        const int len = s_len[lane];
+        const float* ex = sEX + (size_t)lane * RS;
+        float* ah = sAH + (size_t)lane * RS;
+        float* cp = sC + lane * CS;
+        float e[16];  // E[i][j], i = previous tag, j = current tag
+#pragma unroll
+        for (int i = 0; i < 16; ++i) e[i] = sE[i];
+        float4 u = *reinterpret_cast<const float4*>(ex);
+        float c = (u.x + u.y) + (u.z + u.w);
+        float r = __frcp_rn(c);
+        float4 a = make_float4(u.x * r, u.y * r, u.z * r, u.w * r);
+        *reinterpret_cast<float4*>(ah) = a;
+        cp[0] = c;
+        float4 nx = 1 < len ? *reinterpret_cast<const float4*>(ex + K) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int t = 1; t < len; ++t) {
+            const float4 x4 = nx;
+            if (t + 1 < len) nx = *reinterpret_cast<const float4*>(ex + (t + 1) * K);  // one step ahead of its use
+            u.x = fmaf(a.x, e[0], fmaf(a.y, e[4], fmaf(a.z, e[8], a.w * e[12]))) * x4.x;
+            u.y = fmaf(a.x, e[1], fmaf(a.y, e[5], fmaf(a.z, e[9], a.w * e[13]))) * x4.y;
+            u.z = fmaf(a.x, e[2], fmaf(a.y, e[6], fmaf(a.z, e[10], a.w * e[14]))) * x4.z;
+            u.w = fmaf(a.x, e[3], fmaf(a.y, e[7], fmaf(a.z, e[11], a.w * e[15]))) * x4.w;
+            c = (u.x + u.y) + (u.z + u.w);
+            r = __frcp_rn(c);
+            a = make_float4(u.x * r, u.y * r, u.z * r, u.w * r);
+            *reinterpret_cast<float4*>(ah + t * K) = a;
+            cp[t] = c;
+        }
+    } else if (warp == 1 && lane < SEQ && s_len[lane] > 0) {
+        const int len = s_len[lane];
+        const float* ex = sEX + (size_t)lane * RS;
+        float* btp = sBT + (size_t)lane * RS;
+        float* dp = sD + lane * CS;
+        float e[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) e[i] = sE[i];
+        float4 bt = make_float4(1.f, 1.f, 1.f, 1.f);  // beta-tilde_{len-1} (any positive constant: marginals renormalise)
+        float4 nx = *reinterpret_cast<const float4*>(ex + (len - 1) * K);
+        for (int t = len - 1; t >= 0; --t) {
+            const float4 x4 = nx;
+            if (t > 0) nx = *reinterpret_cast<const float4*>(ex + (t - 1) * K);
+            *reinterpret_cast<float4*>(btp + t * K) = bt;
+            if (t > 0) {
+                const float4 w = make_float4(x4.x * bt.x, x4.y * bt.y, x4.z * bt.z, x4.w * bt.w);  // w_t[j]
+                float4 rr;  // r_{t-1}[i] = sum_j E[i][j] w_t[j]
+                rr.x = fmaf(e[0], w.x, fmaf(e[1], w.y, fmaf(e[2], w.z, e[3] * w.w)));
+                rr.y = fmaf(e[4], w.x, fmaf(e[5], w.y, fmaf(e[6], w.z, e[7] * w.w)));
+                rr.z = fmaf(e[8], w.x, fmaf(e[9], w.y, fmaf(e[10], w.z, e[11] * w.w)));
+                rr.w = fmaf(e[12], w.x, fmaf(e[13], w.y, fmaf(e[14], w.z, e[15] * w.w)));
+                const float d = (rr.x + rr.y) + (rr.z + rr.w);
+                dp[t - 1] = d;
+                const float r = __frcp_rn(d);
+                bt = make_float4(rr.x * r, rr.y * r, rr.z * r, rr.w * r);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---------------- phase C1: log-partition and gold-path score, one warp per sequence
+    for (int q = warp; q < SEQ; q += 8) {
+        const int b = b0 + q, len = s_len[q];
+        if (b >= B) continue;  // warp-uniform
+        if (len == 0) {
+            if (lane == 0 && nll_out) nll_out[b] = 0.f;
+            continue;
+        }
+        const float* x = emis + (long long)b * T * K;
+        const int32_t* y = tags + (long long)b * T;
+        float lz = 0.f, sc = 0.f;
+        for (int t = lane; t < len; t += 32) {
+            lz += sM[q * CS + t] + logf(sC[q * CS + t]);
+            const int yt = min(max(y[t], 0), K - 1);
+            sc += x[t * K + yt];
+            if (t + 1 < len) sc += sA[yt * K + min(max(y[t + 1], 0), K - 1)];
+        }
+        lz = warp_sum(lz);
+        sc = warp_sum(sc);
+        if (lane == 0) {
+            const float nll = lz + (float)(len - 1) * amax - sc;
+            if (nll_out) nll_out[b] = nll;
+            if (loss) atomicAdd(loss, nll * s_gscale[q]);
+        }
+    }
+    // ---------------- phase C2: emission gradients gscale * (gamma_t[j] - [y_t == j]), zero beyond len;
+    //                  d_t -> 1 / (d_t g_t), the pair-marginal normaliser
+    for (int it = tid; it < SEQ * T; it += 256) {
+        const int q = it / T, t = it - q * T;
+        const int b = b0 + q;
+        if (b >= B) continue;
+        float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t < s_len[q]) {
+            const float4 a = *reinterpret_cast<const float4*>(sAH + (size_t)q * RS + t * K);
+            const float4 bt = *reinterpret_cast<const float4*>(sBT + (size_t)q * RS + t * K);
+            const float4 pr = make_float4(a.x * bt.x, a.y * bt.y, a.z * bt.z, a.w * bt.w);
+            const float gsum = (pr.x + pr.y) + (pr.z + pr.w);
+            const float inv = 1.0f / gsum;
+            const float gs = s_gscale[q];
+            const int yt = min(max(tags[(long long)b * T + t], 0), K - 1);
+            g4.x = gs * (pr.x * inv - (yt == 0 ? 1.0f : 0.f));
+            g4.y = gs * (pr.y * inv - (yt == 1 ? 1.0f : 0.f));
+            g4.z = gs * (pr.z * inv - (yt == 2 ? 1.0f : 0.f));
+            g4.w = gs * (pr.w * inv - (yt == 3 ? 1.0f : 0.f));
+            if (t + 1 < s_len[q]) sD[q * CS + t] = 1.0f / (sD[q * CS + t] * gsum);
+        }
+        *reinterpret_cast<float4*>(gemis + ((long long)b * T + t) * K) = g4;
+    }
+    __syncthreads();
+    // ---------------- phase C3: transition gradients  sum_q gscale_q (E[i][j] sum_t alpha-hat_t[i] w_{t+1}[j] / (d_t g_t) - #gold(i -> j))
+    if (gtrans != nullptr) {
+        for (int q = warp; q < SEQ; q += 8) {
+            const int len = s_len[q];
+            if (b0 + q >= B || len < 2) continue;  // warp-uniform
+            const int pidx = lane & 15, i = pidx >> 2, j = pidx & 3;
+            const float* ah = sAH + (size_t)q * RS;
+            const float* ex = sEX + (size_t)q * RS;
+            const float* bt = sBT + (size_t)q * RS;
+            float acc = 0.f;
+            for (int t = lane >> 4; t + 1 < len; t += 2)  // the two half-warps take alternate time steps
+                acc = fmaf(ah[t * K + i] * (ex[(t + 1) * K + j] * bt[(t + 1) * K + j]), sD[q * CS + t], acc);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+            if (lane < 16) atomicAdd(&sG[pidx], s_gscale[q] * acc * sE[pidx]);
+            const int32_t* y = tags + (long long)(b0 + q) * T;
+            for (int t = lane; t + 1 < len; t += 32) {
+                const int yp = min(max(y[t], 0), K - 1), yn = min(max(y[t + 1], 0), K - 1);
+                atomicAdd(&sG[yp * K + yn], -s_gscale[q]);
+            }
+        }
+        __syncthreads();
+        if (tid < 16) atomicAdd(gtrans + tid, sG[tid]);
+    }
+}
+
 __global__ void crf_decode_kernel(const float* __restrict__ emis, const int32_t* __restrict__ lens,
                                   const float* __restrict__ trans, int T, int K, int32_t* __restrict__ tags_out,
                                   float* __restrict__ score_out) {
@@ -322,7 +524,23 @@ extern "C" int polus_crf_nll(const float* emis, const int32_t* tags, const int32
     if (B == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (loss) POLUS_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
-    if (K == 4) {  // the polus.ner tag set (PAD, O, B-, I-: polus/ner/utils.py:9-15)
+    // K = 4, the polus.ner tag set (PAD, O, B-, I-: polus/ner/utils.py:9-15): one sequence per lane (POLUS_CRF_LANES=0 -> the
+    // tag-per-lane kernel)
+    const char* lanes_s = getenv("POLUS_CRF_LANES");
+    const bool lanes_ok = K == 4 && !(lanes_s && atoi(lanes_s) == 0) &&
+                          ((reinterpret_cast<uintptr_t>(emis) | reinterpret_cast<uintptr_t>(gemis)) & 15) == 0;
+    auto lanes_smem = [&](int seq) { return ((size_t)48 + (size_t)3 * seq * (T * 4 + 4) + (size_t)3 * seq * (T + 1)) * sizeof(float); };
+    if (lanes_ok && lanes_smem(4) <= 200 * 1024) {
+        if (lanes_smem(8) <= 200 * 1024) {
+            const size_t sz = lanes_smem(8);
+            if (sz > 48 * 1024) POLUS_CHECK_CUDA(cudaFuncSetAttribute(crf_nll_lanes_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sz));
+            crf_nll_lanes_kernel<8><<<cdiv(B, 8), 256, sz, st>>>(emis, tags, lens, trans, weights, B, T, nll, loss, gemis, gtrans);
+        } else {
+            const size_t sz = lanes_smem(4);
+            if (sz > 48 * 1024) POLUS_CHECK_CUDA(cudaFuncSetAttribute(crf_nll_lanes_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sz));
+            crf_nll_lanes_kernel<4><<<cdiv(B, 4), 256, sz, st>>>(emis, tags, lens, trans, weights, B, T, nll, loss, gemis, gtrans);
+        }
+    } else if (K == 4) {
         if (smem > 48 * 1024) POLUS_CHECK_CUDA(cudaFuncSetAttribute(crf_nll_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         crf_nll_kernel<4><<<B, 64, smem, st>>>(emis, tags, lens, trans, weights, B, T, K, nll, loss, gemis, gtrans);
     } else {
