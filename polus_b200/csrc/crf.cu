@@ -1,6 +1,7 @@
 // Linear-chain CRF: negative log-likelihood with gradients (forward-backward in one launch) and Viterbi
-// decode.  One warp per sequence, lane j owns tag j (K <= 32), transitions in shared memory, the
-// T-step recurrence kept in registers + warp shuffles.
+// decode.  General K <= 32: one warp per recursion, lane j owns tag j, transitions in shared memory, the T-step
+// recurrence kept in registers + warp shuffles (crf_nll_kernel, crf_decode_kernel).  K = 4, the polus.ner tag set:
+// one SEQUENCE per lane, the whole K-vector in registers, no cross-lane traffic (crf_nll_lanes_kernel).
 //
 // Replaces tensorflow_addons.text.crf_log_likelihood / crf_decode, which the reference calls from
 // polus/layers.py:78-80 (decode, also run in training), :91-96 and :109-114 (loss); TF executes them

@@ -3,18 +3,53 @@ first; an entity labels tokens only when its span is covered exactly by whole to
 unlabelled ("O"); the first token gets B-<type>, the rest I-<type>."""
 
 
-def get_bio(token_spans, entities, default="O"):
-    """token_spans: [(start, end)] in text order; entities: [(start, end, type)] -> list of tags."""
-    tags = [default] * len(token_spans)
-    for es, ee, etype in sorted(entities, key=lambda e: e[1] - e[0], reverse=True):
-        idx = [i for i, (ts, te) in enumerate(token_spans) if ts >= es and te <= ee]
-        if not idx or token_spans[idx[0]][0] != es or token_spans[idx[-1]][1] != ee:
-            continue  # the entity does not fit token boundaries exactly
-        if any(tags[i] != default for i in idx):
-            continue  # never overwrite a longer entity
+def _entity_fields(entity):
+    """(start, end, type) of a tuple entity or of an object with .start / .end / .typ (the reference's Entity)."""
+    if isinstance(entity, (tuple, list)):
+        return entity[0], entity[1], entity[2]
+    return entity.start, entity.end, entity.typ
+
+
+def longer_entities_first(entities):
+    """Longer spans first: they win when entities overlap (reference bio.py:5-10; stable for equal lengths)."""
+    return sorted(entities, key=lambda e: _entity_fields(e)[1] - _entity_fields(e)[0], reverse=True)
+
+
+def entity_fits_spans(entity, spans):
+    """Indexes of the consecutive token spans that cover the entity EXACTLY (first span starts at entity.start, last one
+    ends at entity.end), or False (reference bio.py:13-43).  `spans` are in text order."""
+    start, end, _ = _entity_fields(entity)
+    indexes = []
+    for i, (s0, s1) in enumerate(spans):
+        if not indexes:
+            if s0 > start:
+                return False  # walked past the entity's first character without a token starting there
+            if s0 != start:
+                continue
+        indexes.append(i)
+        if s1 == end:
+            return indexes
+        if s1 > end:
+            return False
+    return False
+
+
+def update_tags(tags, spans, entity, default="O"):
+    """Writes B-<type> / I-<type> over the entity's tokens, only if it fits token boundaries exactly and none of its tokens
+    is already labelled (reference bio.py:46-89).  In place."""
+    idx = entity_fits_spans(entity, spans)
+    if idx and all(tags[i] == default for i in idx):
+        etype = _entity_fields(entity)[2]
         tags[idx[0]] = f"B-{etype}"
         for i in idx[1:]:
             tags[i] = f"I-{etype}"
+
+
+def get_bio(token_spans, entities, default="O"):
+    """token_spans: [(start, end)] in text order; entities: [(start, end, type)] -> list of tags (reference bio.py:92-114)."""
+    tags = [default] * len(token_spans)
+    for entity in longer_entities_first(entities):
+        update_tags(tags, token_spans, entity, default)
     return tags
 
 

@@ -522,3 +522,46 @@ def test_bioc_sequence_decoder_flow_and_strict_evaluation():
             return iter([("test", [("d", Doc("water", {(0, 5, "Chemical")}))])])
     dec2 = BioCSequenceDecoder([Corpus()])
     assert dec2.documents == {"corpusB": {"test": {"d": {"text": "water", "es": {(0, 5, "Chemical")}}}}}
+
+
+def test_bio_helpers_match_reference_semantics():
+    """polus/ner/bio.py:5-114: longest entity first, exact fit over consecutive token spans, no overwriting."""
+    from polus_b200.ner.bio import entity_fits_spans, get_bio, longer_entities_first, update_tags
+    spans = [(0, 7), (8, 11), (12, 18), (19, 27), (28, 32)]
+    assert entity_fits_spans((12, 27, "Chemical"), spans) == [2, 3]
+    assert entity_fits_spans((0, 7, "Chemical"), spans) == [0]
+    assert entity_fits_spans((12, 20, "Chemical"), spans) is False      # ends inside a token
+    assert entity_fits_spans((13, 27, "Chemical"), spans) is False      # starts inside a token
+    assert entity_fits_spans((40, 45, "Chemical"), spans) is False
+    ents = [(12, 18, "Chemical"), (12, 27, "Chemical"), (0, 7, "Chemical")]
+    assert longer_entities_first(ents)[0] == (12, 27, "Chemical")
+    tags = ["O"] * 5
+    update_tags(tags, spans, (12, 27, "Chemical"))
+    update_tags(tags, spans, (12, 18, "Chemical"))                       # overlaps an annotated entity: discarded
+    assert tags == ["O", "O", "B-Chemical", "I-Chemical", "O"]
+    assert get_bio(spans, ents) == ["B-Chemical", "O", "B-Chemical", "I-Chemical", "O"]
+
+    class E:  # reference-style entity objects
+        def __init__(self, s, e, t):
+            self.start, self.end, self.typ = s, e, t
+    assert get_bio(spans, [E(19, 32, "Chemical")]) == ["O", "O", "O", "B-Chemical", "I-Chemical"]
+    # randomised: same result as a direct statement of the rule
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        cuts = np.sort(rng.choice(np.arange(1, 60), size=rng.integers(2, 12), replace=False))
+        toks = [(int(a), int(b) - int(rng.integers(0, 2))) for a, b in zip(cuts[:-1], cuts[1:])]
+        toks = [(a, max(b, a + 1)) for a, b in toks]
+        ents = []
+        for _ in range(rng.integers(0, 5)):
+            i = int(rng.integers(0, len(toks)))
+            j = int(rng.integers(i, len(toks)))
+            s0, e0 = toks[i][0] + int(rng.integers(0, 2)) * int(rng.integers(0, 2)), toks[j][1]
+            ents.append((s0, e0, "Chemical"))
+        want = ["O"] * len(toks)
+        for s0, e0, ty in sorted(ents, key=lambda e: e[1] - e[0], reverse=True):
+            idx = [k for k, (a, b) in enumerate(toks) if a >= s0 and b <= e0]
+            if idx and toks[idx[0]][0] == s0 and toks[idx[-1]][1] == e0 and all(want[k] == "O" for k in idx):
+                want[idx[0]] = f"B-{ty}"
+                for k in idx[1:]:
+                    want[k] = f"I-{ty}"
+        assert get_bio(toks, ents) == want
