@@ -299,6 +299,40 @@ class EarlyStop(Callback):
             logger.info(f"The training will stop early since the loss did not improve in {self.patience} consecutive epochs")
 
 
+class HPOPruneCallback(Callback):
+    """Reports the validation metric of every epoch to the hyper-parameter search backend and stops a pruned trial
+    (reference callbacks.py:366-405).  The search driver (polus/hpo.py, optuna) is outside the training step and is
+    not part of this package: without an HPO context the reference's callback does nothing but warn, and
+    that is the behaviour kept here -- a script that lists it among its callbacks runs unchanged.  `hpo_backend` may
+    be handed in directly (any object with report(score, step=) and should_prune(), e.g. an optuna Trial)."""
+
+    def __init__(self, validator_name, metric_name, hpo_backend=None):
+        super().__init__()
+        self.hpo_backend = hpo_backend
+        if self.hpo_backend is None:
+            logger.warning("HPOPruneCallback was initialized however, there is no hpo context at the moment")
+        self.validator_name = validator_name
+        self.metric_name = metric_name
+
+    @runs_if_root
+    def on_epoch_end(self, epoch):
+        if self.hpo_backend is None:
+            return
+        score = self.coordinator.shared_dict["validation"][self.validator_name][self.metric_name][-1]
+        if not (hasattr(self.hpo_backend, "report") and hasattr(self.hpo_backend, "should_prune")):
+            raise ValueError(f"The current {self.hpo_backend} backend is not supported so we do not know how to prune")
+        self.hpo_backend.report(score, step=epoch)
+        if self.hpo_backend.should_prune():
+            message = f"Trial was pruned at epoch {epoch} with a score of {score}."
+            try:
+                from optuna.exceptions import TrialPruned
+            except ImportError:
+                self.coordinator.trainer.early_stop = True
+                logger.info(message)
+                return
+            raise TrialPruned(message)
+
+
 class Profiler(Callback):
     """Profiling window over [steps_interval[0], steps_interval[1]) global steps; stops training when
     the window closes, like the reference (callbacks.py:408-470).  Instead of tf.profiler it brackets

@@ -565,3 +565,25 @@ def test_bio_helpers_match_reference_semantics():
                 for k in idx[1:]:
                     want[k] = f"I-{ty}"
         assert get_bio(toks, ents) == want
+
+
+def test_hpo_prune_callback_without_and_with_backend():
+    """polus/callbacks.py:366-405: a no-op (with a warning) when there is no HPO context; with a backend it reports the
+    last validation score of the epoch and stops a pruned trial."""
+    from types import SimpleNamespace
+    from polus_b200.callbacks import HPOPruneCallback
+    cb = HPOPruneCallback("val", "f1")
+    cb.coordinator = SimpleNamespace(shared_dict={"validation": {"val": {"f1": [0.1, 0.2]}}}, trainer=SimpleNamespace(early_stop=False))
+    cb.on_epoch_end(0)  # nothing happens
+    seen = []
+    backend = SimpleNamespace(report=lambda score, step: seen.append((score, step)), should_prune=lambda: len(seen) >= 2)
+    cb = HPOPruneCallback("val", "f1", hpo_backend=backend)
+    cb.coordinator = SimpleNamespace(shared_dict={"validation": {"val": {"f1": [0.1, 0.2]}}}, trainer=SimpleNamespace(early_stop=False))
+    cb.on_epoch_end(0)
+    assert seen == [(0.2, 0)] and cb.coordinator.trainer.early_stop is False
+    try:
+        cb.on_epoch_end(1)
+        pruned = cb.coordinator.trainer.early_stop  # optuna absent: the trainer is told to stop
+    except Exception as e:  # optuna present: TrialPruned
+        pruned = type(e).__name__ == "TrialPruned"
+    assert pruned and seen[-1] == (0.2, 1)
