@@ -28,6 +28,11 @@ SEQ = 256
 TRAIN_GFLOP_PER_SEQ = 137.71  # BASELINE.md §3 (GEMM FLOPs, fwd+bwd = 3x fwd), BERT-base S=256
 
 
+def workload_name(batch):
+    return (f"BERT-base (L12 H768 nh12 I3072) polus.ner token classification + CRF, seq {SEQ}, "
+            f"batch {batch}/GPU, dropout 0.1, Adam+warmup")
+
+
 def read_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -99,7 +104,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "train_sequences_per_second", "value": sps, "unit": "sequences/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"BERT-base NER+CRF train step, seq {SEQ}", "per_step_sample": f"{batch} sequences",
+            "config": {"workload": workload_name(args.batch), "global_batch": args.batch * args.gpus, "seq_len": SEQ,
+                       "parallelism": f"dp{args.gpus}", "per_step_sample": f"{batch} sequences of the same workload per timed step",
                        "note": "CPU port of the reference step (TensorFlow is not installable in this image; oracle/torch_ref.py)"},
             "cpu_baseline": {"value": sps, "unit": "sequences/s", "cores": threads, "kind": "port",
                              "sample": f"{args.steps} steps of {batch} sequences x {SEQ} tokens"},
@@ -296,8 +302,7 @@ def run_ours(args):
     line = {"metric": "train_sequences_per_second", "value": value, "unit": "sequences/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"BERT-base (L12 H768 nh12 I3072) polus.ner token classification + CRF, seq {SEQ}, "
-                                   f"batch {args.batch}/GPU, dropout 0.1, Adam+warmup",
+            "config": {"workload": workload_name(args.batch),
                        "global_batch": args.batch * world, "seq_len": SEQ, "parallelism": f"dp{world}",
                        "preheat_steps": args.preheat_steps,
                        "l2": "per-step working set (weights 0.2 GB bf16 + activations > 3 GB) exceeds the 126 MB L2; no flush needed",
