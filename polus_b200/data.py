@@ -412,24 +412,10 @@ def build_bert_embeddings(checkpoint, bert_layer_index=None, **kwargs):
     computed without recording gradients.  With `bert_layer_index` the model is cut there first (split_bert_model)
     and only the lower layers run.  `checkpoint` is resolved offline (BertConfig / dict / directory / BertModel)."""
     from . import ops
-    from .models import BertModel, split_bert_model, split_bert_model_from_checkpoint
-    if isinstance(checkpoint, BertModel):
-        bert_model = checkpoint
-        if bert_layer_index is not None:
-            bert_model = split_bert_model(bert_model, bert_layer_index, return_post_bert_model=False)
-    elif bert_layer_index is not None:
-        bert_model = split_bert_model_from_checkpoint(checkpoint, bert_layer_index, return_post_bert_model=False)
-    else:
-        from .models import BertConfig
-        import json
-        import os
-        if isinstance(checkpoint, BertConfig):
-            bert_model = BertModel(checkpoint)
-        elif isinstance(checkpoint, dict):
-            bert_model = BertModel(BertConfig(**checkpoint))
-        else:
-            with open(os.path.join(checkpoint, "config.json")) as f:
-                bert_model = BertModel(BertConfig(**json.load(f)))
+    from .models import bert_model_from_checkpoint, split_bert_model
+    bert_model = bert_model_from_checkpoint(checkpoint)
+    if bert_layer_index is not None:
+        bert_model = split_bert_model(bert_model, bert_layer_index, return_post_bert_model=False)
 
     def embeddings(**kw):
         with ops.no_grad():

@@ -149,24 +149,40 @@ def split_bert_model(bert_model, index_layer, init_models=False, return_pre_bert
     return bert_model if return_pre_bert_model else post_model
 
 
+def bert_model_from_checkpoint(bert_model_checkpoint):
+    """Offline stand-in for `TFAutoModel.from_pretrained(checkpoint)` (reference models.py:225-229, data.py:526-530, which
+    download from the HuggingFace hub).  `bert_model_checkpoint` may be
+      * a BertModel (returned as is), a BertConfig or a dict of BertConfig fields (random init), or
+      * a directory holding `config.json` and, optionally, weights: `weights.npz` (arrays weight0..N in get_weights()
+        order, what SavableModel.save writes) or a HuggingFace snapshot's `model.safetensors` (imported with
+        polus_b200.pretrained.load_hf_bert_weights; task heads such as `cls.*` are ignored)."""
+    if isinstance(bert_model_checkpoint, BertModel):
+        return bert_model_checkpoint
+    if isinstance(bert_model_checkpoint, BertConfig):
+        return BertModel(bert_model_checkpoint)
+    if isinstance(bert_model_checkpoint, dict):
+        return BertModel(BertConfig(**bert_model_checkpoint))
+    path = str(bert_model_checkpoint)
+    if not os.path.isdir(path):
+        raise ValueError(f"cannot resolve checkpoint {bert_model_checkpoint!r} offline: pass a BertModel, a BertConfig, a dict "
+                         f"or a directory with config.json (+ weights.npz or model.safetensors)")
+    with open(os.path.join(path, "config.json")) as f:
+        bert_model = BertModel(BertConfig(**json.load(f)))
+    npz, st = os.path.join(path, "weights.npz"), os.path.join(path, "model.safetensors")
+    if os.path.exists(npz):
+        with np.load(npz) as z:
+            bert_model.set_weights([z[f"weight{i}"] for i in range(len(z.files))])
+    elif os.path.exists(st):
+        from .pretrained import load_hf_bert_weights
+        load_hf_bert_weights(bert_model, st, strict=True)
+    else:
+        logger.warning(f"{path} holds no weights.npz / model.safetensors: the encoder keeps its random initialisation")
+    return bert_model
+
+
 def split_bert_model_from_checkpoint(bert_model_checkpoint, index_layer, init_models=False, return_pre_bert_model=True,
                                      return_post_bert_model=True):
-    """The reference downloads a HF checkpoint here (models.py:225-229).  Offline: `bert_model_checkpoint`
-    may be a BertConfig / dict (random init) or a directory holding `config.json` + `weights.npz` in
-    get_weights() order."""
-    if isinstance(bert_model_checkpoint, BertConfig):
-        bert_model = BertModel(bert_model_checkpoint)
-    elif isinstance(bert_model_checkpoint, dict):
-        bert_model = BertModel(BertConfig(**bert_model_checkpoint))
-    elif os.path.isdir(str(bert_model_checkpoint)):
-        with open(os.path.join(bert_model_checkpoint, "config.json")) as f:
-            bert_model = BertModel(BertConfig(**json.load(f)))
-        wpath = os.path.join(bert_model_checkpoint, "weights.npz")
-        if os.path.exists(wpath):
-            with np.load(wpath) as z:
-                bert_model.set_weights([z[f"weight{i}"] for i in range(len(z.files))])
-    else:
-        raise ValueError(f"cannot resolve checkpoint {bert_model_checkpoint!r} offline: pass a BertConfig, a dict or a "
-                         f"directory with config.json (+ weights.npz)")
+    """The reference downloads a HF checkpoint here (models.py:225-229); offline resolution: bert_model_from_checkpoint."""
+    bert_model = bert_model_from_checkpoint(bert_model_checkpoint)
     return split_bert_model(bert_model, index_layer, init_models=init_models,
                             return_pre_bert_model=return_pre_bert_model, return_post_bert_model=return_post_bert_model)
