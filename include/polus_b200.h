@@ -251,10 +251,13 @@ typedef struct {
 } polus_adam_cfg_t;
 /* Keras Adam over a flat arena: lr_t = lr*sqrt(1-b2^t)/(1-b1^t); p -= lr_t*m/(sqrt(v)+eps).
  * Also refreshes the bf16 shadow, zeroes g, and (thread 0) increments *d_step.
- * d_decay_mask: optional per-element u8 (1 = apply weight decay). */
+ * d_decay_mask: optional per-element u8 (1 = apply weight decay).
+ * d_hyper: optional device float[4] {lr, grad_scale, weight_decay, end_lr} that overrides the same cfg
+ * fields at run time -- cfg is frozen into a captured CUDA graph, the buffer is not, so
+ * optimizer.learning_rate.assign() (training.py:90-94) takes effect on the next replay. */
 int polus_adam(float* d_p, float* d_g, float* d_m, float* d_v, polus_bf16_t* d_p_bf16,
                const uint8_t* d_decay_mask, int64_t n, const polus_adam_cfg_t* cfg,
-               uint32_t* d_step, int increment_step, void* stream);
+               const float* d_hyper, uint32_t* d_step, int increment_step, void* stream);
 
 /* ---------------------------------------------------------------- small tensor utilities ---- */
 int polus_cast(const void* d_src, int src_dtype, void* d_dst, int dst_dtype, int64_t n, void* stream);
@@ -293,9 +296,14 @@ int polus_scale_by_clip(float* d_x, int64_t n, const float* d_sumsq, float max_n
  * 208-211; polus/callbacks.py:249) with NCCL over NVLink. */
 int polus_comm_unique_id(void* h_id128);            /* 128 bytes, call on rank 0 */
 int polus_comm_init(int rank, int size, const void* h_id128);
+/* same, capping the communicator's CTAs (ncclConfig_t.maxCTAs): the exchange runs under backward and every SM
+ * NCCL holds is one the persistent GEMMs wait for; max_ctas <= 0 keeps NCCL's default */
+int polus_comm_init_cfg(int rank, int size, const void* h_id128, int max_ctas);
 int polus_comm_size(void);
 int polus_comm_rank(void);
 int polus_comm_allreduce_f32(float* d_buf, int64_t n, void* stream); /* sum, in place */
+/* sum with a bf16 wire format: pack fp32 -> d_scratch (n bf16), ncclAllReduce(bf16), unpack into d_buf */
+int polus_comm_allreduce_bf16(float* d_buf, polus_bf16_t* d_scratch, int64_t n, void* stream);
 int polus_comm_broadcast(void* d_buf, size_t bytes, int root, void* stream);
 int polus_comm_allgather(const void* d_send, void* d_recv, size_t bytes_per_rank, void* stream);
 int polus_comm_destroy(void);

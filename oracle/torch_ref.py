@@ -73,7 +73,7 @@ def time_train_steps(batch=8, seq=256, steps=2, warmup=1, threads=None, **model_
         loss = net(ids, mask, tt, tags)
         loss.backward()
         opt.step()
-        return float(loss)
+        return float(loss.detach())
 
     for _ in range(warmup):
         step()
@@ -82,3 +82,85 @@ def time_train_steps(batch=8, seq=256, steps=2, warmup=1, threads=None, **model_
         step()
     dt = (time.perf_counter() - t0) / max(steps, 1)
     return batch / dt, dt, threads
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Parity helpers (tests/test_fullsize_gpu.py): the SAME weights on both sides, loss / emissions / gradients / N Keras-Adam
+# steps of the full 12-layer model in fp32 on the CPU.
+# ------------------------------------------------------------------------------------------------------------------
+def load_weights(net, hf_state, head):
+    """hf_state: HuggingFace-named numpy state dict of the encoder (polus_b200.pretrained.export_hf_bert_weights layout);
+    head: {"Wa" [H,h], "ba", "Wb" [h,K], "bb", "trans" [K,K]} in the Keras [in, out] layout."""
+    import torch
+    with torch.no_grad():
+        sd = {}
+        for k, v in hf_state.items():
+            v = torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32))
+            if k.startswith("embeddings."):
+                sd["emb." + k[len("embeddings."):]] = v
+            elif k.startswith("encoder.layer."):
+                sd["layers." + k[len("encoder.layer."):]] = v
+        missing, unexpected = net.load_state_dict(sd, strict=False)
+        bad = [m for m in missing if not (m.startswith(("fc1", "fc2", "trans")) or m.endswith("position_ids") or m.endswith("token_type_ids"))]
+        assert not bad and not unexpected, (bad, unexpected)
+        net.fc1.weight.copy_(torch.from_numpy(np.ascontiguousarray(head["Wa"].T, dtype=np.float32)))
+        net.fc1.bias.copy_(torch.from_numpy(np.asarray(head["ba"], np.float32)))
+        net.fc2.weight.copy_(torch.from_numpy(np.ascontiguousarray(head["Wb"].T, dtype=np.float32)))
+        net.fc2.bias.copy_(torch.from_numpy(np.asarray(head["bb"], np.float32)))
+        net.trans.copy_(torch.from_numpy(np.asarray(head["trans"], np.float32)))
+    return net
+
+
+def emissions(net, ids, mask, tt):
+    import torch
+    add = (1.0 - mask.float())[:, None, None, :] * -10000.0
+    h = net.emb(input_ids=ids, token_type_ids=tt)
+    for l in net.layers:
+        h = l(h, attention_mask=add)
+        h = h[0] if isinstance(h, tuple) else h
+    return net.fc2(torch.nn.functional.silu(net.fc1(net.drop(h))))
+
+
+def named_grads(net, H):
+    """Gradients under the names tests/parity.py uses for the device model (Keras [in, out] layout, fused q|k|v)."""
+    g = lambda p: p.grad.detach().numpy().astype(np.float64)
+    out = {"emb/word": g(net.emb.word_embeddings.weight), "emb/pos": g(net.emb.position_embeddings.weight),
+           "emb/type": g(net.emb.token_type_embeddings.weight), "emb/emb_ln_g": g(net.emb.LayerNorm.weight),
+           "emb/emb_ln_b": g(net.emb.LayerNorm.bias), "head/Wa": g(net.fc1.weight).T, "head/ba": g(net.fc1.bias),
+           "head/Wb": g(net.fc2.weight).T, "head/bb": g(net.fc2.bias), "trans": g(net.trans)}
+    for i, l in enumerate(net.layers):
+        a = l.attention
+        out[f"layers/{i}/Wqkv"] = np.concatenate([g(a.self.query.weight).T, g(a.self.key.weight).T, g(a.self.value.weight).T], axis=1)
+        out[f"layers/{i}/bqkv"] = np.concatenate([g(a.self.query.bias), g(a.self.key.bias), g(a.self.value.bias)])
+        out[f"layers/{i}/Wo"], out[f"layers/{i}/bo"] = g(a.output.dense.weight).T, g(a.output.dense.bias)
+        out[f"layers/{i}/ln1_g"], out[f"layers/{i}/ln1_b"] = g(a.output.LayerNorm.weight), g(a.output.LayerNorm.bias)
+        out[f"layers/{i}/W1"], out[f"layers/{i}/b1"] = g(l.intermediate.dense.weight).T, g(l.intermediate.dense.bias)
+        out[f"layers/{i}/W2"], out[f"layers/{i}/b2"] = g(l.output.dense.weight).T, g(l.output.dense.bias)
+        out[f"layers/{i}/ln2_g"], out[f"layers/{i}/ln2_b"] = g(l.output.LayerNorm.weight), g(l.output.LayerNorm.bias)
+    return out
+
+
+def keras_adam_steps(net, batch, steps, lr, beta1=0.9, beta2=0.999, eps=1e-7):
+    """`steps` optimisation steps with Keras Adam (epsilon outside the bias-corrected sqrt, polus/training.py:191 with
+    tf.keras.optimizers.Adam); returns the per-step losses.  torch.optim.Adam places epsilon differently."""
+    import torch
+    ids, mask, tt, tags = batch
+    params = [p for p in net.parameters() if p.requires_grad]
+    m = [torch.zeros_like(p) for p in params]
+    v = [torch.zeros_like(p) for p in params]
+    losses = []
+    for t in range(1, steps + 1):
+        for p in params:
+            p.grad = None
+        loss = net(ids, mask, tt, tags)
+        loss.backward()
+        losses.append(float(loss.detach()))
+        lr_t = lr * (1.0 - beta2 ** t) ** 0.5 / (1.0 - beta1 ** t)
+        with torch.no_grad():
+            for p, mi, vi in zip(params, m, v):
+                if p.grad is None:
+                    continue
+                mi.mul_(beta1).add_(p.grad, alpha=1.0 - beta1)
+                vi.mul_(beta2).addcmul_(p.grad, p.grad, value=1.0 - beta2)
+                p.sub_(lr_t * mi / (vi.sqrt() + eps))
+    return losses

@@ -106,7 +106,7 @@ _SIGS = {
     "polus_crf_mask_transitions": [p, p, i32, p, p],
     "polus_crf_sample_weights": [p, p, f32, i32, i32, i32, p, p],
     "polus_xent": [i32, p, p, p, f32, i32, i32, p, p, p],
-    "polus_adam": [p, p, p, p, p, p, i64, C.POINTER(AdamCfg), p, i32, p],
+    "polus_adam": [p, p, p, p, p, p, i64, C.POINTER(AdamCfg), p, p, i32, p],
     "polus_cast": [p, i32, p, i32, i64, p],
     "polus_fill_f32": [p, f32, i64, p],
     "polus_binary_f32": [i32, p, p, i64, i64, p, p],
@@ -121,9 +121,11 @@ _SIGS = {
     "polus_scale_by_clip": [p, i64, p, f32, p],
     "polus_comm_unique_id": [p],
     "polus_comm_init": [i32, i32, p],
+    "polus_comm_init_cfg": [i32, i32, p, i32],
     "polus_comm_size": [],
     "polus_comm_rank": [],
     "polus_comm_allreduce_f32": [p, i64, p],
+    "polus_comm_allreduce_bf16": [p, p, i64, p],
     "polus_comm_broadcast": [p, sz, i32, p],
     "polus_comm_allgather": [p, p, sz, p],
     "polus_comm_destroy": [],

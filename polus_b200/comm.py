@@ -7,12 +7,15 @@ One process per GPU (polus/__init__.py:122).  Device collectives are NCCL over N
 libpolus_b200.so on a dedicated high-priority stream; the gradient allreduce runs bucket by bucket
 *while backward is still producing earlier layers' gradients* (reference: Horovod's background
 fusion thread, polus/training.py:182-185).  The host-side rendezvous (sharing the NCCL unique id,
-pickled-object gathers for validation) rides on torch.distributed's gloo store when the process was
-started by torchrun, or on a shared directory (POLUS_RENDEZVOUS_DIR) otherwise -- plumbing only.
+pickled-object gathers) is a small socket store from the standard library keyed on MASTER_ADDR / MASTER_PORT
+(whatever launcher exported RANK / WORLD_SIZE / MASTER_*; torchrun does), or a shared directory
+(POLUS_RENDEZVOUS_DIR).  No torch anywhere on this path.
 """
 import ctypes as C
 import os
 import pickle
+import socket
+import struct
 import time
 
 import numpy as np
@@ -20,10 +23,30 @@ import numpy as np
 from . import _lib, device
 from .tensor import Param
 
-_state = {"initialised": False, "rank": 0, "local_rank": 0, "size": 1, "nccl": False, "gloo": False,
+_state = {"initialised": False, "rank": 0, "local_rank": 0, "size": 1, "nccl": False, "store": None,
           "comm_stream": None, "seq": 0}
 
 BUCKET_BYTES = int(os.environ.get("POLUS_BUCKET_MB", "64")) * 1024 * 1024
+# wire format of the gradient exchange: "f32" = Horovod's default (no compression, polus/training.py:182 passes none);
+# "bf16" = half the NVLink bytes, one bf16 rounding per partial sum (like hvd.Compression.fp16); POLUS_GRAD_WIRE selects
+WIRE_DTYPE = os.environ.get("POLUS_GRAD_WIRE", "f32")
+assert WIRE_DTYPE in ("f32", "bf16"), "POLUS_GRAD_WIRE must be f32 or bf16"
+_wire_scratch = {}   # id(chunk) -> device.Buffer (bf16, chunk capacity)
+
+
+def wire_bytes_per_element():
+    return 2 if WIRE_DTYPE == "bf16" else 4
+
+
+def allreduce_bucket(ch, off, n, stream):
+    """Sum-allreduce n gradient elements of arena chunk `ch` starting at element `off`, in place."""
+    if WIRE_DTYPE == "bf16":
+        buf = _wire_scratch.get(id(ch))
+        if buf is None:
+            buf = _wire_scratch[id(ch)] = device.Buffer(ch.capacity * 2)
+        _lib.call("polus_comm_allreduce_bf16", ch.g.ptr + off * 4, buf.ptr + off * 2, n, stream)
+    else:
+        _lib.call("polus_comm_allreduce_f32", ch.g.ptr + off * 4, n, stream)
 
 
 def _env_int(name, default):
@@ -50,7 +73,7 @@ def init(use_device=True):
         if rank == 0:
             _lib.call("polus_comm_unique_id", uid.ctypes.data)
         uid = np.frombuffer(_host_broadcast(uid.tobytes(), 0), np.uint8).copy()
-        _lib.call("polus_comm_init", rank, size, uid.ctypes.data)
+        _lib.call("polus_comm_init_cfg", rank, size, uid.ctypes.data, _env_int("POLUS_NCCL_MAX_CTAS", 0))
         s = C.c_void_p()
         _lib.call("polus_stream_create", C.byref(s), 1)
         _state["comm_stream"] = s.value
@@ -74,20 +97,123 @@ def shutdown():
     if _state["nccl"]:
         _lib.call("polus_comm_destroy")
         _state["nccl"] = False
+    st = _state.get("store")
+    if st is not None:
+        for c in (st if isinstance(st, list) else [st]):
+            try:
+                c.close()
+            except OSError:
+                pass
+        _state["store"] = None
 
 
 # ------------------------------------------------------------------------------------------------
-# host-side rendezvous (pickled objects, a few hundred bytes)
+# host-side rendezvous (pickled objects, a few hundred bytes) -- python standard library only
 # ------------------------------------------------------------------------------------------------
+# The launcher (torchrun, or anything that exports RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT) tells every rank
+# where rank 0 is (see _store_endpoint).  Rank 0 binds and accepts one connection per peer during init(); afterwards every
+# host collective is one synchronous round on those sockets -- each rank sends its frame to rank 0, rank 0 answers
+# with all frames in rank order -- served inside rank 0's own call (every rank makes the same sequence of calls, as with
+# Horovod), so there is no background thread.
+_STORE_TIMEOUT = float(os.environ.get("POLUS_STORE_TIMEOUT", "600"))
+
+
+def _send_frame(sock, payload):
+    sock.sendall(struct.pack("<Q", len(payload)) + payload)
+
+
+def _recv_exact(sock, n):
+    buf = bytearray()
+    while len(buf) < n:
+        chunk = sock.recv(min(n - len(buf), 1 << 20))
+        if not chunk:
+            raise ConnectionError("polus store: peer closed the connection (another rank died?)")
+        buf += chunk
+    return bytes(buf)
+
+
+def _recv_frame(sock):
+    (n,) = struct.unpack("<Q", _recv_exact(sock, 8))
+    return _recv_exact(sock, n)
+
+
+def _store_endpoint():
+    """(family, address) of rank 0's store.  One node (MASTER_ADDR is loopback -- the 8 GPUs of one box): an abstract
+    Unix socket named after MASTER_PORT, which cannot collide with the launcher's own TCP store on that port or with
+    any other listener.  Several nodes: TCP on POLUS_STORE_PORT, default MASTER_PORT + 1."""
+    addr = os.environ.get("MASTER_ADDR", "127.0.0.1")
+    port = _env_int("MASTER_PORT", 29500)
+    kind = os.environ.get("POLUS_STORE", "unix" if addr in ("127.0.0.1", "localhost", "::1") else "tcp")
+    if kind == "unix":
+        return socket.AF_UNIX, "\0polus-store-%d-%s" % (port, os.environ.get("TORCHELASTIC_RUN_ID", ""))
+    return socket.AF_INET, (addr, _env_int("POLUS_STORE_PORT", 0) or port + 1)
+
+
 def _host_rendezvous_init():
     if os.environ.get("POLUS_RENDEZVOUS_DIR"):
         os.makedirs(os.environ["POLUS_RENDEZVOUS_DIR"], exist_ok=True)
         return
-    import torch.distributed as dist  # plumbing: store + gloo object collectives
-    if not dist.is_initialized():
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group(backend="gloo", rank=_state["rank"], world_size=_state["size"])
-    _state["gloo"] = True
+    family, where = _store_endpoint()
+    rank, size = _state["rank"], _state["size"]
+    tcp = family == socket.AF_INET
+    if rank == 0:
+        srv = socket.socket(family, socket.SOCK_STREAM)
+        if tcp:
+            srv.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+        try:
+            srv.bind(("", where[1]) if tcp else where)
+        except OSError as e:
+            raise RuntimeError(f"polus store: rank 0 cannot listen on {where!r} ({e}); set POLUS_STORE_PORT / POLUS_STORE") from e
+        srv.listen(size)
+        srv.settimeout(_STORE_TIMEOUT)
+        peers = {}
+        while len(peers) < size - 1:
+            try:
+                c, _ = srv.accept()
+            except socket.timeout:
+                raise TimeoutError(f"polus store: only {len(peers) + 1} of {size} ranks arrived within {_STORE_TIMEOUT:.0f} s")
+            c.settimeout(_STORE_TIMEOUT)
+            (r,) = struct.unpack("<I", _recv_exact(c, 4))
+            peers[r] = c
+        srv.close()
+        _state["store"] = [peers[r] for r in range(1, size)]
+    else:
+        t0 = time.time()
+        while True:
+            c = socket.socket(family, socket.SOCK_STREAM)
+            try:
+                c.connect(where)
+                break
+            except OSError:
+                c.close()
+                if time.time() - t0 > _STORE_TIMEOUT:
+                    raise TimeoutError(f"polus store: rank {rank} could not reach rank 0 at {where!r}")
+                time.sleep(0.05)
+        c.settimeout(_STORE_TIMEOUT)
+        c.sendall(struct.pack("<I", rank))
+        _state["store"] = c
+    if tcp:
+        for c in (_state["store"] if rank == 0 else [_state["store"]]):
+            c.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
+
+
+def _store_allgather(payload):
+    if _state["rank"] == 0:
+        frames = [payload] + [_recv_frame(c) for c in _state["store"]]
+        blob = struct.pack("<I", len(frames)) + b"".join(struct.pack("<Q", len(f)) + f for f in frames)
+        for c in _state["store"]:
+            _send_frame(c, blob)
+        return frames
+    c = _state["store"]
+    _send_frame(c, payload)
+    blob = _recv_frame(c)
+    (n,) = struct.unpack_from("<I", blob, 0)
+    out, pos = [], 4
+    for _ in range(n):
+        (m,) = struct.unpack_from("<Q", blob, pos)
+        out.append(blob[pos + 8:pos + 8 + m])
+        pos += 8 + m
+    return out
 
 
 def _file_allgather(payload):
@@ -114,11 +240,8 @@ def _file_allgather(payload):
 def _host_allgather(payload: bytes):
     if _state["size"] == 1:
         return [payload]
-    if _state["gloo"]:
-        import torch.distributed as dist
-        out = [None] * _state["size"]
-        dist.all_gather_object(out, payload)
-        return out
+    if _state.get("store") is not None:
+        return _store_allgather(payload)
     return _file_allgather(payload)
 
 
@@ -171,6 +294,10 @@ def broadcast_variables(variables, root_rank=0):
 def plan_buckets(weights, bucket_bytes=None):
     """Group the gradient arena spans of `weights` into contiguous buckets of ~bucket_bytes, ordered
     from the END of the arena (the last-created variables get their gradients first in backward).
+    A variable of at least bucket_bytes / 2 (the word-embedding table: 94 MB fp32 in BERT-base, whose gradient backward
+    produces LAST) is never merged with its neighbours: it closes the running bucket and is cut into its own
+    ~bucket_bytes / 2 pieces, so that the variables before it are exchanged as soon as THEY are ready and the tail of
+    the step pipelines allreduce(piece i+1) with the optimizer update of piece i instead of one long exposed exchange.
     Returns [(chunk, offset_elems, n_elems, [params])...]."""
     bucket_bytes = bucket_bytes or BUCKET_BYTES
     ps = sorted((w for w in {id(w): w for w in weights if isinstance(w, Param)}.values()),
@@ -179,6 +306,19 @@ def plan_buckets(weights, bucket_bytes=None):
     cur = None
     for w in ps:
         n = (w.size + 63) & ~63
+        if n * 4 >= bucket_bytes // 2:
+            cur = None
+            piece = max(64, ((bucket_bytes // 8) + 63) & ~63)          # elements per piece (bucket_bytes / 2 bytes)
+            pieces = []
+            pos = 0
+            while pos < n:
+                m = min(piece, n - pos)
+                if n - pos - m < piece // 4:                           # no tiny last piece
+                    m = n - pos
+                pieces.append({"chunk": w.chunk, "off": w.offset + pos, "n": m, "params": [w]})
+                pos += m
+            buckets.extend(reversed(pieces))
+            continue
         if cur is not None and cur["chunk"] is w.chunk and w.offset + n == cur["off"] and cur["n"] * 4 < bucket_bytes:
             cur["off"] = w.offset
             cur["n"] += n
@@ -208,7 +348,7 @@ class _DistributedTape:
             _lib.call("polus_event_record", ev, main)
             _lib.call("polus_stream_wait_event", comm_stream, ev)
             ops.side_join(comm_stream)  # weight gradients of this bucket issued on the background stream
-            _lib.call("polus_comm_allreduce_f32", ch.g.ptr + off * 4, n, comm_stream)
+            allreduce_bucket(ch, off, n, comm_stream)
             events.append(ev)
             if on_bucket_ready is not None:
                 on_bucket_ready(ch, off, n, after=comm_stream)  # the update waits for the reduced bucket only

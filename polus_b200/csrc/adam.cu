@@ -24,7 +24,10 @@ __device__ __forceinline__ float schedule_lr(const polus_adam_cfg_t& c, uint32_t
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
             bf16* __restrict__ pb, const uint8_t* __restrict__ decay_mask, long long n, polus_adam_cfg_t c,
-            const uint32_t* __restrict__ d_step) {
+            const float* __restrict__ d_hyper, const uint32_t* __restrict__ d_step) {
+    // {lr, grad_scale, weight_decay, end_lr} live in device memory when the caller passes d_hyper: a captured graph
+    // then follows optimizer.learning_rate.assign() (polus/training.py:90-94) without being re-captured
+    if (d_hyper != nullptr) { c.lr = d_hyper[0]; c.grad_scale = d_hyper[1]; c.weight_decay = d_hyper[2]; c.end_lr = d_hyper[3]; }
     const uint32_t it = *d_step;
     const float t = (float)(it + 1);
     const float lr = schedule_lr(c, it);
@@ -73,14 +76,15 @@ __global__ void step_inc_kernel(uint32_t* d_step) { *d_step += 1; }
 }  // namespace
 
 extern "C" int polus_adam(float* p, float* g, float* m, float* v, polus_bf16_t* pb, const uint8_t* decay_mask,
-                          int64_t n, const polus_adam_cfg_t* cfg, uint32_t* d_step, int increment_step, void* stream) {
+                          int64_t n, const polus_adam_cfg_t* cfg, const float* d_hyper, uint32_t* d_step, int increment_step,
+                          void* stream) {
     POLUS_REQUIRE(cfg != nullptr && d_step != nullptr, "polus_adam: cfg and d_step required");
     POLUS_REQUIRE(((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) % 16 == 0, "polus_adam: arenas must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     if (n > 0) {
         long long blocks = ((n >> 2) + 255) / 256;
         long long cap = (long long)polus_num_sms() * 8;
-        adam_kernel<<<(int)(blocks < 1 ? 1 : (blocks < cap ? blocks : cap)), 256, 0, st>>>(p, g, m, v, (bf16*)pb, decay_mask, n, *cfg, d_step);
+        adam_kernel<<<(int)(blocks < 1 ? 1 : (blocks < cap ? blocks : cap)), 256, 0, st>>>(p, g, m, v, (bf16*)pb, decay_mask, n, *cfg, d_hyper, d_step);
         g_launch_count++;
         POLUS_LAUNCH_CHECK();
     }

@@ -79,3 +79,22 @@ def pairwise_softplus_loss(y_unused, scores):
     pos = ops.slice_rows(s0, 0, half)
     neg = ops.slice_rows(s0, half, half)
     return ops.reduce_mean(ops.unary("softplus", ops.sub(neg, pos)))
+
+
+def explicit_negative_scores(q, d_pos, *d_negs):
+    """compute_scores for k explicit negatives per query (polus/ir/training.py:94-107 hands compute_scores the
+    projected query, positive and the k negative representations): pos [B], neg = list of k [B] dot products."""
+    q = ops.cast(q, F32)
+    pos = ops.reduce_sum(ops.mul(q, ops.cast(d_pos, F32)), axis=-1)
+    negs = [ops.reduce_sum(ops.mul(q, ops.cast(n, F32)), axis=-1) for n in d_negs]
+    return pos, negs
+
+
+def pairwise_softplus_ranking_loss(pos_scores, neg_scores):
+    """mean over the batch and the k negatives of softplus(s_neg - s_pos)."""
+    negs = neg_scores if isinstance(neg_scores, (list, tuple)) else [neg_scores]
+    total = None
+    for n in negs:
+        term = ops.reduce_mean(ops.unary("softplus", ops.sub(n, pos_scores)))
+        total = term if total is None else ops.add(total, term)
+    return ops.unary("scale", total, 1.0 / len(negs))

@@ -2,6 +2,7 @@
 in-batch or k explicit negatives.  The frozen encoders run without recording gradients
 (`forward_without_grads`), the projections + user `compute_scores` + user loss are differentiated."""
 from .. import nn, ops
+from ..tensor import I32
 from ..training import BaseTrainer
 
 
@@ -20,11 +21,14 @@ class EfficientDenseRetrievalTrainer(BaseTrainer):
         d = self.model.encode_document(positive_doc, training=True)
         if negative_doc is None:
             return q, d
-        ids, mask = nn.as_tensor(negative_doc["input_ids"]), nn.as_tensor(negative_doc["attention_mask"])
+        ids, mask = nn.as_tensor(negative_doc["input_ids"], I32), nn.as_tensor(negative_doc["attention_mask"], I32)
         B, k, S = ids.shape
         self.k_negatives = k
-        ids_h, mask_h = ids.numpy(), mask.numpy()  # [B,k,S] -> k x [B,S]; host slicing of int ids, before capture only
-        negs = [self.model.encode_document({"input_ids": ids_h[:, i, :], "attention_mask": mask_h[:, i, :]}, training=True)
+        # negative_docs[...][:, i, :] (ir/training.py:64) on the device: rows i, i+k, i+2k ... of the [B*k, S] view --
+        # no host round trip, so the slicing is part of the captured step and follows every new batch
+        ids2, mask2 = ids.view((B * k, S)), mask.view((B * k, S))
+        negs = [self.model.encode_document({"input_ids": ops.gather_rows(ids2, i, k, B),
+                                            "attention_mask": ops.gather_rows(mask2, i, k, B)}, training=True)
                 for i in range(k)]
         return (q, d, negs)
 

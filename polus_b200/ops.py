@@ -144,7 +144,9 @@ def run_backward(nodes, loss, before_node=None):
     allreduces as soon as backward has passed the variables of a bucket.  Contributions to the same tensor
     are kept as a list and summed lazily: a node whose backward carries `pair_ok` (LayerNorm backward)
     consumes two contributions directly, fusing the residual-stream addition into its own pass."""
-    grads = {id(loss): ones_like(loss)}
+    root = ones_like(loss)
+    root.is_one = True
+    grads = {id(loss): root}
     for idx in range(len(nodes) - 1, -1, -1):
         if before_node is not None:
             before_node(idx)
@@ -749,16 +751,29 @@ def crf_nll_loss(emissions, tags, transitions, lens=None, sample_weights=None):
     gemis = Tensor(emissions.shape, F32)
     tape = _recording(emissions, transitions)
     is_param = isinstance(transitions, Param)
-    gtrans = transitions.grad if is_param else Tensor(transitions.shape, F32, zero=True)
+    gtrans = Tensor(transitions.shape, F32, zero=True) if tape is not None else None  # the kernel accumulates into it
     _lib.call("polus_crf_nll", emissions.ptr, tags.ptr, lens.ptr if lens is not None else None, transitions.ptr,
               sample_weights.ptr if sample_weights is not None else None, Bsz, T, K, nll.ptr, loss.ptr, gemis.ptr,
               gtrans.ptr if tape is not None else None, device.stream())
     if tape is not None:
         def backward(g):
-            # loss is the root of the tape in polus (training.py:180-185): g == 1
-            return [gemis, None if is_param else gtrans]
+            # The kernel produced d loss / d(emissions, transitions) with the forward pass.  In polus the loss is the
+            # root of the tape (training.py:180-185, g == 1); a user loss that scales or combines it (0.5*crf + aux)
+            # arrives here with its own upstream gradient, applied as a scalar broadcast.
+            ge, gt = (gemis, gtrans) if g.is_one else (_scale_by(gemis, g), _scale_by(gtrans, g))
+            if is_param:  # accumulated in BACKWARD: evaluating the loss twice, or only in forward, leaves .grad alone
+                _lib.call("polus_binary_f32", 0, transitions.grad.ptr, gt.ptr, gt.size, gt.size, transitions.grad.ptr,
+                          device.stream())
+            return [ge, None if is_param else gt]
         _record(tape, [emissions, transitions], loss, backward)
     return loss
+
+
+def _scale_by(x, g):
+    """x * g for a scalar upstream gradient g (device tensor), no tape."""
+    out = Tensor(x.shape, F32)
+    _lib.call("polus_binary_f32", 2, x.ptr, cast(g, F32).ptr, x.size, 1, out.ptr, device.stream())
+    return out
 
 
 def crf_decode(emissions, transitions, lens=None):
@@ -781,7 +796,7 @@ def cross_entropy(kind, logits, labels, class_weights=None, negative_weight=0.0)
               float(negative_weight), rows, Cn, loss.ptr, glog.ptr, device.stream())
     tape = _recording(logits)
     if tape is not None:
-        _record(tape, [logits], loss, lambda g: [glog])
+        _record(tape, [logits], loss, lambda g: [glog if g.is_one else _scale_by(glog, g)])
     return loss
 
 
@@ -935,3 +950,18 @@ def constant_arange(n):
     if t is None:
         t = _const_cache[("arange", n)] = Tensor.from_numpy(np.arange(n, dtype=np.int32), I32)
     return t
+
+
+def clip_by_global_norm(grads, clip_norm):
+    """tf.clip_by_global_norm for a post_process_grads hook (polus/training.py:187-189): every gradient is scaled by
+    clip_norm / max(global_norm, clip_norm), in place, with no host round trip (usable inside the captured step).
+    Returns (grads, global_norm_squared device scalar)."""
+    sumsq = Tensor((1,), F32, zero=True)
+    st = device.stream()
+    live = [g for g in grads if g is not None]
+    for g in live:
+        assert g.dtype == F32, "clip_by_global_norm works on the fp32 gradient arena views"
+        _lib.call("polus_sumsq_f32", g.ptr, g.size, sumsq.ptr, st)
+    for g in live:
+        _lib.call("polus_scale_by_clip", g.ptr, g.size, sumsq.ptr, float(clip_norm), st)
+    return grads, sumsq

@@ -61,6 +61,8 @@ class WarmUp:
 
     def assign(self, v):
         self.initial_learning_rate = float(v)
+        if getattr(self, "_on_change", None):
+            self._on_change()
 
 
 class Adam:
@@ -68,6 +70,9 @@ class Adam:
 
     def __init__(self, learning_rate=0.001, beta_1=0.9, beta_2=0.999, epsilon=1e-7, weight_decay_rate=0.0, name="Adam",
                  **kwargs):
+        self._hyper = None          # device float[4] {lr, grad_scale, weight_decay, end_lr}: read by the kernel, so a
+        self._hyper_host = None     # captured graph follows learning_rate.assign() / grad_scale changes (no re-capture)
+        self._hyper_dirty = True
         self.learning_rate = learning_rate if isinstance(learning_rate, WarmUp) else Variable(learning_rate)
         self.beta_1, self.beta_2, self.epsilon = float(beta_1), float(beta_2), float(epsilon)
         self.weight_decay_rate = float(weight_decay_rate)
@@ -81,6 +86,55 @@ class Adam:
     @property
     def lr(self):
         return self.learning_rate
+
+    # ---- hyper-parameters a user may change between steps (polus/training.py:90-94 assigns learning_rate; LR-changing
+    # callbacks; reuse of one optimizer across HPO trials): attribute writes mark the device copy stale
+    def _touch(self):
+        self._hyper_dirty = True
+
+    @property
+    def learning_rate(self):
+        return self._learning_rate
+
+    @learning_rate.setter
+    def learning_rate(self, value):
+        if not isinstance(value, (WarmUp, Variable)):
+            value = Variable(value)
+        value._on_change = self._touch
+        self._learning_rate = value
+        self._hyper_dirty = True
+
+    @property
+    def grad_scale(self):
+        return self._grad_scale
+
+    @grad_scale.setter
+    def grad_scale(self, value):
+        self._grad_scale = float(value)
+        self._hyper_dirty = True
+
+    @property
+    def weight_decay_rate(self):
+        return self._weight_decay_rate
+
+    @weight_decay_rate.setter
+    def weight_decay_rate(self, value):
+        self._weight_decay_rate = float(value)
+        self._hyper_dirty = True
+
+    def sync_hyper(self):
+        """Make the device copy of {lr, grad_scale, weight_decay, end_lr} current.  Called by the trainer before every
+        step (eager or graph replay) and by _launch; a no-op unless something was assigned since the last call."""
+        if self._hyper is None:
+            self._hyper = device.Buffer(16, zero=True)
+            self._hyper_dirty = True
+        if self._hyper_dirty:
+            lr = self._learning_rate
+            vals = np.array([lr.initial_learning_rate if isinstance(lr, WarmUp) else float(lr), self._grad_scale,
+                             self._weight_decay_rate, lr.end_learning_rate if isinstance(lr, WarmUp) else 0.0], np.float32)
+            device.upload(self._hyper.ptr, vals)   # stream-ordered on the compute stream, then synchronised
+            self._hyper_dirty = False
+        return self._hyper.ptr
 
     @property
     def iterations(self):
@@ -136,9 +190,12 @@ class Adam:
     def _launch(self, ch, off, n, increment, stream):
         cfg = self._cfg()
         m, v, dm, _ = self._chunk_state(ch)
+        from .tensor import _pool
+        if self._hyper is None or (self._hyper_dirty and _pool.trace is None):
+            self.sync_hyper()   # never inside a capture: the trainer refreshes it before every step
         _lib.call("polus_adam", ch.p.ptr + off * 4, ch.g.ptr + off * 4, m.ptr + off * 4, v.ptr + off * 4,
-                  ch.pb.ptr + off * 2, (dm.ptr + off) if dm is not None else None, n, C.byref(cfg), ops.step_counter(),
-                  1 if increment else 0, stream)
+                  ch.pb.ptr + off * 2, (dm.ptr + off) if dm is not None else None, n, C.byref(cfg), self._hyper.ptr,
+                  ops.step_counter(), 1 if increment else 0, stream)
 
     def apply_span_early(self, ch, off, n, after=None):
         """Update one contiguous arena span while backward is still running (its gradients are final and, with `after`
@@ -153,7 +210,17 @@ class Adam:
         return True
 
     def apply_gradients(self, grads_and_vars):
-        weights = [w for g, w in grads_and_vars if g is not None]
+        pairs = [(g, w) for g, w in grads_and_vars if g is not None]
+        weights = [w for _, w in pairs]
+        # The kernel reads the gradient arena.  A post_process_grads hook (polus/training.py:187-189) may hand back NEW
+        # tensors (clipping, scaling through ops.mul ...): those values are what must be applied, so they are copied
+        # over the arena slot first.  Tensors that are the arena views themselves (the default) cost nothing.
+        for g, w in pairs:
+            if isinstance(w, Param) and isinstance(g, Tensor) and g.ptr != w.grad.ptr:
+                if g.size != w.size:
+                    raise ValueError(f"gradient of {w.name} has shape {g.shape}, variable has {w.shape}")
+                g32 = ops.cast(g, F32)
+                _lib.call("polus_memcpy_d2d", w.grad.ptr, g32.ptr, w.grad.nbytes, device.stream())
         key = tuple(id(w) for w in weights)
         if key != self._ranges_key:
             self._ranges_key, self._ranges = key, self._contiguous_ranges(weights)

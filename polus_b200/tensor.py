@@ -95,7 +95,7 @@ def end_trace():
 
 class Tensor:
     __slots__ = ("ptr", "shape", "dtype", "block", "requires_grad", "node", "name", "consumers", "bwd_fuse", "fused_for",
-                 "__weakref__")
+                 "is_one", "__weakref__")
 
     def __init__(self, shape, dtype, ptr=None, block=None, zero=False):
         self.shape = tuple(int(s) for s in shape)
@@ -106,6 +106,7 @@ class Tensor:
         self.consumers = 0     # tape nodes that read this tensor (ops._record)
         self.bwd_fuse = None   # (act' tensor, bias-grad tensor): the consumer's dgrad GEMM may apply them in its epilogue
         self.fused_for = None  # id() of the activation output whose backward this gradient already includes
+        self.is_one = False    # the tape's root gradient (d loss / d loss == 1): loss ops skip the multiply
         if ptr is None:
             block = Block(max(self.nbytes, 16))
             ptr = block.ptr

@@ -10,6 +10,7 @@ The returned loss is a lazy handle: it syncs only when a callback formats or doe
 """
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -21,7 +22,7 @@ from .tensor import BF16, F32, I32, Tensor
 class LazyLoss:
     """Scalar loss of one step, living in a pinned host slot filled by an async D2H copy."""
 
-    __slots__ = ("_slot", "_event", "_value")
+    __slots__ = ("_slot", "_event", "_value", "__weakref__")
 
     def __init__(self, slot_array, event):
         self._slot, self._event, self._value = slot_array, event, None
@@ -222,6 +223,17 @@ class _CompiledStep:
     def launch(self):
         _lib.call("polus_graph_launch", self.graph, device.stream())
 
+    def release(self):
+        """Destroy the graph and hand its activation blocks back to the pool (they were pinned to this trace)."""
+        device.device_sync()
+        if self.graph is not None:
+            _lib.call("polus_graph_destroy", self.graph)
+            self.graph = None
+        for b in self.blocks or []:
+            b.pinned = False
+        self.blocks = None
+        self.loss = None
+
 
 class BaseTrainer:
     """Abstraction of a gradient-descent training procedure (reference training.py:14-338)."""
@@ -305,19 +317,29 @@ class BaseTrainer:
         if self._loss_ring is None:
             self._loss_ring = device.PinnedArray((_LOSS_RING, 4), np.float32)
             self._loss_events = []
+            self._loss_owner = [None] * _LOSS_RING   # weakref to the LazyLoss currently reading each slot
             for _ in range(_LOSS_RING):
                 ev = C.c_void_p()
                 _lib.call("polus_event_create", C.byref(ev))
                 self._loss_events.append(ev.value)
         i = self._ring_pos
         self._ring_pos = (i + 1) % _LOSS_RING
+        # a handle from _LOSS_RING steps ago that some callback still holds unread (EarlyStop / ConsoleLogCallback keep
+        # them until the epoch ends) takes its value now, before its slot and event are reused
+        prev = self._loss_owner[i]() if self._loss_owner[i] is not None else None
+        if prev is not None:
+            prev._get()
         st = device.stream()
         _lib.call("polus_memcpy_d2h", self._loss_ring.ptr + i * 16, loss_tensor.ptr, 4, st)
         _lib.call("polus_event_record", self._loss_events[i], st)
-        return LazyLoss(self._loss_ring.array[i], self._loss_events[i])
+        out = LazyLoss(self._loss_ring.array[i], self._loss_events[i])
+        self._loss_owner[i] = weakref.ref(out)
+        return out
 
     def train_step(self, *inputs):
         """One optimisation step on one batch; returns the (lazy) scalar loss of that batch."""
+        if hasattr(self.optimizer, "sync_hyper"):
+            self.optimizer.sync_hyper()   # lr / grad_scale assigned since the last step reach the device before this one
         struct, leaves = _flatten_inputs(inputs)
         key = (repr(struct), tuple((tuple(x.shape) if isinstance(x, Tensor) else np.asarray(x).shape, _leaf_dtype(x))
                                    for x in leaves))
@@ -343,6 +365,13 @@ class BaseTrainer:
         step.launch()
         self.last_h2d_bytes = step.h2d_bytes
         return self._lazy_loss(step.loss)
+
+    def release_graphs(self):
+        """Forget every captured step (new shapes re-capture): frees the activation memory pinned to those graphs."""
+        for step in self._compiled.values():
+            step.release()
+        self._compiled = {}
+        self._warm = set()
 
     def lr_finder(self, tf_dataset, use_lr_found=False):
         pass

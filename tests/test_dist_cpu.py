@@ -1,4 +1,4 @@
-"""N>1 host path on CPU: two processes over gloo (world_size 2).  Covers rendezvous, hvd-shaped
+"""N>1 host path on CPU: two processes (world_size 2) over the package's own socket store (no torch).  Covers rendezvous, hvd-shaped
 allgather_object, dataset sharding across ranks, learning-rate scaling and rank-0-only callbacks.
 Device collectives (NCCL) are exercised on the GPU box by bench.py --gpus N."""
 import os
@@ -6,6 +6,8 @@ import socket
 import subprocess
 import sys
 import textwrap
+
+import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -34,6 +36,8 @@ WORKER = textwrap.dedent("""
         @runs_if_root
         def f(self): return "ran"
     comm.barrier()
+    assert "torch" not in sys.modules, "the product path must not import torch (north_star)"
+    comm.shutdown()
     print(json.dumps({"rank": h.rank(), "gathered": gathered, "mine": mine, "lr": opt.learning_rate.read_value(),
                       "grad_scale": opt.grad_scale, "root_only": C().f()}))
 """) % ROOT
@@ -47,13 +51,15 @@ def _free_port():
     return p
 
 
-def test_two_rank_host_path_over_gloo():
+@pytest.mark.parametrize("store", ["unix", "tcp"])
+def test_two_rank_host_path_over_socket_store(store):
     import json
-    port = _free_port()
+    port, store_port = _free_port(), _free_port()
     procs = []
     for r in range(2):
         env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1",
-                   MASTER_PORT=str(port), POLUS_COMM_HOST_ONLY="1", POLUS_LOGGER_LEVEL="ERROR")
+                   MASTER_PORT=str(port), POLUS_COMM_HOST_ONLY="1", POLUS_LOGGER_LEVEL="ERROR", POLUS_STORE=store,
+                   POLUS_STORE_PORT=str(store_port))
         procs.append(subprocess.Popen([sys.executable, "-c", WORKER], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
     outs = []
     for p in procs:
@@ -69,7 +75,7 @@ def test_two_rank_host_path_over_gloo():
 
 
 def test_file_rendezvous_fallback(tmp_path):
-    """Same gather without torch.distributed: POLUS_RENDEZVOUS_DIR shared directory."""
+    """Same gather over a shared directory (POLUS_RENDEZVOUS_DIR), for launchers that export no MASTER_ADDR."""
     code = textwrap.dedent("""
         import os, sys, json
         sys.path.insert(0, %r)

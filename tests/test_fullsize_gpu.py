@@ -1,0 +1,160 @@
+"""Full-size parity (north_star: "logits, loss and gradients after N steps must agree within a stated bf16/fp32
+tolerance"): the 12-layer BERT-base NER+CRF model of BASELINE.json configs[1] on the device (bf16 GEMM operands, fp32
+accumulation and statistics) against oracle/torch_ref.py -- HuggingFace's own BertEmbeddings / BertLayer in fp32 with
+torch autograd -- loaded with the SAME weights, on the same ragged batch, B=2, S=256, dropout 0.
+
+Bars (BASELINE.md §3, bf16 path): emissions atol/rtol 2e-2; loss rel 1e-2; per-tensor gradient cosine >= 0.999; loss
+trajectory over 3 Keras-Adam steps rel 1e-2."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _build_pair(seed, B, S, L=12, H=768, nh=12, I=3072, vocab=30522):
+    import torch
+    from oracle import torch_ref
+    from polus_b200 import ops, tensor
+    from polus_b200.models import BertConfig
+    from polus_b200.ner.models import BertNERModel
+    from polus_b200.pretrained import export_hf_bert_weights
+    from polus_b200.utils import set_random_seed
+    from tests.parity import make_batch, round_weights_to_bf16
+    tensor.reset_arena()
+    set_random_seed(seed)
+    ops.set_step(0)
+    cfg = BertConfig(vocab_size=vocab, hidden_size=H, num_hidden_layers=L, num_attention_heads=nh, intermediate_size=I,
+                     hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    model = BertNERModel(cfg, output_classes=4, hidden_space=128, droupout_p=0.0)
+    rng = np.random.default_rng(seed)
+    ids, mask, tt, tags = make_batch(rng, B, S, vocab, 4)
+    tt = ((np.arange(S)[None] >= S // 3) & (mask > 0)).astype(np.int32)   # both token types in play
+    x = {"input_ids": ids, "attention_mask": mask, "token_type_ids": tt}
+    model(**x, training=False)                                            # builds the lazily created head / CRF variables
+    for w in model.weights:                                               # non-trivial LayerNorm / bias values
+        if w.name.endswith("gamma"):
+            w.assign(1.0 + 0.1 * rng.standard_normal(w.shape))
+        elif w.name.endswith(("beta", "bias")):
+            w.assign(0.02 * rng.standard_normal(w.shape))
+    round_weights_to_bf16(model)   # both sides start from identical, bf16-representable values
+    torch.manual_seed(0)
+    net = torch_ref.build(hidden=H, layers=L, heads=nh, inter=I, vocab=vocab, max_pos=cfg.max_position_embeddings, K=4,
+                          head_hidden=128, dropout=0.0)
+    head = {"Wa": model.hidden.kernel.numpy(), "ba": model.hidden.bias.numpy(), "Wb": model.out.kernel.numpy(),
+            "bb": model.out.bias.numpy(), "trans": model.crf.transitions.numpy()}
+    torch_ref.load_weights(net, export_hf_bert_weights(model.bert), head)
+    net.train()
+    tb = tuple(torch.from_numpy(a.astype(np.int64)) for a in (ids, mask, tt, tags))
+    return model, net, x, tags, tb
+
+
+def test_full_bert_base_matches_fp32_torch_reference():
+    import torch
+    from oracle import ner_model as O, torch_ref
+    from polus_b200 import ops
+    from polus_b200.optimizers import Adam
+    from polus_b200.training import ClassifierTrainer
+    from tests.parity import device_grads
+    B, S = 2, 256
+    model, net, x, tags, tb = _build_pair(21, B, S)
+    y = np.eye(4, dtype=np.float32)[tags]
+    # ---- forward + gradients of one step
+    with ops.GradientTape() as tape:
+        e_dev = model.emissions(**x, training=True)
+        loss_dev_t = model.loss(y, model.crf(e_dev, training=True))
+    tape.gradient(loss_dev_t, model.trainable_weights)
+    loss_dev, e_dev = float(loss_dev_t), e_dev.numpy()
+    g_dev = O.flatten(device_grads(model))
+    from polus_b200 import _lib, device
+    for w in model.weights:
+        _lib.call("polus_memset", w.grad.ptr, 0, w.grad.nbytes, device.stream())
+    ids, mask, tt, tg = tb
+    e_ref = torch_ref.emissions(net, ids, mask, tt).detach().numpy()
+    loss_ref_t = net(ids, mask, tt, tg)
+    loss_ref_t.backward()
+    loss_ref = float(loss_ref_t.detach())
+    g_ref = torch_ref.named_grads(net, 768)
+    np.testing.assert_allclose(e_dev, e_ref, atol=2e-2, rtol=2e-2)
+    assert abs(loss_dev - loss_ref) / abs(loss_ref) < 1e-2, (loss_dev, loss_ref)
+    assert set(g_ref) == set(g_dev)
+    worst = (1.0, None)
+    for k, gr in g_ref.items():
+        gd = g_dev[k]
+        assert gd.shape == gr.shape, k
+        denom = np.linalg.norm(gr) * np.linalg.norm(gd)
+        cos = float((gr * gd).sum() / denom) if denom > 0 else 1.0
+        if cos < worst[0]:
+            worst = (cos, k)
+    assert worst[0] >= 0.999, worst
+    # ---- 3 optimisation steps through the public trainer (eager, captured, replayed) vs Keras Adam on the torch model
+    lr = 1e-4
+    for p in net.parameters():
+        p.grad = None
+    ref_losses = torch_ref.keras_adam_steps(net, tb, 3, lr)
+    trainer = ClassifierTrainer(model, Adam(lr), model.loss)
+    dev_losses = [float(trainer.train_step(x, y)) for _ in range(3)]
+    rel = max(abs(a - b) / abs(b) for a, b in zip(dev_losses, ref_losses))
+    assert rel < 1e-2, (dev_losses, ref_losses)
+    assert ref_losses[-1] < ref_losses[0] and dev_losses[-1] < dev_losses[0]
+
+
+@pytest.mark.parametrize("S,H,nh,I,L", [(64, 128, 2, 512, 2), (256, 768, 12, 3072, 1)])
+def test_model_level_parity_with_dropout_on(S, H, nh, I, L):
+    """Dropout 0.1 through the ASSEMBLED step: the device draws its masks from Philox4x32-10 keyed by (seed, site, step);
+    the oracle regenerates every one of them (oracle/philox.py -- embeddings, attention probabilities, both hidden
+    dropouts of every layer, the head's Dropout) and must reproduce emissions, loss and all gradients.  Checks the site
+    numbering and counters of the whole forward/backward, not just each kernel on its own."""
+    from oracle import ner_model as O, philox
+    from polus_b200 import _lib, device, ops, tensor
+    from polus_b200.models import BertConfig
+    from polus_b200.ner.models import BertNERModel
+    from polus_b200.utils import set_random_seed
+    from tests.parity import device_grads, device_params_to_oracle, make_batch, round_weights_to_bf16
+    p, seed, step, B, vocab, K = 0.1, 1234, 5, 2, 700, 4
+    tensor.reset_arena()
+    set_random_seed(seed)
+    cfg = BertConfig(vocab_size=vocab, hidden_size=H, num_hidden_layers=L, num_attention_heads=nh, intermediate_size=I,
+                     max_position_embeddings=max(S, 64), hidden_dropout_prob=p, attention_probs_dropout_prob=p)
+    model = BertNERModel(cfg, output_classes=K, hidden_space=128, droupout_p=p)
+    rng = np.random.default_rng(seed)
+    ids, mask, tt, tags = make_batch(rng, B, S, vocab, K)
+    x = {"input_ids": ids, "attention_mask": mask, "token_type_ids": tt}
+    y = np.eye(K, dtype=np.float32)[tags]
+    model(**x, training=False)
+    for w in model.weights:
+        if w.name.endswith("gamma"):
+            w.assign(1.0 + 0.1 * rng.standard_normal(w.shape))
+        elif w.name.endswith(("beta", "bias")):
+            w.assign(0.05 * rng.standard_normal(w.shape))
+    round_weights_to_bf16(model)
+    params = device_params_to_oracle(model)
+    ops.set_step(step)
+    ops.reset_dropout_sites()
+    with ops.GradientTape() as tape:
+        e_dev = model.emissions(**x, training=True)
+        loss_t = model.loss(y, model.crf(e_dev, training=True))
+    tape.gradient(loss_t, model.trainable_weights)
+    loss_dev, e_dev = float(loss_t), e_dev.numpy()
+    g_dev = O.flatten(device_grads(model))
+    for w in model.weights:
+        _lib.call("polus_memset", w.grad.ptr, 0, w.grad.nbytes, device.stream())
+    # the same masks, regenerated on the host: sites are numbered in forward order
+    site = [0]
+
+    def m(shape):
+        site[0] += 1
+        return philox.dropout_scale_mask(shape, p, seed, site[0], step).astype(np.float64)
+    masks = {"emb": m((B, S, H))}
+    for li in range(L):
+        masks[("layer", li)] = {"attn": m((B, nh, S, S)), "hidden1": m((B, S, H)), "hidden2": m((B, S, H))}
+    masks["head"] = m((B, S, H))
+    loss_ref, e_ref, g_ref = O.loss_and_grads(params, ids, mask, tt, tags, nh, masks=masks)
+    g_ref = O.flatten(g_ref)
+    np.testing.assert_allclose(e_dev, e_ref, atol=2e-2, rtol=2e-2)
+    assert abs(loss_dev - loss_ref) / abs(loss_ref) < 1e-2, (loss_dev, loss_ref)
+    worst = min(((float((g_ref[k] * g_dev[k]).sum() / (np.linalg.norm(g_ref[k]) * np.linalg.norm(g_dev[k]) + 1e-300)), k)
+                 for k in g_ref), key=lambda t: t[0])
+    assert worst[0] >= 0.999, worst
+    # and the masks matter: the no-dropout oracle must NOT match (guards against a silently disabled dropout)
+    _, e_nodrop, _ = O.loss_and_grads(params, ids, mask, tt, tags, nh)
+    assert np.abs(e_dev - e_nodrop).max() > 4 * np.abs(e_dev - e_ref).max()

@@ -171,6 +171,26 @@ def test_bio_labels_bit_exact_vs_reference_algorithm():
     assert get_bio([(0, 3), (4, 9), (10, 12)], [(4, 12, "Chemical"), (4, 9, "Chemical")]) == ["O", "B-Chemical", "I-Chemical"]
 
 
+def test_bio_labels_bit_exact_vs_reference_fixture():
+    """get_bio and TAG2INT against tests/golden/bio_ref.json, which tests/golden/make_bio_golden.py produced by running
+    the reference's OWN polus/ner/bio.py + elements.py (TF-free, loaded with stubbed packages): label indices bit-exact
+    with the reference itself, not with a restatement."""
+    import json
+    from polus_b200.ner.bio import get_bio
+    from polus_b200.ner.utils import TAG2INT
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bio_ref.json")) as f:
+        doc = json.load(f)
+    assert TAG2INT == doc["tag2int"]
+    assert len(doc["cases"]) >= 400
+    for case in doc["cases"]:
+        spans = [tuple(sp) for sp in case["spans"]]
+        ents = [tuple(e) for e in case["entities"]]
+        assert get_bio(spans, ents) == case["tags"], case
+        # and as label indices, for the Chemical-only cases the reference's TAG2INT covers
+        if all(t in TAG2INT for t in case["tags"]):
+            assert [TAG2INT[t] for t in get_bio(spans, ents)] == [doc["tag2int"][t] for t in case["tags"]]
+
+
 # ------------------------------------------------------------------ callbacks + trainer loop (fake step, no device)
 def test_training_loop_order_and_callbacks(monkeypatch):
     from polus_b200.callbacks import Callback, ConsoleLogCallback, EarlyStop, LossSmoothCallback, TimerCallback
@@ -249,8 +269,17 @@ def test_gradient_bucket_plan():
     assert spans[0][0] + spans[0][1] == off                       # first bucket ends the arena
     for (o1, n1), (o2, n2) in zip(spans, spans[1:]):
         assert o2 + n2 == o1                                       # contiguous, descending
-    assert all(n * 4 < 100000 + 4 * 300032 for _, n in spans)
-    assert [id(p) for b in buckets for p in b[3]] == [id(p) for p in reversed(ps)]
+    # the 300000-element variable (>= bucket_bytes / 2) stands alone, cut into ~bucket_bytes / 2 pieces; nothing is merged
+    # with it, so its neighbours are exchanged as soon as they are ready
+    big = [b for b in buckets if b[3] == [ps[4]]]
+    assert len(big) >= 2 and sum(b[2] for b in big) == 300032 and all(b[2] * 4 <= 100000 for b in big)
+    assert all(n * 4 <= 100000 + 4 * 5056 for _, n in spans)
+    order = []
+    for b in buckets:
+        for p in b[3]:
+            if not order or order[-1] != id(p):
+                order.append(id(p))
+    assert order == [id(p) for p in reversed(ps)]
 
 
 def test_mock_horovod_surface():

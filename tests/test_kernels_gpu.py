@@ -343,7 +343,7 @@ def test_adam_matches_keras_formula(dev, n, schedule, wd):
     for t in range(1, 5):
         g = rng.standard_normal(n).astype(np.float32)
         dev.upload(g_t.ptr, g)
-        call("polus_adam", p.ptr, g_t.ptr, m.ptr, v.ptr, pb.ptr, T(decay, U8).ptr if wd > 0 else None, n, C.byref(cfg), sp, 1, st())
+        call("polus_adam", p.ptr, g_t.ptr, m.ptr, v.ptr, pb.ptr, T(decay, U8).ptr if wd > 0 else None, n, C.byref(cfg), None, sp, 1, st())
         lr = R.warmup_schedule_lr(t - 1, 10, 1e-2, 0.2) if schedule else 1e-2
         if wd > 0:
             pr = np.where(decay == 1, pr - lr * wd * pr, pr)
