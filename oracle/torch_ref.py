@@ -140,27 +140,37 @@ def named_grads(net, H):
     return out
 
 
-def keras_adam_steps(net, batch, steps, lr, beta1=0.9, beta2=0.999, eps=1e-7):
+def keras_adam_steps(net, batch, steps, lr, beta1=0.9, beta2=0.999, eps=1e-7, bf16_compute_weights=False):
     """`steps` optimisation steps with Keras Adam (epsilon outside the bias-corrected sqrt, polus/training.py:191 with
-    tf.keras.optimizers.Adam); returns the per-step losses.  torch.optim.Adam places epsilon differently."""
+    tf.keras.optimizers.Adam); returns the per-step losses.  torch.optim.Adam places epsilon differently.
+
+    bf16_compute_weights: the storage format of the device path -- fp32 MASTER weights that Adam updates, and a
+    bf16-rounded copy of them in every forward / backward (activations and all arithmetic stay fp32 here).  With it
+    the comparison is about the arithmetic; without it, an update far below bf16's resolution (2^-9 relative) moves
+    the fp32 reference but not yet the bf16 operand, and the two trajectories differ for that reason alone."""
     import torch
     ids, mask, tt, tags = batch
     params = [p for p in net.parameters() if p.requires_grad]
     m = [torch.zeros_like(p) for p in params]
     v = [torch.zeros_like(p) for p in params]
+    master = [p.detach().clone() for p in params] if bf16_compute_weights else None
     losses = []
     for t in range(1, steps + 1):
         for p in params:
             p.grad = None
+        if master is not None:
+            with torch.no_grad():
+                for p, w in zip(params, master):
+                    p.copy_(w.to(torch.bfloat16).to(torch.float32))
         loss = net(ids, mask, tt, tags)
         loss.backward()
         losses.append(float(loss.detach()))
         lr_t = lr * (1.0 - beta2 ** t) ** 0.5 / (1.0 - beta1 ** t)
         with torch.no_grad():
-            for p, mi, vi in zip(params, m, v):
+            for i, (p, mi, vi) in enumerate(zip(params, m, v)):
                 if p.grad is None:
                     continue
                 mi.mul_(beta1).add_(p.grad, alpha=1.0 - beta1)
                 vi.mul_(beta2).addcmul_(p.grad, p.grad, value=1.0 - beta2)
-                p.sub_(lr_t * mi / (vi.sqrt() + eps))
+                (master[i] if master is not None else p).sub_(lr_t * mi / (vi.sqrt() + eps))
     return losses

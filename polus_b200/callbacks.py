@@ -337,7 +337,10 @@ class Profiler(Callback):
     """Profiling window over [steps_interval[0], steps_interval[1]) global steps; stops training when
     the window closes, like the reference (callbacks.py:408-470).  Instead of tf.profiler it brackets
     the window with cudaProfilerStart/Stop, so `ncu/nsys --capture-range=cudaProfilerApi` record exactly
-    those steps.  Enabled by POLUS_PROFILER / POLUS_PROFILER_RANGE (training.py:279-285)."""
+    those steps, and every step of the window is one NVTX range "step <n>" -- the reference's
+    tf.profiler.experimental.Trace('step', step_num=step) (callbacks.py:452-461) -- bracketed by CUDA events whose
+    device times are written to <logs_dir>/step_times.json when the window closes.
+    Enabled by POLUS_PROFILER / POLUS_PROFILER_RANGE (training.py:279-285)."""
 
     def __init__(self, write_graph=True, steps_interval=[10, 20], logs_dir="logs/tensorboard_logs"):
         super().__init__()
@@ -345,21 +348,60 @@ class Profiler(Callback):
         self.steps_interval = steps_interval
         self.logs_dir = logs_dir
         self.trace_started = False
+        self._range_open = False
+        self._events = []   # (global step, start event, stop event)
+        self.step_times_ms = {}
+
+    def _event(self):
+        import ctypes as C
+        from . import device
+        e = C.c_void_p()
+        _lib.call("polus_event_create", C.byref(e))
+        _lib.call("polus_event_record", e, device.stream())
+        return e
 
     @runs_if_root
     def on_train_batch_begin(self, epoch, step):
-        if self.coordinator.trainer.step_counter >= self.steps_interval[0] and not self.trace_started:
+        n = self.coordinator.trainer.step_counter
+        if n >= self.steps_interval[0] and not self.trace_started:
             logger.info("Profiler - trace start!")
             _lib.call("polus_profiler_start")
             self.trace_started = True
+        if self.steps_interval[0] <= n < self.steps_interval[1] and self.trace_started:
+            logger.info(f"Step - {step}")
+            _lib.call("polus_profiler_range_push", f"step {n}".encode())
+            self._range_open = True
+            self._events.append([n, self._event(), None])
 
     @runs_if_root
     def on_train_batch_end(self, epoch, step, loss):
-        if self.coordinator.trainer.step_counter >= self.steps_interval[1] - 1 and self.trace_started:
+        n = self.coordinator.trainer.step_counter
+        if self._range_open:
+            self._events[-1][2] = self._event()
+            _lib.call("polus_profiler_range_pop")
+            self._range_open = False
+        if n >= self.steps_interval[1] - 1 and self.trace_started:
             _lib.call("polus_device_sync")
             _lib.call("polus_profiler_stop")
             self.trace_started = False
             self.coordinator.trainer.early_stop = True
+            self._write_step_times()
+
+    def _write_step_times(self):
+        import ctypes as C
+        import json
+        for n, e0, e1 in self._events:
+            if e1 is None:
+                continue
+            ms = C.c_float()
+            _lib.call("polus_event_elapsed_ms", e0, e1, C.byref(ms))
+            self.step_times_ms[int(n)] = float(ms.value)
+        try:
+            os.makedirs(self.logs_dir, exist_ok=True)
+            with open(os.path.join(self.logs_dir, "step_times.json"), "w") as f:
+                json.dump({"unit": "ms", "steps": self.step_times_ms}, f)
+        except OSError as e:
+            logger.warning(f"Profiler could not write step_times.json: {e}")
 
 
 class WandBLogCallback(Callback, IOutput):

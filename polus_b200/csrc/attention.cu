@@ -47,8 +47,16 @@ struct AttnParams {
     const int32_t* mask;   // [B,S] or null
     float* lse;            // [B,nh,S]
     uint32_t* keepbits;    // [B*nh*S][S/32] dropout keep bits (forward writes, backward reads); null when p = 0
+    uint32_t* keepbits_alt;  // second buffer: steps with odd *d_step use it (null: one buffer for every step)
+    const uint32_t* ready;   // [2] ready[s & 1] == s + 1: the buffer of step s was filled ahead of time by
+                             // attn_keepbits_kernel (polus_attention_keepbits); null / mismatch: the forward draws them itself
     float* gbias;          // backward: [3H] bias gradient of the QKV projection += column sums of dqkv; may be null
 };
+
+// keep-bit buffer of the step that is running (double-buffered on the parity of the step counter when `keepbits_alt` is set)
+__device__ __forceinline__ uint32_t* keep_buffer(const AttnParams& p, uint32_t step) {
+    return (p.keepbits_alt != nullptr && (step & 1u)) ? p.keepbits_alt : p.keepbits;
+}
 
 // 2^x as ONE MUFU.EX2.  exp2f() costs four issue slots per value -- compare against -126, pre-scale by 0.5, MUFU, square --
 // to return denormal results; here x <= 0 always and a probability below 2^-126 is 0 in the bf16 P tile anyway.
@@ -191,21 +199,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         const int chunks_per_row = p.S >> 3;
         uint32_t kbits[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
         if (p.thresh16) {
+            uint32_t* kb = keep_buffer(p, step);
+            // Filled ahead of time (on a background stream, during the previous step) by attn_keepbits_kernel?  Then the 16
+            // Philox blocks per thread -- 56 % of this kernel's instructions -- are four 4-byte loads.  Warp-uniform.
+            const bool pre = p.ready != nullptr && p.ready[step & 1u] == step + 1u;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const int kc = half * 128 + c * 32;
                 if (qvalid && kc < p.S) {
                     uint32_t bits = 0;
+                    if (pre) {
+                        bits = __ldg(kb + grow * (p.S >> 5) + (kc >> 5));
+                    } else {
 #pragma unroll
-                    for (int g8 = 0; g8 < 4; ++g8) {
-                        const int key0 = kc + g8 * 8;
-                        uint32_t keep = 0xFFu;
-                        if (key0 < p.S)
-                            keep = dropout_keep8(p.seed, p.site, step, (unsigned long long)grow * chunks_per_row + (key0 >> 3), p.thresh16);
-                        bits |= keep << (8 * g8);
+                        for (int g8 = 0; g8 < 4; ++g8) {
+                            const int key0 = kc + g8 * 8;
+                            uint32_t keep = 0xFFu;
+                            if (key0 < p.S)
+                                keep = dropout_keep8(p.seed, p.site, step, (unsigned long long)grow * chunks_per_row + (key0 >> 3), p.thresh16);
+                            bits |= keep << (8 * g8);
+                        }
+                        kb[grow * (p.S >> 5) + (kc >> 5)] = bits;  // reused by the backward kernel
                     }
                     kbits[c] = bits;
-                    p.keepbits[grow * (p.S >> 5) + (kc >> 5)] = bits;  // reused by the backward kernel
                 }
             }
         }
@@ -215,19 +231,40 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         ptx::mbar_wait(&bars[1], 0);
         ptx::tc_fence_after();
         const float sc = p.scale;
-        float mx = -INFINITY;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-            float v[32];
-            ptx::tmem_ld32(lane_addr + half * 128 + c * 32, v);
-            ptx::tmem_ld_wait();
-            if (masked) {
+        // Both passes keep the NEXT 32-column chunk's tcgen05.ld in flight while the current one is processed (the load
+        // used to sit, fully exposed, at the head of every chunk) and run four independent max / sum chains instead of one
+        // 128-long dependent chain per thread.
+        float va[32], vb[32];
+        float mx;
+        {
+            float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+            ptx::tmem_ld32(lane_addr + half * 128, va);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaf(v[j], sc, sMask[half * 128 + c * 32 + j]));
-            } else {
+            for (int c = 0; c < 4; ++c) {
+                float* cur = (c & 1) ? vb : va;
+                float* nxt = (c & 1) ? va : vb;
+                ptx::tmem_ld_wait();
+                // chunk c + 1 of this pass, or chunk 0 of the exp pass (the same columns are read twice)
+                ptx::tmem_ld32(lane_addr + half * 128 + ((c + 1) & 3) * 32, nxt);
+                if (masked) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) mx = fmaxf(mx, v[j]);
+                    for (int j = 0; j < 32; j += 4) {
+                        m0 = fmaxf(m0, fmaf(cur[j], sc, sMask[half * 128 + c * 32 + j]));
+                        m1 = fmaxf(m1, fmaf(cur[j + 1], sc, sMask[half * 128 + c * 32 + j + 1]));
+                        m2 = fmaxf(m2, fmaf(cur[j + 2], sc, sMask[half * 128 + c * 32 + j + 2]));
+                        m3 = fmaxf(m3, fmaf(cur[j + 3], sc, sMask[half * 128 + c * 32 + j + 3]));
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        m0 = fmaxf(m0, cur[j]);
+                        m1 = fmaxf(m1, cur[j + 1]);
+                        m2 = fmaxf(m2, cur[j + 2]);
+                        m3 = fmaxf(m3, cur[j + 3]);
+                    }
+                }
             }
+            mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
         }
         if (!masked) mx *= sc;  // sc > 0: max(x_j * sc) == max(x_j) * sc, rounding included
         sRed[half * 128 + row] = mx;
@@ -235,40 +272,57 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 #pragma unroll
         for (int g = 1; g < NSEG; ++g) mx = fmaxf(mx, sRed[((half + g) % NSEG) * 128 + row]);  // keys beyond S are -inf, real keys finite: mx is finite
         named_bar_sync(1, SMT);                        // sRed is reused for the sums below
-        float sum = 0.f;
+        float sum;
         const float mxl = mx * kLog2e;
         const float scl = sc * kLog2e;
+        {
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            float v[32];
-            ptx::tmem_ld32(lane_addr + half * 128 + c * 32, v);
-            ptx::tmem_ld_wait();
-            const int kc = half * 128 + c * 32;  // first key of this chunk
-            if (masked) {
+            for (int c = 0; c < 4; ++c) {
+                float* v = (c & 1) ? vb : va;      // chunk 0 was requested at the end of the max pass into va
+                float* nxt = (c & 1) ? va : vb;
+                ptx::tmem_ld_wait();
+                if (c < 3) ptx::tmem_ld32(lane_addr + half * 128 + (c + 1) * 32, nxt);
+                const int kc = half * 128 + c * 32;  // first key of this chunk
+                if (masked) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    v[j] = fast_exp2(fmaf(v[j], scl, fmaf(sMask[kc + j], kLog2e, -mxl)));
-                    sum += v[j];
+                    for (int j = 0; j < 32; j += 4) {
+                        v[j] = fast_exp2(fmaf(v[j], scl, fmaf(sMask[kc + j], kLog2e, -mxl)));
+                        v[j + 1] = fast_exp2(fmaf(v[j + 1], scl, fmaf(sMask[kc + j + 1], kLog2e, -mxl)));
+                        v[j + 2] = fast_exp2(fmaf(v[j + 2], scl, fmaf(sMask[kc + j + 2], kLog2e, -mxl)));
+                        v[j + 3] = fast_exp2(fmaf(v[j + 3], scl, fmaf(sMask[kc + j + 3], kLog2e, -mxl)));
+                        s0 += v[j];
+                        s1 += v[j + 1];
+                        s2 += v[j + 2];
+                        s3 += v[j + 3];
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        v[j] = fast_exp2(fmaf(v[j], scl, -mxl));
+                        v[j + 1] = fast_exp2(fmaf(v[j + 1], scl, -mxl));
+                        v[j + 2] = fast_exp2(fmaf(v[j + 2], scl, -mxl));
+                        v[j + 3] = fast_exp2(fmaf(v[j + 3], scl, -mxl));
+                        s0 += v[j];
+                        s1 += v[j + 1];
+                        s2 += v[j + 2];
+                        s3 += v[j + 3];
+                    }
                 }
-            } else {
+                if (p.thresh16) {
+                    const uint32_t bits = kbits[c];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    v[j] = fast_exp2(fmaf(v[j], scl, -mxl));
-                    sum += v[j];
+                    for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? v[j] : 0.f;  // (the 1/(1-p) factor rides on 1/sum below)
+                }
+                // keys [kc, kc+32) -> k-block kc/64, 16-byte chunks ((kc/32)&1)*4 .. +3 of row `row`
+                uint8_t* blk = sP + (kc >> 6) * 16384 + row * 128;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int chunk = (((kc >> 5) & 1) * 4 + j) ^ (row & 7);
+                    *reinterpret_cast<bf16x8*>(blk + chunk * 16) = pack8(v + 8 * j);
                 }
             }
-            if (p.thresh16) {
-                const uint32_t bits = kbits[c];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? v[j] : 0.f;  // (the 1/(1-p) factor rides on 1/sum below)
-            }
-            // keys [kc, kc+32) -> k-block kc/64, 16-byte chunks ((kc/32)&1)*4 .. +3 of row `row`
-            uint8_t* blk = sP + (kc >> 6) * 16384 + row * 128;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int chunk = (((kc >> 5) & 1) * 4 + j) ^ (row & 7);
-                *reinterpret_cast<bf16x8*>(blk + chunk * 16) = pack8(v + 8 * j);
-            }
+            sum = (s0 + s1) + (s2 + s3);
         }
         sRed[half * 128 + row] = sum;
         ptx::fence_proxy_async_smem();
@@ -516,6 +570,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         float delta0 = 0.f, delta1 = 0.f, L0 = 0.f, L1 = 0.f;
         uint32_t kbits[NKB][2];
         {
+            const uint32_t* kbuf = p.thresh16 ? keep_buffer(p, *p.d_step) : nullptr;  // the buffer the forward of THIS step used
             bool ok[2];
 #pragma unroll
             for (int i = 0; i < 2; ++i) ok[i] = (i < n_qt) && (qbase + i * 128 + row < p.S);
@@ -526,7 +581,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                     const int q = qbase + i * 128 + row, kc = j * 128 + q4 * 32;
                     uint32_t bits = 0xFFFFFFFFu;
                     if (p.thresh16 && i < n_qt && j < n_kh && q < p.S && kc < p.S)
-                        bits = p.keepbits[((long long)(b * p.nh + h) * p.S + q) * (p.S >> 5) + (kc >> 5)];
+                        bits = kbuf[((long long)(b * p.nh + h) * p.S + q) * (p.S >> 5) + (kc >> 5)];
                     kbits[j][i] = bits;
                 }
             if (ok[0]) L0 = p.lse[(long long)(b * p.nh + h) * p.S + qbase + row];
@@ -744,6 +799,30 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     }
 }
 
+// ================================================================================================ keep bits ahead of time
+// The dropout decisions of the NEXT step's attention probabilities, drawn off the critical path: one thread per 32-key word
+// (four Philox4x32-10 blocks), launched on a low-priority background stream inside the captured step, so that its short
+// CTAs run in the partly idle tails of the GEMM waves and next to the HBM-bound kernels.  Same counters as the forward
+// kernel's own path (and as the unfused softmax kernel): element index = row * S + key, 8 elements per block.
+__global__ void __launch_bounds__(256)
+attn_keepbits_kernel(uint32_t* __restrict__ buf0, uint32_t* __restrict__ buf1, long long n_words, unsigned long long seed,
+                     uint32_t site, const uint32_t* __restrict__ d_step, uint32_t step_offset, uint32_t thresh16) {
+    const uint32_t step = *d_step + step_offset;
+    uint32_t* out = (step & 1u) ? buf1 : buf0;
+    for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += (long long)gridDim.x * blockDim.x) {
+        uint32_t bits = 0;
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8)
+            bits |= dropout_keep8(seed, site, step, (unsigned long long)w * 4 + g8, thresh16) << (8 * g8);
+        out[w] = bits;
+    }
+}
+// stream-ordered behind the generator: publishes "buffer (step & 1) holds the bits of `step`"
+__global__ void attn_keepbits_mark_kernel(uint32_t* ready, const uint32_t* d_step, uint32_t step_offset) {
+    const uint32_t step = *d_step + step_offset;
+    ready[step & 1u] = step + 1u;
+}
+
 EncodeTiledFn encode_fn() {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
@@ -778,7 +857,8 @@ int head_map(CUtensorMap* m, const void* ptr, int B, int S, int slots, int box_r
 }
 
 AttnParams make_params(int B, int S, int nh, float p_drop, uint64_t seed, uint32_t site, const uint32_t* d_step,
-                       const int32_t* mask, float* lse, uint32_t* keepbits, float* gbias = nullptr) {
+                       const int32_t* mask, float* lse, uint32_t* keepbits, float* gbias = nullptr,
+                       uint32_t* keepbits_alt = nullptr, const uint32_t* ready = nullptr) {
     AttnParams p;
     p.B = B; p.S = S; p.nh = nh;
     p.scale = 1.0f / sqrtf((float)DH);
@@ -786,6 +866,8 @@ AttnParams make_params(int B, int S, int nh, float p_drop, uint64_t seed, uint32
     p.inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
     p.seed = seed; p.site = site; p.d_step = d_step; p.mask = mask; p.lse = lse; p.keepbits = keepbits;
     p.gbias = gbias;
+    p.keepbits_alt = keepbits_alt;
+    p.ready = ready;
     return p;
 }
 
@@ -794,9 +876,30 @@ AttnParams make_params(int B, int S, int nh, float p_drop, uint64_t seed, uint32
 extern "C" int polus_attention_supported(int S, int dh) { return (dh == DH && S >= 32 && S <= 512 && S % 32 == 0) ? 1 : 0; }
 extern "C" size_t polus_attention_keepbits_words(int B, int S, int nh) { return (size_t)B * nh * S * (S / 32); }
 
+extern "C" int polus_attention_keepbits(uint32_t* keepbits, uint32_t* keepbits_alt, uint32_t* ready, int B, int S, int nh,
+                                        float p_drop, uint64_t seed, uint32_t site, const uint32_t* d_step,
+                                        uint32_t step_offset, void* stream) {
+    POLUS_REQUIRE(keepbits != nullptr && keepbits_alt != nullptr && ready != nullptr && d_step != nullptr,
+                  "polus_attention_keepbits: two buffers, the ready flags and d_step are required");
+    POLUS_REQUIRE(p_drop > 0.f && S % 32 == 0, "polus_attention_keepbits: needs p_drop > 0 and S %% 32 == 0");
+    const long long n_words = (long long)B * nh * S * (S / 32);
+    if (n_words == 0) return 0;
+    const uint32_t thresh16 = (uint32_t)lrintf(p_drop * 65536.0f);
+    const long long blocks = (n_words + 255) / 256;
+    const long long cap = (long long)polus_num_sms() * 64;   // many short CTAs: they only fill gaps
+    attn_keepbits_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(keepbits, keepbits_alt, n_words, seed, site,
+                                                                                             d_step, step_offset, thresh16);
+    g_launch_count++;
+    POLUS_LAUNCH_CHECK();
+    attn_keepbits_mark_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(ready, d_step, step_offset);
+    g_launch_count++;
+    POLUS_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int polus_attention_fwd(const polus_bf16_t* qkv, const int32_t* mask, int B, int S, int nh, int dh, float p_drop,
                                    uint64_t seed, uint32_t site, const uint32_t* d_step, polus_bf16_t* ctx, float* lse,
-                                   uint32_t* keepbits, void* stream) {
+                                   uint32_t* keepbits, uint32_t* keepbits_alt, const uint32_t* ready, void* stream) {
     POLUS_REQUIRE(polus_attention_supported(S, dh), "polus_attention_fwd: needs head_dim 64 and S <= 512, S %% 32 == 0 (got S=%d dh=%d)", S, dh);
     POLUS_REQUIRE(p_drop == 0.f || (d_step != nullptr && keepbits != nullptr), "polus_attention_fwd: dropout needs d_step and keepbits");
     if (B == 0) return 0;
@@ -811,7 +914,7 @@ extern "C" int polus_attention_fwd(const polus_bf16_t* qkv, const int32_t* mask,
         POLUS_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdCfg<4>::SMEM));
         set = true;
     }
-    AttnParams p = make_params(B, S, nh, p_drop, seed, site, d_step, mask, lse, keepbits);
+    AttnParams p = make_params(B, S, nh, p_drop, seed, site, d_step, mask, lse, keepbits, nullptr, keepbits_alt, ready);
     const int q_tiles = (S + 127) / 128;
     if (S <= 256)
         POLUS_CHECK_CUDA(polus_launch_pdl(attn_fwd_kernel<2>, dim3(B * nh * q_tiles), dim3(FwdCfg<2>::THREADS), FwdCfg<2>::SMEM, (cudaStream_t)stream, tq, to, p));
@@ -825,7 +928,7 @@ extern "C" int polus_attention_fwd(const polus_bf16_t* qkv, const int32_t* mask,
 extern "C" int polus_attention_bwd(const polus_bf16_t* qkv, const int32_t* mask, const polus_bf16_t* ctx,
                                    const polus_bf16_t* dctx, const float* lse, int B, int S, int nh, int dh, float p_drop,
                                    uint64_t seed, uint32_t site, const uint32_t* d_step, const uint32_t* keepbits,
-                                   polus_bf16_t* dqkv, float* gbias_qkv, void* stream) {
+                                   const uint32_t* keepbits_alt, polus_bf16_t* dqkv, float* gbias_qkv, void* stream) {
     POLUS_REQUIRE(polus_attention_supported(S, dh), "polus_attention_bwd: needs head_dim 64 and S <= 512, S %% 32 == 0 (got S=%d dh=%d)", S, dh);
     POLUS_REQUIRE(p_drop == 0.f || keepbits != nullptr, "polus_attention_bwd: dropout needs the forward's keepbits");
     if (B == 0) return 0;
@@ -844,7 +947,9 @@ extern "C" int polus_attention_bwd(const polus_bf16_t* qkv, const int32_t* mask,
         POLUS_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
         set = true;
     }
-    AttnParams p = make_params(B, S, nh, p_drop, seed, site, d_step, mask, const_cast<float*>(lse), const_cast<uint32_t*>(keepbits), gbias_qkv);
+    POLUS_REQUIRE(p_drop == 0.f || d_step != nullptr, "polus_attention_bwd: dropout needs d_step");
+    AttnParams p = make_params(B, S, nh, p_drop, seed, site, d_step, mask, const_cast<float*>(lse), const_cast<uint32_t*>(keepbits), gbias_qkv,
+                               const_cast<uint32_t*>(keepbits_alt), nullptr);
     const int n_half = (S + 255) / 256;
     if (n_half > 1) {
         // two CTAs per head (one per 256-query half) add their dK / dV partial sums into dqkv with bf16 TMA reduce-adds:

@@ -132,7 +132,12 @@ int polus_comm_allgather(const void* d_send, void* d_recv, size_t bytes_per_rank
 
 int polus_comm_destroy(void) {
     if (g_comm != nullptr) {
-        ncclCommDestroy(g_comm);
+        // ncclCommAbort, not ncclCommDestroy: Destroy waits for every reference to the communicator, and a captured
+        // CUDA graph that holds NCCL kernels keeps one for as long as the graph exists (measured: a 2-rank run that
+        // called Destroy after training through captured steps blocked until the watchdog fired).  All device work
+        // has been synchronised by the caller's last read; Abort releases the resources without that wait.
+        cudaDeviceSynchronize();
+        ncclCommAbort(g_comm);
         g_comm = nullptr;
     }
     g_rank = 0;

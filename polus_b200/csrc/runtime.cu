@@ -3,6 +3,7 @@
 // polus/training.py:150-151 tf.function graph).
 #include "common.cuh"
 #include <cuda_profiler_api.h>
+#include <nvtx3/nvToolsExt.h>   // header-only: ranges are no-ops unless a profiler injected itself
 #include <atomic>
 #include <stdarg.h>
 #include <stdlib.h>
@@ -207,6 +208,17 @@ int polus_profiler_start(void) {
 }
 int polus_profiler_stop(void) {
     POLUS_CHECK_CUDA(cudaProfilerStop());
+    return 0;
+}
+// Named, nestable ranges on the calling thread (NVTX): what tf.profiler.experimental.Trace('step', step_num=...) marks in
+// the reference (polus/callbacks.py:442-470).  nsys / ncu --nvtx show them; without a profiler attached they cost nothing.
+int polus_profiler_range_push(const char* name) {
+    POLUS_REQUIRE(name != nullptr, "polus_profiler_range_push: name required");
+    nvtxRangePushA(name);
+    return 0;
+}
+int polus_profiler_range_pop(void) {
+    nvtxRangePop();
     return 0;
 }
 

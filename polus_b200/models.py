@@ -15,7 +15,9 @@ from .utils import complex_json_deserializer, complex_json_serializer, flatten_d
 
 def load_model(file_name_w_ext, change_config={}, external_module=None):
     """Rebuild a model from `<name>.cfg` (+ `.init`, weights) written by SavableModel.save
-    (reference models.py:18-50).  Weights are read from `<name>.npz`, or `<name>.h5` when h5py exists."""
+    (reference models.py:18-50).  Weights come from `<name>.h5` -- the reference's format, datasets weight0..N of the root
+    group, read with h5py when it is installed and with the package's own HDF5 reader (h5lite) otherwise -- or from the
+    `<name>.npz` files round 1 of this package wrote."""
     file_name = os.path.splitext(file_name_w_ext)[0]
     with open(file_name_w_ext, "r") as f:
         cfg = complex_json_deserializer(json.load(f))
@@ -26,13 +28,17 @@ def load_model(file_name_w_ext, change_config={}, external_module=None):
         with open(file_name + ".init", "rb") as f:
             args, kwargs = pickle.load(f)
         model.init_from_data(*args, **kwargs)
-    if os.path.exists(file_name + ".npz"):
+    if os.path.exists(file_name + ".h5"):
+        try:
+            import h5py
+            with h5py.File(file_name + ".h5", 'r') as f:
+                model.set_weights([f['weight' + str(i)][:] for i in range(len(f.keys()))])
+        except ImportError:
+            from . import h5lite
+            model.set_weights(h5lite.read_weights(file_name + ".h5"))
+    else:
         with np.load(file_name + ".npz") as z:
             model.set_weights([z[f"weight{i}"] for i in range(len(z.files))])
-    else:
-        import h5py  # optional: the reference's on-disk format
-        with h5py.File(file_name + ".h5", 'r') as f:
-            model.set_weights([f['weight' + str(i)][:] for i in range(len(f.keys()))])
     return model
 
 
@@ -73,7 +79,8 @@ class PolusModel(nn.Model):
 class SavableModel(PolusModel):
     def save(self, base_path=os.path.join(".polus_cache", "saved_models"), extension=""):
         """`<base>/<name><ext>.cfg` (complex JSON) + `.init` (pickle) + weights in get_weights() order
-        (reference models.py:112-133; datasets weight0..N go to .h5 when h5py is installed, else .npz)."""
+        (reference models.py:112-133): datasets weight0..N of `<name>.h5`, through h5py when it is installed, else through
+        h5lite (same on-disk layout: version-0 superblock, symbol-table root group, contiguous datasets)."""
         os.makedirs(base_path, exist_ok=True)
         path = os.path.join(base_path, self.name + extension)
         with open(path + ".cfg", "w") as f:
@@ -88,7 +95,8 @@ class SavableModel(PolusModel):
                 for i, w in enumerate(weights):
                     f.create_dataset('weight' + str(i), data=w)
         except ImportError:
-            np.savez(path + ".npz", **{f"weight{i}": w for i, w in enumerate(weights)})
+            from . import h5lite
+            h5lite.write_weights(path + ".h5", weights)
 
 
 class SequentialSavableModel(nn.Sequential, SavableModel):

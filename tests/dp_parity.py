@@ -89,7 +89,15 @@ def run_dp_parity(steps=3, per_rank=4, seq=32, base_lr=1e-3, seed=11, log=None):
     del trainer1, model
     from polus_b200 import tensor
     tensor.reset_arena()
-    return {"world": world, "replicas_identical": bool(identical), "vs_single_rank_rel": rel, "weights_max_abs_diff": wdiff,
+    # hvd.allgather_object with device tensors inside (what ValidationDataCallback gathers, polus/callbacks.py:249): the
+    # tensors travel through ncclAllGather, the host labels through the socket store
+    pred = tensor.Tensor.from_numpy(np.arange(12, dtype=np.int32).reshape(3, 4) + 100 * rank, tensor.I32)
+    got = h.allgather_object((pred, {"labels": np.full(3, rank), "rank": rank}))
+    gather_ok = len(got) == world and all(
+        np.array_equal(got[r][0].numpy() if hasattr(got[r][0], "numpy") else np.asarray(got[r][0]),
+                       np.arange(12, dtype=np.int32).reshape(3, 4) + 100 * r)
+        and got[r][1]["rank"] == r and np.array_equal(got[r][1]["labels"], np.full(3, r)) for r in range(world))
+    return {"allgather_ok": bool(gather_ok), "world": world, "replicas_identical": bool(identical), "vs_single_rank_rel": rel, "weights_max_abs_diff": wdiff,
             "weights_mean_abs_diff": wmean, "lr": lr_used, "steps": steps, "losses_dp_mean": [float(v) for v in losses_dp_mean],
             "losses_single": [float(v) for v in losses1]}
 
@@ -113,6 +121,8 @@ if __name__ == "__main__":   # python -m torch.distributed.run ... tests/dp_pari
     polus_b200.PolusContext()
     _log("context ready")
     out = run_dp_parity(steps=4, log=_log)
-    comm.shutdown()
     if r == 0:
         print("DPPARITY " + json.dumps(out), flush=True)
+    faulthandler.cancel_dump_traceback_later()
+    sys.stdout.flush()
+    os._exit(0)   # like bench.py: leave without tearing the communicator down (graphs holding NCCL kernels are still alive)

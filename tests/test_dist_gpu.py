@@ -18,6 +18,7 @@ WEIGHT_MEAN_ABS = 2e-5
 
 def check(report):
     assert report["replicas_identical"], report
+    assert report["allgather_ok"], report                               # device tensors through ncclAllGather (callbacks.py:249)
     assert report["vs_single_rank_rel"] < LOSS_REL, report
     assert report["weights_mean_abs_diff"] < WEIGHT_MEAN_ABS, report
     assert report["weights_max_abs_diff"] <= 2.02 * report["lr"] * report["steps"], report

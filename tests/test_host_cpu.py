@@ -231,7 +231,7 @@ def test_training_loop_order_and_callbacks(monkeypatch):
     assert abs(smooth.smooth_loss - mov / (1 - 0.97 ** n)) < 1e-12
 
 
-def test_profiler_env_appends_callback_and_stops(monkeypatch):
+def test_profiler_env_appends_callback_and_stops(monkeypatch, tmp_path):
     from polus_b200 import callbacks
     from polus_b200.training import ClassifierTrainer
 
@@ -239,14 +239,23 @@ def test_profiler_env_appends_callback_and_stops(monkeypatch):
         name = "fake"
         trainable_weights = []
     calls = []
-    monkeypatch.setattr(callbacks._lib, "call", lambda name, *a: calls.append(name) or 0)
+    from polus_b200 import device
+    monkeypatch.setattr(callbacks._lib, "call", lambda name, *a: calls.append((name, a)) or 0)
+    monkeypatch.setattr(device, "stream", lambda: 0)
     monkeypatch.setenv("POLUS_PROFILER", "true")
     monkeypatch.setenv("POLUS_PROFILER_RANGE", "2:4")
+    monkeypatch.chdir(tmp_path)
     tr = ClassifierTrainer(M(), optimizer=object(), loss=None)
     monkeypatch.setattr(tr, "train_step", lambda *d: 1.0)
     tr.train([(0, 0)] * 10, epochs=1, callbacks=[])
     assert tr.step_counter == 4 and tr.early_stop  # window [2,4) then stop, like the reference
-    assert calls.count("polus_profiler_start") == 1 and calls.count("polus_profiler_stop") == 1
+    names = [n for n, _ in calls]
+    assert names.count("polus_profiler_start") == 1 and names.count("polus_profiler_stop") == 1
+    # one named range per step of the window (reference: tf.profiler.experimental.Trace('step', step_num=...), callbacks.py:452-461)
+    pushes = [a[0] for n, a in calls if n == "polus_profiler_range_push"]
+    assert pushes == [b"step 2", b"step 3"] and names.count("polus_profiler_range_pop") == 2
+    assert names.index("polus_profiler_start") < names.index("polus_profiler_range_push")
+    assert (tmp_path / "logs" / "tensorboard_logs" / "step_times.json").exists()
 
 
 def test_gradient_bucket_plan():
@@ -616,3 +625,25 @@ def test_hpo_prune_callback_without_and_with_backend():
     except Exception as e:  # optuna present: TrialPruned
         pruned = type(e).__name__ == "TrialPruned"
     assert pruned and seen[-1] == (0.2, 1)
+
+
+def test_polus_alias_package_resolves_to_the_same_modules():
+    """`from polus.training import ClassifierTrainer` (a script written against the reference) gets polus_b200's class, and
+    the module objects are shared (one parameter arena, one PolusContext), not re-imported copies."""
+    import sys
+    import polus
+    import polus.callbacks
+    from polus.ir.training import EfficientDenseRetrievalTrainer
+    from polus.mock import horovod
+    from polus.ner.models import baselineNER_MLP_Dropout_CRF
+    from polus.training import BaseTrainer, ClassifierTrainer
+    import polus_b200
+    import polus_b200.training
+    assert ClassifierTrainer is polus_b200.training.ClassifierTrainer and issubclass(ClassifierTrainer, BaseTrainer)
+    assert sys.modules["polus.training"] is sys.modules["polus_b200.training"]
+    assert sys.modules["polus.callbacks"] is sys.modules["polus_b200.callbacks"]
+    assert polus.PolusContext is polus_b200.PolusContext and polus.__version__ == polus_b200.__version__
+    assert horovod.size() == 1 and callable(baselineNER_MLP_Dropout_CRF) and EfficientDenseRetrievalTrainer.__name__ == "EfficientDenseRetrievalTrainer"
+    import pytest
+    with pytest.raises(ImportError):
+        import polus.hpo  # noqa: F401  (out of scope: not provided, and the alias must not invent it)

@@ -582,3 +582,48 @@ def test_fused_attention_fwd_bwd(dev, B, nh, S, p, use_mask):
     np.testing.assert_allclose(dq_f, dqkv_r, atol=tol_g, rtol=0)
     np.testing.assert_allclose(ctx_u, ctx_r, atol=tol_c, rtol=0)
     np.testing.assert_allclose(dq_u, dqkv_r, atol=tol_g, rtol=0)
+
+
+# -------------------------------------------------------------------------------------------------- keep bits ahead of time
+def test_attention_keepbits_ahead_bit_exact_and_equivalent(dev):
+    """polus_attention_keepbits (the dropout decisions of the NEXT step, drawn on a background stream) writes exactly the
+    bits the oracle's Philox4x32-10 gives for (seed, site, step + offset) into the buffer of that step's parity and
+    publishes the step; a forward launch that finds them published produces bit-identical output to one that draws them
+    itself, and leaves identical bits for the backward."""
+    from oracle import philox
+    from polus_b200 import ops
+    from polus_b200.tensor import BF16, F32, I32
+    B, S, nh, p, seed, site = 2, 128, 3, 0.1, 991, 4
+    H = nh * 64
+    words = int(call("polus_attention_keepbits_words", B, S, nh))
+    assert words == B * nh * S * S // 32
+    rng = np.random.default_rng(0)
+    qkv = T(dev.bf16_round(rng.standard_normal((B, S, 3 * H)).astype(np.float32)), BF16)
+    for step in (6, 7):   # even and odd: both buffers
+        sp = step_ptr(step - 1)                       # the generator runs during step - 1 with offset 1
+        k0, k1, ready = new((words,), I32), new((words,), I32), new((4,), I32)
+        call("polus_attention_keepbits", k0.ptr, k1.ptr, ready.ptr, B, S, nh, p, seed, site, sp, 1, st())
+        buf = k1 if step & 1 else k0
+        got = buf.numpy().view(np.uint32)
+        keep = philox.dropout_keep_mask(B * nh * S * S, p, seed, site, step).reshape(-1, 32)
+        want = (keep.astype(np.uint32) << np.arange(32, dtype=np.uint32)).sum(1, dtype=np.uint64).astype(np.uint32)
+        assert np.array_equal(got, want)
+        r = ready.numpy().view(np.uint32)
+        assert r[step & 1] == step + 1 and r[(step & 1) ^ 1] == 0
+        assert not (k0 if step & 1 else k1).numpy().any()         # the other buffer was not touched
+        # forward at `step`: (a) bits published ahead, (b) no record -> draws them itself
+        sp = step_ptr(step)
+        ctx_a, ctx_b = new((B, S, H), BF16), new((B, S, H), BF16)
+        lse = new((B, nh, S), F32)
+        call("polus_attention_fwd", qkv.ptr, None, B, S, nh, 64, p, seed, site, sp, ctx_a.ptr, lse.ptr, k0.ptr, k1.ptr, ready.ptr, st())
+        j0, j1 = new((words,), I32), new((words,), I32)
+        call("polus_attention_fwd", qkv.ptr, None, B, S, nh, 64, p, seed, site, sp, ctx_b.ptr, lse.ptr, j0.ptr, j1.ptr, None, st())
+        assert np.array_equal(ctx_a.numpy(), ctx_b.numpy())
+        assert np.array_equal((j1 if step & 1 else j0).numpy().view(np.uint32), want)
+        # a stale record (bits of another step) must be ignored
+        sp = step_ptr(step + 2)
+        ctx_c, ctx_d = new((B, S, H), BF16), new((B, S, H), BF16)
+        call("polus_attention_fwd", qkv.ptr, None, B, S, nh, 64, p, seed, site, sp, ctx_c.ptr, lse.ptr, k0.ptr, k1.ptr, ready.ptr, st())
+        call("polus_attention_fwd", qkv.ptr, None, B, S, nh, 64, p, seed, site, sp, ctx_d.ptr, lse.ptr, j0.ptr, j1.ptr, None, st())
+        assert np.array_equal(ctx_c.numpy(), ctx_d.numpy())
+        assert not np.array_equal(ctx_c.numpy(), ctx_a.numpy())

@@ -2,6 +2,8 @@
 post_process_grads results are what the optimizer applies, learning-rate assignments reach a captured step, lazy loss
 handles keep their value past the pinned ring, losses honour their upstream gradient, and the IR trainer's k explicit
 negatives are sliced on the device inside the captured step (polus/ir/training.py:59-67,94-107)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -268,3 +270,28 @@ def test_ir_trainer_k_explicit_negatives_on_device():
         got = float(trainer.train_step(q, d, n))
         assert got == pytest.approx(expect, rel=2e-2, abs=2e-3), (step, got, expect)
     assert trainer.k_negatives == k and len(trainer._compiled) == 1   # captured once, replayed on new batches
+
+
+def test_save_and_load_model_through_the_reference_h5_format(tmp_path):
+    """SavableModel.save -> load_model (polus/models.py:18-50,107-133): `<name>.cfg` + `<name>.h5` with datasets
+    weight0..N in get_weights() order (written by h5lite when h5py is absent), rebuilt through the factory name."""
+    from polus_b200 import h5lite, tensor
+    from polus_b200 import models as M
+    from polus_b200.ner import models as NM
+    from polus_b200.utils import set_random_seed
+    tensor.reset_arena()
+    set_random_seed(1)
+    model = NM.baselineNER_MLP_Dropout_CRF(model={"sequence_length": 16, "output_classes": 4, "hidden_space": 32, "activation": "mish"})
+    x = np.random.default_rng(0).standard_normal((2, 16, 768)).astype(np.float32)
+    ref = model(x, training=False).numpy()
+    model.save(base_path=str(tmp_path))
+    stem = os.path.join(str(tmp_path), model.name)
+    assert os.path.exists(stem + ".cfg") and os.path.exists(stem + ".h5") and not os.path.exists(stem + ".npz")
+    on_disk = h5lite.read_weights(stem + ".h5")
+    for a, b in zip(on_disk, model.get_weights()):
+        assert a.dtype == np.float32 and np.array_equal(a, b)
+    loaded = M.load_model(stem + ".cfg", external_module=NM)
+    assert loaded.name == model.name and len(loaded.get_weights()) == len(on_disk)
+    for a, b in zip(loaded.get_weights(), model.get_weights()):
+        assert np.array_equal(a, b)
+    np.testing.assert_array_equal(loaded(x, training=False).numpy(), ref)
