@@ -375,7 +375,7 @@ def run_ours(args):
                 "traffic_source": (f"{cap['_path']} ({cap['n_launches']} launches, ncu --set full, batch {cap['batch']}; "
                                    f"scaled linearly to batch {args.batch})") if cap else None,
                 "tensor_pipe_active_pct": cap["tensor_pipe_active_pct_time_weighted"] if cap else None,
-                "algorithmic_bytes_per_launch": 244.2e6 * args.batch / 128.0,
+                "algorithmic_bytes_per_launch": 244.2e6 * args.batch / 128.0,   # sum over the step's GEMMs of (A + B + C bytes) / launches
                 "kernel": "gemm_tc_kernel (all tcgen05 GEMM launches of one step)", "launches": n_tc,
                 "gemm_ms_per_step": gemm_only_ms, "gemm_gflop_per_step": tot_flop / 1e9,
                 "method": "frac: CUDA-event time of a captured replay of the step's GEMM launches alone (same order/buffers/"
@@ -447,6 +447,17 @@ def run_ours(args):
         except Exception:
             pass
         dbg(f"strong scaling done: {strong}")
+    # ---- the same step at round 1's headline batch (128 / GPU), so the two rounds' lines can be compared like for like
+    sweep = None
+    if world == 1 and args.sweep_batch and args.sweep_batch != args.batch:
+        sb = to_device(synthetic_batches(4, args.sweep_batch, SEQ, 30522, 4, seed=21 + rank))
+        for i in range(4):
+            float(trainer.train_step(*sb[i % len(sb)]))
+        for i in range(40):
+            last = trainer.train_step(*sb[i % len(sb)])
+        float(last)
+        ms_s, _, _ = timed(trainer, sb, args.steps)
+        sweep = {str(args.sweep_batch): {"seq_s": args.sweep_batch * args.steps / (ms_s * 1e-3), "ms_per_step": ms_s / args.steps}}
     trainer.release_graphs()
     del trainer, dev_batches
 
@@ -482,6 +493,8 @@ def run_ours(args):
         line["dp_parity"] = dp_parity
     if strong is not None:
         line["strong_gb256"] = strong
+    if sweep is not None:
+        line["batch_sweep"] = sweep
     if extra is not None:
         line["configs"] = extra
     if world == 1 and not args.no_cpu_baseline:
@@ -498,7 +511,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=128, help="sequences per GPU per step (weak scaling: global batch = batch x N)")
+    ap.add_argument("--batch", type=int, default=256, help="sequences per GPU per step (weak scaling: global batch = batch x N); "
+                    "BASELINE.json names the model and sequence length, not the batch: 256 is the best of the 32..256 sweep (DESIGN.md)")
+    ap.add_argument("--sweep-batch", type=int, default=128, help="a second per-GPU batch timed briefly at N = 1 (round 1's headline batch)")
     ap.add_argument("--ref-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--preheat-steps", type=int, default=100, help="untimed steps before the timed regions (~2.4 s at batch 128)")

@@ -125,15 +125,37 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const int q0 = qt * 128;
 
     pdl_trigger();
-    if (threadIdx.x == 0) {
+    // (1) the additive key mask of this thread's key slot: a graph input, never written inside the step, so the load may
+    //     start before pdl_wait() and overlaps the whole prologue (it used to be a fully exposed global load in front of
+    //     the first named barrier: 7 % of the kernel's stall samples at p = 0, profiles/r02_ncu_attn_fwd_p0.txt)
+    float my_mask = -INFINITY;
+    if (warp > 0) {
+        const int t = threadIdx.x - 32;
+        if (t < p.S) my_mask = p.mask ? (1.0f - (float)__ldg(p.mask + (long long)b * p.S + t)) * -10000.0f : 0.f;
+    }
+    // (2) the first thread of warp 1 owns the load barrier and issues the TMA loads at once, while warp 0 initialises the
+    //     other barriers and allocates TMEM: allocation and the block-wide barrier run UNDER the loads, not in front of them
+    if (threadIdx.x == 32) {
         ptx::prefetch_tensormap(&tmQKV);
-        ptx::prefetch_tensormap(&tmO);
         ptx::mbar_init(&bars[0], 1);
+        ptx::fence_barrier_init();
+        pdl_wait();  // qkv is the previous kernel's output
+        ptx::mbar_expect_tx(&bars[0], 16384 + NSEG * 32768);
+        ptx::tma_load_4d(sQ, &tmQKV, &bars[0], 0, q0, h, b);
+#pragma unroll
+        for (int g = 0; g < NSEG; ++g) {
+            ptx::tma_load_4d(sK + g * 16384, &tmQKV, &bars[0], 0, g * 128, p.nh + h, b);
+            ptx::tma_load_4d(sV + g * 16384, &tmQKV, &bars[0], 0, g * 128, 2 * p.nh + h, b);
+        }
+    }
+    if (threadIdx.x == 0) {
+        ptx::prefetch_tensormap(&tmO);
         ptx::mbar_init(&bars[1], 1);
         ptx::mbar_init(&bars[2], SMT);
         ptx::mbar_init(&bars[3], 1);
         ptx::fence_barrier_init();
     }
+    __syncwarp();
     if (warp == 0) ptx::tmem_alloc<128 * NSEG>(tmem_slot);
     ptx::tc_fence_before();
     __syncthreads();
@@ -143,13 +165,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 
     if (warp == 0) {
         if (lane == 0) {
-            ptx::mbar_expect_tx(&bars[0], 16384 + NSEG * 32768);
-            ptx::tma_load_4d(sQ, &tmQKV, &bars[0], 0, q0, h, b);
-#pragma unroll
-            for (int g = 0; g < NSEG; ++g) {
-                ptx::tma_load_4d(sK + g * 16384, &tmQKV, &bars[0], 0, g * 128, p.nh + h, b);
-                ptx::tma_load_4d(sV + g * 16384, &tmQKV, &bars[0], 0, g * 128, 2 * p.nh + h, b);
-            }
             ptx::mbar_wait(&bars[0], 0);
             ptx::tc_fence_after();
             {   // S = Q K^T : A = Q (K-major), B = K (K-major), M128 N256 per 256 keys, K = 64 in 4 steps
@@ -186,9 +201,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         const int half = e >> 2;                 // key segment: keys [128*half, 128*half + 128)
         const int row = quad * 32 + lane;        // row inside the tile (== TMEM lane)
         const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
-        // additive key mask, staged once: (1 - m) * -10000 for real keys, -inf for keys beyond S
-        float my_mask = -INFINITY;
-        if (t < p.S) my_mask = p.mask ? (1.0f - (float)p.mask[(long long)b * p.S + t]) * -10000.0f : 0.f;
+        // additive key mask, staged once: (1 - m) * -10000 for real keys, -inf for keys beyond S (loaded at the top)
         sMask[t] = my_mask;
         // Dropout decisions of this thread's 128 probabilities, made (and written out for the backward kernel) while the
         // Q/K/V tiles are still in flight and the first MMA runs: 16 Philox blocks that used to sit between the two
@@ -427,18 +440,47 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const bool partial_kv = n_half > 1;
 
     pdl_trigger();
-    if (threadIdx.x == 0) {
+    // The first thread of warp 1 owns the three load barriers and issues every initial TMA load at once; warp 0 meanwhile
+    // initialises the other barriers and allocates TMEM, so allocation and the block-wide barrier run under the loads.
+    // O (the forward output) comes through TMA as well: delta = rowsum(dO * O) is computed from shared memory, so dO is
+    // read from HBM once and no thread-issued global load sits in the prologue.  Three load groups, in the order of
+    // first use: block (0,0) starts when the first 80 KB have landed; the second query tile and the second key block
+    // (another 80 KB) arrive under its arithmetic (every CTA of a wave starts at the same time: the prologue is
+    // bandwidth-bound, profiles/r01_attn_bwd_timeline_v11.txt)
+    if (threadIdx.x == 32) {
         ptx::prefetch_tensormap(&tmQKV);
         ptx::prefetch_tensormap(&tmDO);
-        ptx::prefetch_tensormap(&tmDQKV);
+        ptx::prefetch_tensormap(&tmO);
         ptx::mbar_init(&bars[0], 1);
+        ptx::mbar_init(&bars[6], 1);
+        ptx::mbar_init(&bars[7], 1);
+        ptx::fence_barrier_init();
+        pdl_wait();  // qkv / ctx / dctx are earlier kernels' outputs
+        ptx::mbar_expect_tx(&bars[0], 5 * 16384);
+        ptx::tma_load_4d(sQ, &tmQKV, &bars[0], 0, qbase, h, b);
+        ptx::tma_load_4d(sK, &tmQKV, &bars[0], 0, 0, p.nh + h, b);
+        ptx::tma_load_4d(sDO, &tmDO, &bars[0], 0, qbase, h, b);
+        ptx::tma_load_4d(sV, &tmQKV, &bars[0], 0, 0, 2 * p.nh + h, b);
+        ptx::tma_load_4d(sPd, &tmO, &bars[0], 0, qbase, h, b);
+        if (n_qt > 1) {
+            ptx::mbar_expect_tx(&bars[6], 3 * 16384);
+            ptx::tma_load_4d(sQ + 16384, &tmQKV, &bars[6], 0, qbase + 128, h, b);
+            ptx::tma_load_4d(sDO + 16384, &tmDO, &bars[6], 0, qbase + 128, h, b);
+            ptx::tma_load_4d(sO1, &tmO, &bars[6], 0, qbase + 128, h, b);
+        }
+        if (n_kh > 1) {
+            ptx::mbar_expect_tx(&bars[7], 2 * 16384);
+            ptx::tma_load_4d(sK + 16384, &tmQKV, &bars[7], 0, 128, p.nh + h, b);
+            ptx::tma_load_4d(sV + 16384, &tmQKV, &bars[7], 0, 128, 2 * p.nh + h, b);
+        }
+    }
+    if (threadIdx.x == 0) {
+        ptx::prefetch_tensormap(&tmDQKV);
         ptx::mbar_init(&bars[1], 1);
         ptx::mbar_init(&bars[2], BWD_SM_THREADS);
         ptx::mbar_init(&bars[3], 1);
         ptx::mbar_init(&bars[4], 1);
         ptx::mbar_init(&bars[5], 1);
-        ptx::mbar_init(&bars[6], 1);
-        ptx::mbar_init(&bars[7], 1);
         ptx::fence_barrier_init();
     }
     if (warp == 0) ptx::tmem_alloc<512>(tmem_slot);
@@ -451,28 +493,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 
     if (warp == 0) {
         if (lane == 0) {
-            // O (the forward output) comes through TMA as well: delta = rowsum(dO * O) is computed from shared memory, so dO is
-            // read from HBM once and no thread-issued global load sits in the prologue.  Three load groups, in the order of
-            // first use: block (0,0) starts when the first 80 KB have landed; the second query tile and the second key block
-            // (another 80 KB) arrive under its arithmetic (every CTA of a wave starts at the same time: the prologue is
-            // bandwidth-bound, profiles/r01_attn_bwd_timeline_v11.txt)
-            ptx::mbar_expect_tx(&bars[0], 5 * 16384);
-            ptx::tma_load_4d(sQ, &tmQKV, &bars[0], 0, qbase, h, b);
-            ptx::tma_load_4d(sK, &tmQKV, &bars[0], 0, 0, p.nh + h, b);
-            ptx::tma_load_4d(sDO, &tmDO, &bars[0], 0, qbase, h, b);
-            ptx::tma_load_4d(sV, &tmQKV, &bars[0], 0, 0, 2 * p.nh + h, b);
-            ptx::tma_load_4d(sPd, &tmO, &bars[0], 0, qbase, h, b);
-            if (n_qt > 1) {
-                ptx::mbar_expect_tx(&bars[6], 3 * 16384);
-                ptx::tma_load_4d(sQ + 16384, &tmQKV, &bars[6], 0, qbase + 128, h, b);
-                ptx::tma_load_4d(sDO + 16384, &tmDO, &bars[6], 0, qbase + 128, h, b);
-                ptx::tma_load_4d(sO1, &tmO, &bars[6], 0, qbase + 128, h, b);
-            }
-            if (n_kh > 1) {
-                ptx::mbar_expect_tx(&bars[7], 2 * 16384);
-                ptx::tma_load_4d(sK + 16384, &tmQKV, &bars[7], 0, 128, p.nh + h, b);
-                ptx::tma_load_4d(sV + 16384, &tmQKV, &bars[7], 0, 128, 2 * p.nh + h, b);
-            }
             ptx::mbar_wait(&bars[0], 0);
             ptx::tc_fence_after();
             const uint64_t kbase = ptx::umma_desc_base(16, 1024);            // K-major, one 64-wide k-block

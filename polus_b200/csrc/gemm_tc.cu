@@ -449,12 +449,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + cc * 32;
                 const bool full32 = p.N - col0 >= 32;
                 if (p.has_c2 && p.c2_grad && full32) {
-                    // activation + derivative (the FFN-up GEMM): 16 accumulator columns at a time (96 registers)
+                    // activation + derivative (the FFN-up GEMM): 16 accumulator columns at a time; the second half's
+                    // tcgen05.ld is in flight while the first half is processed (21 % of this path's stall samples were
+                    // long-scoreboard waits behind the loads, profiles/r02_ncu_gemm_ffn1.txt)
+                    float va[16], vb[16];
+                    ptx::tmem_ld16(tcol, va);
 #pragma unroll
                     for (int sub = 0; sub < 2; ++sub) {
-                        float v[16];
-                        ptx::tmem_ld16(tcol + sub * 16, v);
+                        float* v = sub == 0 ? va : vb;
                         ptx::tmem_ld_wait();
+                        if (sub == 0) ptx::tmem_ld16(tcol + 16, vb);
                         if (p.alpha != 1.0f) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j) v[j] *= p.alpha;

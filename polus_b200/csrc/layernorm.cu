@@ -283,8 +283,9 @@ ln_res_bwd_pf_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, 
     extern __shared__ __align__(128) uint8_t ln_smem[];
     float* red = reinterpret_cast<float*>(ln_smem);            // [kWarps][H] reduction scratch
     float* sg = red + kWarps * H;                               // gamma [H]
-    uint8_t* rows = reinterpret_cast<uint8_t*>(sg + H);         // [kWarps][2 slots][3][ROWB]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(rows + kWarps * 2 * 3 * ROWB);  // [kWarps][2]
+    constexpr int SLOT = 3 * ROWB + 128;                        // dy | dy2 | z rows + the row's dropout keep bytes (H / 8 <= 128)
+    uint8_t* rows = reinterpret_cast<uint8_t*>(sg + H);         // [kWarps][2 slots][SLOT]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(rows + kWarps * 2 * SLOT);  // [kWarps][2]
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     constexpr int chunks = H >> 3;
@@ -306,15 +307,21 @@ ln_res_bwd_pf_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, 
     const uint32_t step = dc.thresh16 ? *d_step : 0u;
     constexpr float inv_h = 1.0f / (float)H;
     const int row_step = gridDim.x * kWarps;
-    const uint32_t tx = (dy2 != nullptr ? 3u : 2u) * ROWB;
-    uint8_t* my = rows + warp * (2 * 3 * ROWB);
+    // The keep bytes of the row ride on the same bulk copy as the row itself (H / 8 bytes, a 16-byte multiple for the three
+    // widths this kernel is built for).  They used to be prefetched into registers with LDG.U8: with 72 accumulator
+    // registers per thread ptxas spilled them, and the spill STORE right behind the load waited for the load -- 12 % of
+    // the kernel's stall samples sat on that one instruction (profiles/r02_ncu_ln_bwd.txt).
+    const bool kb_smem = dc.thresh16 && keepbits != nullptr;
+    const uint32_t tx = (dy2 != nullptr ? 3u : 2u) * ROWB + (kb_smem ? (uint32_t)chunks : 0u);
+    uint8_t* my = rows + warp * (2 * SLOT);
     auto post = [&](int row, int slot) {  // lane 0 only
-        uint8_t* dst = my + slot * (3 * ROWB);
+        uint8_t* dst = my + slot * SLOT;
         uint64_t* bar = &bars[warp * 2 + slot];
         ptx::mbar_expect_tx(bar, tx);
         ptx::bulk_load(dst, dy + (long long)row * H, ROWB, bar);
         ptx::bulk_load(dst + 2 * ROWB, z + (long long)row * H, ROWB, bar);
         if (dy2 != nullptr) ptx::bulk_load(dst + ROWB, dy2 + (long long)row * H, ROWB, bar);
+        if (kb_smem) ptx::bulk_load(dst + 3 * ROWB, keepbits + (long long)row * chunks, chunks, bar);
     };
     int row = blockIdx.x * kWarps + warp;
     if (row < M && lane == 0) post(row, 0);
@@ -335,13 +342,8 @@ ln_res_bwd_pf_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, 
             rstd_n = rstd_in[next];
             mean_n = mean_in[next];
         }
-        uint32_t kb[NC];
-        if (dc.thresh16 && keepbits != nullptr) {
-#pragma unroll
-            for (int i = 0; i < NC; ++i) kb[i] = keepbits[(long long)row * chunks + lane + 32 * i];
-        }
         ptx::mbar_wait(&bars[warp * 2 + slot], (uint32_t)(k >> 1) & 1u);
-        uint8_t* src = my + slot * (3 * ROWB);
+        uint8_t* src = my + slot * SLOT;
         const long long base = (long long)row * H;
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -388,7 +390,7 @@ ln_res_bwd_pf_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, 
             }
             if (dres != nullptr && dres != dx) st_global16(dres + base + c * 8, pack8(dz));
             if (dc.thresh16) {
-                if (keepbits != nullptr) dropout_apply8_bits(kb[i], dc.inv_keep, dz);
+                if (keepbits != nullptr) dropout_apply8_bits(src[3 * ROWB + c], dc.inv_keep, dz);
                 else dropout_apply8(dc.seed, dc.site, step, (unsigned long long)row * chunks + c, dc.thresh16, dc.inv_keep, dz);
             }
             st_global16(dx + base + c * 8, pack8(dz));
@@ -683,9 +685,10 @@ extern "C" int polus_ln_res_bwd(const polus_bf16_t* dy, const polus_bf16_t* dy2,
     }
     // rows prefetched through shared memory (H = 768: 101 KB per CTA, two CTAs per SM)
     static const bool pf_env = !(getenv("POLUS_LN_PREFETCH") && atoi(getenv("POLUS_LN_PREFETCH")) == 0);
-    const bool aligned = ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dy2) | reinterpret_cast<uintptr_t>(z)) & 15) == 0;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dy2) | reinterpret_cast<uintptr_t>(z) |
+                           reinterpret_cast<uintptr_t>(keepbits)) & 15) == 0;
     if (pf_env && aligned && (H == 768 || H == 512 || H == 256)) {
-        const size_t smem_pf = (size_t)(kWarps + 1) * H * sizeof(float) + (size_t)kWarps * 2 * 3 * H * 2 + kWarps * 2 * sizeof(uint64_t);
+        const size_t smem_pf = (size_t)(kWarps + 1) * H * sizeof(float) + (size_t)kWarps * 2 * (3 * H * 2 + 128) + kWarps * 2 * sizeof(uint64_t);
 #define LN_BWD_PF(NC_)                                                                                                          \
     {                                                                                                                          \
         static bool set = false;                                                                                               \

@@ -36,8 +36,11 @@ def _num(v):
 def rows_of(path):
     """[(kernel name, {metric: (value, unit)})] from a .ncu-rep or a text summary of this tool."""
     out = []
-    if path.endswith(".ncu-rep"):
-        txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if path.endswith(".ncu-rep") or path.endswith(".csv"):   # a report, or its `--page raw --csv` dump made on the GPU box
+        if path.endswith(".csv"):
+            txt = open(path).read()
+        else:
+            txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(txt.splitlines()))
         hdr, units = rows[0], rows[1]
         for r in rows[2:]:
