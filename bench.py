@@ -317,6 +317,9 @@ def run_ours(args):
     dbg("timed (e2e) done")
     clocks = sampler.stop() if sampler else None
     ms_dev, ms_e2e = timer.max_over_ranks([ms_dev, ms_e2e])
+    if not (np.isfinite(loss_dev) and np.isfinite(loss_e2e)):
+        # a step that diverged runs on NaNs (less switching, higher clocks): its timing is not a measurement
+        raise RuntimeError(f"bench: non-finite training loss (resident {loss_dev}, e2e {loss_e2e}) on rank {rank}")
 
     # ---- roofline of the dominant kernel family (tcgen05 GEMMs, ~all FLOPs of the step)
     # (1) one op-by-op step counts the launches and their algorithmic FLOPs (2mnk each);

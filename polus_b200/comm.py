@@ -31,7 +31,6 @@ BUCKET_BYTES = int(os.environ.get("POLUS_BUCKET_MB", "64")) * 1024 * 1024
 # "bf16" = half the NVLink bytes, one bf16 rounding per partial sum (like hvd.Compression.fp16); POLUS_GRAD_WIRE selects
 WIRE_DTYPE = os.environ.get("POLUS_GRAD_WIRE", "f32")
 assert WIRE_DTYPE in ("f32", "bf16"), "POLUS_GRAD_WIRE must be f32 or bf16"
-_wire_scratch = {}   # id(chunk) -> device.Buffer (bf16, chunk capacity)
 
 
 def wire_bytes_per_element():
@@ -41,9 +40,9 @@ def wire_bytes_per_element():
 def allreduce_bucket(ch, off, n, stream):
     """Sum-allreduce n gradient elements of arena chunk `ch` starting at element `off`, in place."""
     if WIRE_DTYPE == "bf16":
-        buf = _wire_scratch.get(id(ch))
+        buf = getattr(ch, "wire_scratch", None)   # bf16 staging of the chunk's gradients; lives and dies with the chunk
         if buf is None:
-            buf = _wire_scratch[id(ch)] = device.Buffer(ch.capacity * 2)
+            buf = ch.wire_scratch = device.Buffer(ch.capacity * 2)
         _lib.call("polus_comm_allreduce_bf16", ch.g.ptr + off * 4, buf.ptr + off * 2, n, stream)
     else:
         _lib.call("polus_comm_allreduce_f32", ch.g.ptr + off * 4, n, stream)
@@ -68,6 +67,15 @@ def init(use_device=True):
         return "mock"
     _host_rendezvous_init()
     if use_device:
+        # NCCL's automatic user-buffer registration of collectives captured into CUDA graphs is switched off unless the
+        # user asks for it.  Measured on 2 x B200 (tools/nan_hunt.py, profiles/r02_nan_hunt.txt): with it, a process that
+        # captures a step, frees that model's gradient arena and captures the step of a NEW model (an HPO loop; bench.py's
+        # parity harness followed by the timed model) received garbage through the allreduce in ~60 % of the rebuilt
+        # models whenever NCCL chose the registered path (communicator capped with maxCTAs) -- every weight non-finite
+        # within 15 steps; 0 of 4 with NCCL_GRAPH_REGISTER=0, independent of this library's own stream schedule (early
+        # updates, side-stream wgrads and programmatic launches were each switched off in turn).  NCCL reads the variable
+        # when the communicator is created, i.e. below.
+        os.environ.setdefault("NCCL_GRAPH_REGISTER", "0")
         device.init(local_rank)
         uid = np.zeros(128, np.uint8)
         if rank == 0:
