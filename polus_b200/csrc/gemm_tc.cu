@@ -66,6 +66,7 @@ struct TcParams {
     int c2_grad;      // C2 = act'(pre-activation) instead of the pre-activation
     int has_emul;     // C = (alpha A.B^T + bias) * Emul, Emul read through tmC2
     float* colsum;    // colsum[n] += sum_m C[m,n]
+    int l2_hint;      // L2 evict_first hints: 1 = C2 stores, 2 = C stores, 4 = multiplier-tile loads
 };
 
 template <int BN, int CG>
@@ -380,6 +381,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int e = warp - 4;
         const int quad = e & 3;
         const int csub = e >> 2;
+        const uint64_t pol_ef = ptx::l2_policy_evict_first();
         constexpr int kCPW = (BN / 32) / 4 > 0 ? (BN / 32) / 4 : 1;  // 32-column chunks per warp per tile
         const uint32_t sC = ptx::smem_u32(sStage) + (uint32_t)e * 4096u;  // [32 rows][64 B] C
         const uint32_t sX = sC + 2048u;                                    // [32 rows][64 B] C2 or multiplier
@@ -407,11 +409,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 int mt, nt, sp, b0, b1;
                 decode(t, mt, nt, sp, b0, b1);
                 ptx::mbar_expect_tx(ebar, 2048);
-                asm volatile(
-                    "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                    ::"r"(sX), "l"(reinterpret_cast<uint64_t>(&tmC2)), "r"(ptx::smem_u32(ebar)),
-                    "r"(nt * BN + (csub * kCPW + i) * 32), "r"((mt * CG + (int)cta_rank) * BM + quad * 32), "r"(b0), "r"(b1)
-                    : "memory");
+                if (p.l2_hint & 4) {   // read once, by this warp: evict first
+                    asm volatile(
+                        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+                        ::"r"(sX), "l"(reinterpret_cast<uint64_t>(&tmC2)), "r"(ptx::smem_u32(ebar)),
+                        "r"(nt * BN + (csub * kCPW + i) * 32), "r"((mt * CG + (int)cta_rank) * BM + quad * 32), "r"(b0), "r"(b1), "l"(pol_ef)
+                        : "memory");
+                } else {
+                    asm volatile(
+                        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                        ::"r"(sX), "l"(reinterpret_cast<uint64_t>(&tmC2)), "r"(ptx::smem_u32(ebar)),
+                        "r"(nt * BN + (csub * kCPW + i) * 32), "r"((mt * CG + (int)cta_rank) * BM + quad * 32), "r"(b0), "r"(b1)
+                        : "memory");
+                }
             }
         };
         auto sts16 = [&](uint32_t tile, int chunk, const float* v8) {  // 8 values -> 16-byte chunk `chunk` of row `lane`
@@ -420,9 +430,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile + (uint32_t)lane * 64u + (((uint32_t)chunk ^ swz) << 4)),
                          "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]) : "memory");
         };
-        auto tma_store32 = [&](const CUtensorMap* map, uint32_t tile, int c0, int c1, int c2, int c3) {
-            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                         ::"l"(reinterpret_cast<uint64_t>(map)), "r"(tile), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+        auto tma_store32 = [&](const CUtensorMap* map, uint32_t tile, int c0, int c1, int c2, int c3, bool evict_first) {
+            if (evict_first)
+                asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5}], [%1], %6;"
+                             ::"l"(reinterpret_cast<uint64_t>(map)), "r"(tile), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(pol_ef) : "memory");
+            else
+                asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                             ::"l"(reinterpret_cast<uint64_t>(map)), "r"(tile), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
         };
         int pf_t = tile0, pf_i = -1;
         if (p.has_emul) {
@@ -535,8 +549,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 ptx::fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    tma_store32(&tmC, sC, col0, row0, b0, b1);  // rows >= M / columns >= N are clipped by the tensor map
-                    if (p.has_c2) tma_store32(&tmC2, sX, col0, row0, b0, b1);
+                    tma_store32(&tmC, sC, col0, row0, b0, b1, (p.l2_hint & 2) != 0);  // rows >= M / columns >= N are clipped by the tensor map
+                    if (p.has_c2) tma_store32(&tmC2, sX, col0, row0, b0, b1, (p.l2_hint & 1) != 0);
                     ptx::tma_store_commit();
                 }
                 store_pending = true;
@@ -983,6 +997,8 @@ extern "C" int polus_gemm_tc(const polus_gemm_t* g, void* stream) {
     p.c2_grad = g->c2_kind == 1;
     p.has_emul = g->Emul != nullptr;
     p.colsum = g->colsum;
+    static const int l2_env = getenv("POLUS_GEMM_L2HINT") ? atoi(getenv("POLUS_GEMM_L2HINT")) : 0;
+    p.l2_hint = l2_env;
     p.stg_warp = (p.c_f32 || p.has_c2 || p.has_emul) ? 2 * STG_BLOCK : STG_BLOCK;
     p.n_stages = 0;  // set per instantiation in launch()
 

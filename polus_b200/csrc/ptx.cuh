@@ -102,6 +102,28 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
         ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+// L2 eviction-priority hints (createpolicy): a tensor written for a much later reader -- or read exactly once -- should
+// not push the GEMM's own operands out of the 126 MB L2
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_store_4d_hint(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2, int c3, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5}], [%1], %6;"
+        ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(pol)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_hint(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                                 int c0, int c1, int c2, int c3, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)),
+        "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(pol)
+        : "memory");
+}
 // TMA reduction: global[tile] += smem block (element type from the tensor map; fp32 add done at L2)
 __device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2, int c3) {
     asm volatile(
