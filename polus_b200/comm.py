@@ -67,15 +67,6 @@ def init(use_device=True):
         return "mock"
     _host_rendezvous_init()
     if use_device:
-        # NCCL's automatic user-buffer registration of collectives captured into CUDA graphs is switched off unless the
-        # user asks for it.  Measured on 2 x B200 (tools/nan_hunt.py, profiles/r02_nan_hunt.txt): with it, a process that
-        # captures a step, frees that model's gradient arena and captures the step of a NEW model (an HPO loop; bench.py's
-        # parity harness followed by the timed model) received garbage through the allreduce in ~60 % of the rebuilt
-        # models whenever NCCL chose the registered path (communicator capped with maxCTAs) -- every weight non-finite
-        # within 15 steps; 0 of 4 with NCCL_GRAPH_REGISTER=0, independent of this library's own stream schedule (early
-        # updates, side-stream wgrads and programmatic launches were each switched off in turn).  NCCL reads the variable
-        # when the communicator is created, i.e. below.
-        os.environ.setdefault("NCCL_GRAPH_REGISTER", "0")
         device.init(local_rank)
         uid = np.zeros(128, np.uint8)
         if rank == 0:
@@ -326,23 +317,38 @@ def _tensor_sigs(o, out=None):
 # ------------------------------------------------------------------------------------------------
 # device collectives
 # ------------------------------------------------------------------------------------------------
+def plan_broadcast_spans(variables):
+    """[[ptr, nbytes], ...] in the order the ncclBroadcast calls are issued.
+
+    The sequence of calls (and their sizes) must be the same on every rank.  Device addresses are NOT the same on every
+    rank, so the spans keep the caller's variable order (arena creation order: fp32 masters first, then the bf16
+    shadows) and only neighbours IN THAT ORDER that are also adjacent in memory are merged.  (Round 2: the spans used to
+    be sorted by local address.  Models built after the first one of a process get their buffers from a fragmented free
+    list, the master / shadow / optimizer-slot buffers then come out in a different address order on different ranks,
+    and the ranks paired a 438 MB fp32 span with a 219 MB bf16 one, or Adam's m with v -- garbage weights, or a negative
+    second moment, on the receiving ranks: every weight non-finite a few steps later; profiles/r02_nan_hunt.txt.)"""
+    variables = list(variables)
+    # (ptr, nbytes, owner): spans are merged only inside one allocation (an arena chunk's master or shadow buffer), so
+    # that two allocations which happen to be neighbours on ONE rank cannot change that rank's call sequence
+    spans = [(v.ptr, v.nbytes, ("p", v.chunk.index) if isinstance(v, Param) else ("t", id(getattr(v, "block", None)) or i))
+             for i, v in enumerate(variables)]
+    spans += [(v.shadow.ptr, v.shadow.nbytes, ("pb", v.chunk.index)) for v in variables if isinstance(v, Param)]
+    merged, owner = [], None
+    for ptr, n, own in spans:
+        if merged and own == owner and 0 <= ptr - (merged[-1][0] + merged[-1][1]) <= 256 and (ptr - merged[-1][0]) % 4 == 0:
+            merged[-1][1] = ptr + n - merged[-1][0]
+        else:
+            merged.append([ptr, n])
+            owner = own
+    return merged
+
+
 def broadcast_variables(variables, root_rank=0):
     """hvd.broadcast_variables (polus/training.py:208-211): rank-0 values to every rank.  Adjacent
     arena variables are merged so BERT-base ships in a handful of ncclBroadcast calls."""
     if _state["size"] == 1 or not _state["nccl"]:
         return
-    spans = []
-    for v in variables:
-        spans.append((v.ptr, v.nbytes))
-        if isinstance(v, Param):
-            spans.append((v.shadow.ptr, v.shadow.nbytes))
-    spans.sort()
-    merged = []
-    for ptr, n in spans:
-        if merged and 0 <= ptr - (merged[-1][0] + merged[-1][1]) <= 256 and (ptr - merged[-1][0]) % 4 == 0:
-            merged[-1][1] = ptr + n - merged[-1][0]
-        else:
-            merged.append([ptr, n])
+    merged = plan_broadcast_spans(variables)
     st = device.stream()
     for ptr, n in merged:
         _lib.call("polus_comm_broadcast", ptr, n, root_rank, st)
@@ -357,8 +363,10 @@ def plan_buckets(weights, bucket_bytes=None):
     the step pipelines allreduce(piece i+1) with the optimizer update of piece i instead of one long exposed exchange.
     Returns [(chunk, offset_elems, n_elems, [params])...]."""
     bucket_bytes = bucket_bytes or BUCKET_BYTES
+    # (chunk creation index, offset): the same order on every rank -- id(chunk) is a host address and differs between
+    # processes, which for a model of several chunks (BERT-large dims: three) made the ranks exchange different buckets
     ps = sorted((w for w in {id(w): w for w in weights if isinstance(w, Param)}.values()),
-                key=lambda w: (id(w.chunk), w.offset), reverse=True)
+                key=lambda w: (w.chunk.index, w.offset), reverse=True)
     buckets = []
     cur = None
     for w in ps:

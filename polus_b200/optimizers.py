@@ -156,7 +156,8 @@ class Adam:
     def variables(self):
         """Optimizer slots as (ptr, nbytes) spans -- what broadcast_init_vars ships (training.py:211)."""
         out = []
-        for m, v, _, ch in self._state.values():
+        # chunk creation order: the same on every rank (the dict's insertion order follows host object ids)
+        for m, v, _, ch in sorted(self._state.values(), key=lambda st: st[3].index):
             out.append(Tensor((ch.used,), F32, ptr=m.ptr, block=m))
             out.append(Tensor((ch.used,), F32, ptr=v.ptr, block=v))
         return out
@@ -175,7 +176,7 @@ class Adam:
 
     @staticmethod
     def _contiguous_ranges(weights):
-        spans = sorted(((id(w.chunk), w.offset, (w.size + 63) & ~63, w.chunk) for w in weights if isinstance(w, Param)),
+        spans = sorted(((w.chunk.index, w.offset, (w.size + 63) & ~63, w.chunk) for w in weights if isinstance(w, Param)),
                        key=lambda s: (s[0], s[1]))
         out = []
         for cid, off, n, ch in spans:

@@ -188,7 +188,13 @@ class Tensor:
 # parameter arena
 # ------------------------------------------------------------------------------------------------
 class ArenaChunk:
+    _created = 0
+
     def __init__(self, capacity):
+        # creation order: the rank-invariant sort key for anything that orders chunks across processes (id() and device
+        # addresses differ from rank to rank, and collectives must be issued in the same order everywhere)
+        ArenaChunk._created += 1
+        self.index = ArenaChunk._created
         self.capacity = int(capacity)
         self.used = 0
         self.p = device.Buffer(self.capacity * 4, zero=True)

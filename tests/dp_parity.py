@@ -68,6 +68,7 @@ def run_dp_parity(steps=3, per_rank=4, seq=32, base_lr=1e-3, seed=11, log=None):
     everyone.sort(key=lambda d: d["rank"])
     identical = all(d["digest"] == everyone[0]["digest"] and d["probe"] == everyone[0]["probe"] for d in everyone)
     losses_dp_mean = np.mean([d["losses"] for d in everyone], axis=0)
+    trainer.release_graphs()
     del trainer, model
 
     # ---- arm 2: ONE rank on the whole global batch with lr x N, no collective
@@ -86,6 +87,7 @@ def run_dp_parity(steps=3, per_rank=4, seq=32, base_lr=1e-3, seed=11, log=None):
     rel = float(np.max(np.abs(losses_dp_mean - np.asarray(losses1)) / np.maximum(np.abs(losses1), 1e-12)))
     wdiff = float(max(np.abs(a - b).max() for a, b in zip(w_dp, w_1)))
     wmean = float(sum(np.abs(a - b).sum() for a, b in zip(w_dp, w_1)) / sum(a.size for a in w_dp))
+    trainer1.release_graphs()
     del trainer1, model
     from polus_b200 import tensor
     tensor.reset_arena()

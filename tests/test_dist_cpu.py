@@ -91,3 +91,46 @@ def test_file_rendezvous_fallback(tmp_path):
         o, e = p.communicate(timeout=60)
         assert p.returncode == 0, e[-2000:]
         assert o.strip().splitlines()[-1] == '[["r", 0], ["r", 1]]'
+
+
+def test_broadcast_and_bucket_order_do_not_depend_on_device_addresses():
+    """Collectives must be issued in the same order, with the same sizes, on every rank -- but device addresses (and
+    host object ids) differ from rank to rank.  Two simulated ranks whose master / shadow / optimizer-slot buffers sit in
+    opposite address order must plan identical ncclBroadcast sequences and identical gradient buckets (round 2: spans
+    were sorted by local address and buckets by id(chunk); rebuilt models on >= 2 GPUs went non-finite)."""
+    from polus_b200 import comm
+    from polus_b200.tensor import Param, Tensor, F32, BF16
+
+    class Chunk:
+        def __init__(self, index, base):
+            self.index, self.base = index, base
+
+    def fake_rank(p_bases, pb_bases, g_base, slot_bases, reverse_ids):
+        chunks = [Chunk(1, p_bases[0]), Chunk(2, p_bases[1])]
+        if reverse_ids:
+            chunks = chunks[::-1]          # (only so that id() order differs; .index stays the creation order)
+            chunks.sort(key=lambda c: c.index)
+        params = []
+        sizes = [(1000, 0), (64, 0), (5000, 0), (300, 1), (70000, 1)]     # (elements, chunk)
+        used = [0, 0]
+        for n, c in sizes:
+            w = Param.__new__(Param)
+            Tensor.__init__(w, (n,), F32, ptr=p_bases[c] + used[c] * 4, block=chunks[c])
+            w.chunk, w.offset = chunks[c], used[c]
+            w.shadow = Tensor((n,), BF16, ptr=pb_bases[c] + used[c] * 2, block=chunks[c])
+            w.grad = Tensor((n,), F32, ptr=g_base[c] + used[c] * 4, block=chunks[c])
+            used[c] += (n + 63) & ~63
+            params.append(w)
+        slots = [Tensor((used[0],), F32, ptr=slot_bases[0], block=object()), Tensor((used[0],), F32, ptr=slot_bases[1], block=object())]
+        return params, slots
+
+    GB = 1 << 30
+    a_params, a_slots = fake_rank([10 * GB, 20 * GB], [30 * GB, 40 * GB], [50 * GB, 60 * GB], [70 * GB, 80 * GB], False)
+    b_params, b_slots = fake_rank([20 * GB, 10 * GB], [5 * GB, 2 * GB], [60 * GB, 50 * GB], [80 * GB, 70 * GB], True)
+    sizes = lambda spans: [n for _, n in spans]
+    assert sizes(comm.plan_broadcast_spans(a_params)) == sizes(comm.plan_broadcast_spans(b_params))
+    assert sizes(comm.plan_broadcast_spans(a_slots)) == sizes(comm.plan_broadcast_spans(b_slots))
+    assert len(comm.plan_broadcast_spans(a_params)) == 4            # master + shadow of two chunks, each merged into one span
+    bk = lambda ps: [(ch.index, off, n) for ch, off, n, _ in comm.plan_buckets(ps, bucket_bytes=64 * 1024)]
+    assert bk(a_params) == bk(b_params)
+    assert bk(a_params)[0][0] == 2                                  # the last-created chunk's variables are exchanged first

@@ -19,6 +19,9 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 
+_KEEP = []
+
+
 def nonfinite_report(trainer):
     from polus_b200 import device
     from polus_b200.tensor import Param
@@ -38,12 +41,12 @@ def nonfinite_report(trainer):
     return bad, slots
 
 
-def trial(name, batch, steps, early=True, side=True, check_every=10):
+def trial(name, batch, steps, early=True, side=True, check_every=10, workload="ner_base"):
     from polus_b200 import device, ops, training
     training._EARLY_UPDATE = early
     ops.SIDE_WGRAD = side
     rank = int(os.environ.get("RANK", "0"))
-    trainer, batches, _, _, _ = bench.build_workload("ner_base", batch)
+    trainer, batches, _, _, _ = bench.build_workload(workload, batch)
     t0 = time.time()
     for i in range(5):
         loss = trainer.train_step(*batches[i % len(batches)])
@@ -55,7 +58,7 @@ def trial(name, batch, steps, early=True, side=True, check_every=10):
     first_bad = None
     if any_rank_bad(float(loss)):
         first_bad = 4
-    if trainer.use_horovod:
+    if trainer.use_horovod and os.environ.get("NANHUNT_NOBCAST") != "1":
         trainer.broadcast_init_vars()
     dev = bench.to_device(batches)
     i = 0
@@ -74,7 +77,11 @@ def trial(name, batch, steps, early=True, side=True, check_every=10):
         out["bad_first"] = bad[:6]
         out["bad_last"] = bad[-6:]
         out["slots_nonfinite"] = slots
-    trainer.release_graphs()
+    if os.environ.get("NANHUNT_KEEP") == "1":      # never free anything a previous model owned (arena, slots, graphs)
+        from polus_b200 import tensor as _t
+        _KEEP.append((trainer, dev, _t.arena()))
+    else:
+        trainer.release_graphs()
     del trainer, dev
     print("NANHUNT " + json.dumps(out), flush=True)
     return first_bad
@@ -90,8 +97,10 @@ def main():
     polus_b200.PolusContext()
     variants = os.environ.get("NANHUNT_VARIANTS", "base,base,base,noearly,noearly,noside,noside").split(",")
     for k, v in enumerate(variants):
-        trial(f"{v}#{k}", batch, steps, early=(v != "noearly" and v != "neither"), side=(v != "noside" and v != "neither"),
-              check_every=int(os.environ.get("NANHUNT_CHECK_EVERY", "10")))
+        v, _, wl = v.partition(":")            # "base:cfg4" = default schedule on bench.py's cfg4 workload
+        wl, _, wb = (wl or "ner_base").partition("@")   # "base:cfg5@32" = ... at batch 32
+        trial(f"{v}:{wl}#{k}", int(wb) if wb else batch, steps, early=(v != "noearly" and v != "neither"), side=(v != "noside" and v != "neither"),
+              check_every=int(os.environ.get("NANHUNT_CHECK_EVERY", "10")), workload=wl)
     sys.stdout.flush()
     os._exit(0)
 
