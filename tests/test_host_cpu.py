@@ -264,7 +264,7 @@ def test_gradient_bucket_plan():
     from polus_b200.tensor import Param
 
     class Chunk:
-        pass
+        index = 1   # creation order: plan_buckets' rank-invariant sort key
     ch = Chunk()
     ps, off = [], 0
     for n in [1000, 64, 5000, 64, 300000, 64, 128]:
