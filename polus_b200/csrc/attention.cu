@@ -51,6 +51,7 @@ struct AttnParams {
     const uint32_t* ready;   // [2] ready[s & 1] == s + 1: the buffer of step s was filled ahead of time by
                              // attn_keepbits_kernel (polus_attention_keepbits); null / mismatch: the forward draws them itself
     float* gbias;          // backward: [3H] bias gradient of the QKV projection += column sums of dqkv; may be null
+    int pf_stride;         // backward: CTA i warms the L2 with the tiles of CTA i + pf_stride (0 = off)
 };
 
 // keep-bit buffer of the step that is running (double-buffered on the parity of the step counter when `keepbits_alt` is set)
@@ -608,6 +609,34 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             if (ok[1]) L1 = p.lse[(long long)(b * p.nh + h) * p.S + qbase + 128 + row];
             ptx::mbar_wait(&bars[0], 0);
         }
+        // One CTA per SM: every CTA of a wave starts together and their 176 KB prologues are HBM-bound while the tensor
+        // cores idle; then HBM idles while they compute (profiles/r01_attn_bwd_timeline_v11.txt).  Once this CTA's first
+        // load group has landed, one thread asks the TMA unit to pull the tiles of the CTA that runs one wave later
+        // (block index + number of SMs) into L2: that traffic runs under this CTA's arithmetic, and the later CTA's
+        // prologue is served from L2.
+        if (t == 0 && p.pf_stride > 0) {
+            const long long nbk = (long long)blockIdx.x + p.pf_stride;
+            if (nbk < (long long)gridDim.x) {
+                const int nb = (int)nbk;
+                const int nqh = nb % n_half, nh_ = (nb / n_half) % p.nh, nbb = nb / (n_half * p.nh);
+                const int nq0 = nqh * 256;
+                const int nqt = min(2, (p.S - nq0 + 127) / 128);
+                ptx::tma_prefetch_l2_4d(&tmQKV, 0, nq0, nh_, nbb);
+                ptx::tma_prefetch_l2_4d(&tmQKV, 0, 0, p.nh + nh_, nbb);
+                ptx::tma_prefetch_l2_4d(&tmDO, 0, nq0, nh_, nbb);
+                ptx::tma_prefetch_l2_4d(&tmQKV, 0, 0, 2 * p.nh + nh_, nbb);
+                ptx::tma_prefetch_l2_4d(&tmO, 0, nq0, nh_, nbb);
+                if (nqt > 1) {
+                    ptx::tma_prefetch_l2_4d(&tmQKV, 0, nq0 + 128, nh_, nbb);
+                    ptx::tma_prefetch_l2_4d(&tmDO, 0, nq0 + 128, nh_, nbb);
+                    ptx::tma_prefetch_l2_4d(&tmO, 0, nq0 + 128, nh_, nbb);
+                }
+                if (n_kh > 1) {
+                    ptx::tma_prefetch_l2_4d(&tmQKV, 0, 128, p.nh + nh_, nbb);
+                    ptx::tma_prefetch_l2_4d(&tmQKV, 0, 128, 2 * p.nh + nh_, nbb);
+                }
+            }
+        }
         // delta_row = sum_d dO[row,d] * O[row,d]: the four threads sharing a row split the 64 columns (two 16-byte chunks
         // each) of the swizzled dO / O tiles and exchange their quarters through shared memory
         auto delta_part = [&](const uint8_t* o_tile, const uint8_t* do_tile, int i) {
@@ -888,6 +917,7 @@ AttnParams make_params(int B, int S, int nh, float p_drop, uint64_t seed, uint32
     p.gbias = gbias;
     p.keepbits_alt = keepbits_alt;
     p.ready = ready;
+    p.pf_stride = 0;
     return p;
 }
 
@@ -970,6 +1000,8 @@ extern "C" int polus_attention_bwd(const polus_bf16_t* qkv, const int32_t* mask,
     POLUS_REQUIRE(p_drop == 0.f || d_step != nullptr, "polus_attention_bwd: dropout needs d_step");
     AttnParams p = make_params(B, S, nh, p_drop, seed, site, d_step, mask, const_cast<float*>(lse), const_cast<uint32_t*>(keepbits), gbias_qkv,
                                const_cast<uint32_t*>(keepbits_alt), nullptr);
+    static const int pf_env = getenv("POLUS_ATTN_PREFETCH") ? atoi(getenv("POLUS_ATTN_PREFETCH")) : 1;
+    p.pf_stride = pf_env > 0 ? pf_env * polus_num_sms() : 0;   // CTA i warms the L2 for CTA i + (number of SMs): one wave ahead
     const int n_half = (S + 255) / 256;
     if (n_half > 1) {
         // two CTAs per head (one per 256-query half) add their dK / dV partial sums into dqkv with bf16 TMA reduce-adds:

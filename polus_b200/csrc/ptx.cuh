@@ -124,6 +124,11 @@ __device__ __forceinline__ void tma_load_4d_hint(void* smem_dst, const CUtensorM
         "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(pol)
         : "memory");
 }
+// TMA prefetch of one box into L2 (no shared-memory destination, no barrier): warms the L2 for a load that a LATER CTA will issue
+__device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 // TMA reduction: global[tile] += smem block (element type from the tensor map; fp32 add done at L2)
 __device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2, int c3) {
     asm volatile(
