@@ -70,3 +70,24 @@ def test_product_path_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, os.path.join(dirpath, f)
+
+
+def test_product_path_never_imports_torch():
+    """north_star: "no PyTorch" -- device memory, streams, graphs and NCCL are driven from libpolus_b200.so and the
+    host-side rendezvous is a stdlib socket store (polus_b200/comm.py).  Neither the package sources nor a process that
+    has imported every module of it may pull torch in."""
+    import subprocess
+    import sys
+    pkg = os.path.join(ROOT, "polus_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import torch" not in text and "from torch" not in text, os.path.join(dirpath, f)
+    code = ("import sys, pkgutil, importlib, polus_b200\n"
+            "for m in pkgutil.walk_packages(polus_b200.__path__, 'polus_b200.'):\n"
+            "    if 'libpolus' not in m.name: importlib.import_module(m.name)\n"
+            "import polus\n"
+            "assert 'torch' not in sys.modules, 'torch was imported'\n")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
