@@ -271,8 +271,11 @@ ln_res_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, con
 // row, waits out the DRAM latency, computes, and only then asks for its next row.  Here each warp owns two shared-memory
 // row slots (dy | dy2 | z, 3 x 2H bytes); lane 0 posts the bulk copies of row k+1 before the warp starts on row k, so a
 // CTA keeps 2 x 8 rows in flight without a single extra register and the loads overlap the arithmetic.
+// NC = 4 (H = 1024, the BERT-large-sized configuration): 137 KB of shared memory per CTA, one CTA per SM, and therefore the
+// whole register file for its 256 threads -- the register-resident kernel needs ~250 registers per thread for four
+// column chunks and spilled 520 bytes per thread under its two-CTA bound (csrc/build/layernorm.ptxas.log, round 1).
 template <int NC>
-__global__ void __launch_bounds__(kWarps * 32, 2)
+__global__ void __launch_bounds__(kWarps * 32, NC <= 3 ? 2 : 1)
 ln_res_bwd_pf_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, const bf16* __restrict__ z, const float* __restrict__ mean_in,
                      const float* __restrict__ rstd_in, const float* __restrict__ gamma, int M, DropCfg dc,
                      const uint32_t* __restrict__ d_step, bf16* __restrict__ dx, bf16* __restrict__ dres,
@@ -687,7 +690,7 @@ extern "C" int polus_ln_res_bwd(const polus_bf16_t* dy, const polus_bf16_t* dy2,
     static const bool pf_env = !(getenv("POLUS_LN_PREFETCH") && atoi(getenv("POLUS_LN_PREFETCH")) == 0);
     const bool aligned = ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dy2) | reinterpret_cast<uintptr_t>(z) |
                            reinterpret_cast<uintptr_t>(keepbits)) & 15) == 0;
-    if (pf_env && aligned && (H == 768 || H == 512 || H == 256)) {
+    if (pf_env && aligned && (H == 1024 || H == 768 || H == 512 || H == 256)) {
         const size_t smem_pf = (size_t)(kWarps + 1) * H * sizeof(float) + (size_t)kWarps * 2 * (3 * H * 2 + 128) + kWarps * 2 * sizeof(uint64_t);
 #define LN_BWD_PF(NC_)                                                                                                          \
     {                                                                                                                          \
@@ -696,7 +699,7 @@ extern "C" int polus_ln_res_bwd(const polus_bf16_t* dy, const polus_bf16_t* dy2,
         POLUS_CHECK_CUDA(polus_launch_pdl(ln_res_bwd_pf_kernel<NC_>, dim3(grid), dim3(kWarps * 32), smem_pf, st, (const bf16*)dy, (const bf16*)dy2, (const bf16*)z, mean, rstd, gamma, M, dc, \
                                           d_step, (bf16*)dx, (bf16*)dres, ggamma, gbeta, gbias_x, keepbits));                  \
     }
-        if (H == 768) LN_BWD_PF(3) else if (H == 512) LN_BWD_PF(2) else LN_BWD_PF(1)
+        if (H == 1024) LN_BWD_PF(4) else if (H == 768) LN_BWD_PF(3) else if (H == 512) LN_BWD_PF(2) else LN_BWD_PF(1)
 #undef LN_BWD_PF
         g_launch_count++;
         POLUS_LAUNCH_CHECK();

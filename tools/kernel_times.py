@@ -14,7 +14,11 @@ from polus_b200 import _lib, device, ops  # noqa: E402
 from polus_b200.tensor import BF16, F32, I32, U8, Tensor  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
-S, H, NH, I = 256, 768, 12, 3072
+# KT_H / KT_S: other hidden sizes and sequence lengths (H = 1024, S = 512: the BERT-large-sized configuration);
+# KT_ONLY=ln: stop after the LayerNorm kernels
+H = int(os.environ.get("KT_H", "768"))
+S = int(os.environ.get("KT_S", "256"))
+NH, I = H // 64, 4 * H
 M = B * S
 NSETS, REPS = 6, 5
 device.init(0)
@@ -77,6 +81,8 @@ for p_drop in (0.1, 0.0):
     report(f"ln_res_bwd p={p_drop} (dy, dy2, z -> dx, dres)", us, M * H * (10 if p_drop else 8))
     del xs, rs, ys, dxs, drs, keep
 
+if os.environ.get("KT_ONLY") == "ln":
+    sys.exit(0)
 # attention
 for p_drop in (0.1, 0.0):
     qkv = [rnd((B, S, 3 * H)) for _ in range(NSETS)]
