@@ -19,13 +19,10 @@ from polus_b200.utils import set_random_seed  # noqa: E402
 
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 device.init(0)
-set_random_seed(42)
-cfg = BertConfig()
-model = BertNERModel(cfg, output_classes=4)
-trainer = ClassifierTrainer(model, Adam(warmup_scheduler(10000, 5e-5)), model.loss)
-batches = bench.synthetic_batches(2, batch, 256, cfg.vocab_size, 4, seed=1)
+workload = os.environ.get("PS_WORKLOAD", "ner_base")   # ner_base | cfg4 | cfg5 (bench.build_workload)
+trainer, batches, _, label, _ = bench.build_workload(workload, batch)
 for i in range(3):
-    float(trainer.train_step(*batches[i % 2]))
+    float(trainer.train_step(*batches[i % len(batches)]))
 e0, e1 = C.c_void_p(), C.c_void_p()
 _lib.call("polus_event_create", C.byref(e0)); _lib.call("polus_event_create", C.byref(e1))
 device.device_sync()
@@ -38,4 +35,4 @@ device.device_sync()
 _lib.call("polus_profiler_stop")
 ms = C.c_float()
 _lib.call("polus_event_elapsed_ms", e0, e1, C.byref(ms))
-print(f"profiled step (op-by-op, batch {batch}): {ms.value:.3f} ms, loss {float(loss):.4f}")
+print(f"profiled step (op-by-op, {label}): {ms.value:.3f} ms, loss {float(loss):.4f}")
