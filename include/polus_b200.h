@@ -41,7 +41,8 @@ typedef enum {
     POLUS_ACT_SWISH = 3, /* polus/ner/models.py:30 */
     POLUS_ACT_TANH = 4, /* HF BertPooler */
     POLUS_ACT_MISH = 5, /* polus/models.py:53-57 */
-    POLUS_ACT_DERIV = 100 /* polus_act_bwd_colsum only: `z` already holds act'(pre-activation) (polus_gemm_t.c2_kind = 1) */
+    POLUS_ACT_DERIV = 100, /* polus_act_bwd_colsum only: `z` already holds act'(pre-activation) (polus_gemm_t.c2_kind = 1) */
+    POLUS_ACT_DERIV_U8 = 101 /* ... as 8-bit fixed point, one byte per element: gelu' = (q - 28) * 0.005 (c2_kind = 2) */
 } polus_act_t;
 
 /* ---------------------------------------------------------------- runtime / memory ---------- */
@@ -116,8 +117,11 @@ typedef struct {
      * layout as C, multiplies the result element-wise, C = (alpha A.B^T + bias) * Emul, and colsum[n] += sum_m C[m,n]
      * accumulates the bias gradient (fp32 atomics) -- the tf.GradientTape ops GeluGrad + BiasAddGrad of
      * polus/training.py:185 without a pass over the [M,N] tensor. */
-    int32_t c2_kind;    /* 0: C2 = pre-activation, 1: C2 = activation derivative */
-    const void* Emul;   /* optional bf16 [M,N] (ldc/cbs0/cbs1 as C); requires act == NONE, no C2 */
+    int32_t c2_kind;    /* 0: C2 = pre-activation, 1: C2 = activation derivative (bf16), 2: C2 (GELU forward) / Emul (the
+                         * dgrad that consumes it) = gelu' as 8-bit fixed point, one byte per element, row pitch ldc BYTES,
+                         * q = 28 + round(200 gelu'): half the bytes of these two store-bandwidth-bound GEMMs; supported
+                         * where polus_gemm_tc_supported says so (256-wide pair tiles, N % 32 == 0, ldc % 16 == 0) */
+    const void* Emul;   /* optional [M,N] multiplier, bf16 (or 8-bit, c2_kind = 2), ldc/cbs0/cbs1 as C; requires act == NONE, no C2 */
     float* colsum;      /* optional fp32 [N] */
 } polus_gemm_t;
 

@@ -12,6 +12,7 @@ LIB_PATH = os.environ.get("POLUS_LIB") or os.path.join(_HERE, "libpolus_b200.so"
 F32, BF16, I32, U8 = 0, 1, 2, 3
 ACT = {None: 0, "linear": 0, "none": 0, "gelu": 1, "relu": 2, "swish": 3, "silu": 3, "tanh": 4, "mish": 5}
 ACT_DERIV = 100  # polus_act_bwd_colsum: `z` already holds act'(pre-activation) (written by the forward GEMM, c2_kind = 1)
+ACT_DERIV_U8 = 101  # ... as 8-bit fixed point (c2_kind = 2)
 UNARY = {"exp": 16, "log": 17, "softplus": 18, "sigmoid": 19, "neg": 20, "square": 21, "scale": 22,
          "gelu": 1, "relu": 2, "swish": 3, "tanh": 4, "mish": 5, "identity": 0}
 

@@ -255,6 +255,24 @@ __device__ __forceinline__ void gelu_fwd_grad2(float2 x, float2& y, float2& d) {
     d = fma2(x, e, cdf);
 }
 
+// ---- gelu' as 8-bit fixed point (polus_gemm_t.c2_kind = 2).  gelu'(x) lies in [-0.1290, 1.1290]; q = 28 + round(200 x)
+// lies in [2, 254], step 0.005: the same aggregate gradient error as a bf16 copy (relative 2^-9 at |x| ~ 1) at half the
+// bytes -- the two GEMMs that write / read this tensor are bound by SM store bandwidth and multiplier-tile traffic
+// (DESIGN.md section 8).  Encode: one FMA against 1.5 * 2^23 + 28 leaves q in the low mantissa byte (round to nearest
+// even done by the FMA); decode: the byte is dropped into the mantissa of 1.5 * 2^23, one subtract, one multiply.
+constexpr float kD8Scale = 200.0f, kD8Step = 0.005f, kD8Magic = 12582912.0f, kD8Bias = 28.0f;
+__device__ __forceinline__ uint32_t d8_pack4(float a, float b, float c, float d) {
+    const uint32_t ya = __float_as_uint(fmaf(a, kD8Scale, kD8Magic + kD8Bias)), yb = __float_as_uint(fmaf(b, kD8Scale, kD8Magic + kD8Bias));
+    const uint32_t yc = __float_as_uint(fmaf(c, kD8Scale, kD8Magic + kD8Bias)), yd = __float_as_uint(fmaf(d, kD8Scale, kD8Magic + kD8Bias));
+    return __byte_perm(__byte_perm(ya, yb, 0x0040), __byte_perm(yc, yd, 0x0040), 0x5410);
+}
+__device__ __forceinline__ void d8_unpack4(uint32_t w, float* out) {
+    out[0] = (__uint_as_float(__byte_perm(w, 0x4B400000u, 0x7650)) - (kD8Magic + kD8Bias)) * kD8Step;
+    out[1] = (__uint_as_float(__byte_perm(w, 0x4B400000u, 0x7651)) - (kD8Magic + kD8Bias)) * kD8Step;
+    out[2] = (__uint_as_float(__byte_perm(w, 0x4B400000u, 0x7652)) - (kD8Magic + kD8Bias)) * kD8Step;
+    out[3] = (__uint_as_float(__byte_perm(w, 0x4B400000u, 0x7653)) - (kD8Magic + kD8Bias)) * kD8Step;
+}
+
 // activations (polus_act_t)
 __device__ __forceinline__ float act_fwd(int act, float x) {
     switch (act) {

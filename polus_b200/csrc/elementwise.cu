@@ -32,7 +32,12 @@ act_bwd_colsum_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, i
                 if (rr < r1) {
                     const long long off = (long long)rr * N + col;
                     gq[u] = ld_stream8(dy + off);
-                    if (act != POLUS_ACT_NONE) zq[u] = ld_stream8(z + off);
+                    if (act == POLUS_ACT_DERIV_U8) {   // 8 one-byte derivatives (polus_gemm_t.c2_kind = 2): the first two words
+                        const uint2 w = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(z) + off));
+                        uint32_t* zu = reinterpret_cast<uint32_t*>(&zq[u]);
+                        zu[0] = w.x;
+                        zu[1] = w.y;
+                    } else if (act != POLUS_ACT_NONE) zq[u] = ld_stream8(z + off);
                 }
             }
 #pragma unroll
@@ -41,7 +46,14 @@ act_bwd_colsum_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, i
                 if (rr < r1) {
                     float g[8];
                     unpack8(gq[u], g);
-                    if (act != POLUS_ACT_NONE) {
+                    if (act == POLUS_ACT_DERIV_U8) {
+                        float zv[8];
+                        const uint32_t* zu = reinterpret_cast<const uint32_t*>(&zq[u]);
+                        d8_unpack4(zu[0], zv);
+                        d8_unpack4(zu[1], zv + 4);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) g[j] *= zv[j];
+                    } else if (act != POLUS_ACT_NONE) {
                         float zv[8];
                         unpack8(zq[u], zv);
 #pragma unroll

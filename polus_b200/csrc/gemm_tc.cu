@@ -67,6 +67,7 @@ struct TcParams {
     int has_emul;     // C = (alpha A.B^T + bias) * Emul, Emul read through tmC2
     float* colsum;    // colsum[n] += sum_m C[m,n]
     int l2_hint;      // L2 evict_first hints: 1 = C2 stores, 2 = C stores, 4 = multiplier-tile loads
+    int c2_u8;        // C2 (forward) / Emul (backward) holds gelu' as 8-bit fixed point (common.cuh d8_pack4): 16-warp kernel only
 };
 
 template <int BN, int CG>
@@ -222,7 +223,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* tfull_bar = empty_bar + kMaxStages;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint64_t* emul_bar = tempty_bar + 2;  // [epilogue warp]: Emul tile landed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(emul_bar + 2 * kEpiWarps);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(emul_bar + 4 * kEpiWarps);  // (16-warp kernel, 8-bit multipliers: two barriers per warp)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -242,7 +243,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ptx::mbar_init(&tfull_bar[s], 1);
             ptx::mbar_init(&tempty_bar[s], (EPI == 16 ? 16 : C::kEpiActive) * CG);  // one arrive per working epilogue warp of the group
         }
-        for (int s = 0; s < 2 * kEpiWarps; ++s) ptx::mbar_init(&emul_bar[s], 1);
+        for (int s = 0; s < 4 * kEpiWarps; ++s) ptx::mbar_init(&emul_bar[s], 1);
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
@@ -386,7 +387,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t sC = ptx::smem_u32(sStage) + (uint32_t)e * 4096u;  // [32 rows][64 B] C
         const uint32_t sX = sC + 2048u;                                    // [32 rows][64 B] C2 or multiplier
         const uint32_t swz = (uint32_t)((lane >> 1) & 3);                 // 64B swizzle: 16-byte chunk index ^ (row/2)%4
-        uint64_t* ebar = &emul_bar[e];
         int acc = 0;
         uint32_t acc_phase = 0;
         bool store_pending = false;
@@ -404,21 +404,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 i = 0;
             }
         };
-        auto emul_issue = [&](int t, int i) {
+        // Multiplier tiles.  bf16: one 2 KB tile per warp, fetched one block ahead.  8-bit: the same 2 KB hold TWO 1 KB
+        // tiles with a barrier each, fetched two blocks ahead -- the bf16 path waits on this load at every block (halving
+        // its bytes alone changed nothing: 157.0 vs 156.3 us, profiles/r02_gemm_d8.log).
+        auto emul_issue = [&](int t, int i, int buf) {
             if (lane == 0) {
                 int mt, nt, sp, b0, b1;
                 decode(t, mt, nt, sp, b0, b1);
-                ptx::mbar_expect_tx(ebar, 2048);
+                uint64_t* ebar = &emul_bar[buf * 16 + e];
+                const uint32_t dstX = sX + (uint32_t)buf * 1024u;
+                ptx::mbar_expect_tx(ebar, p.c2_u8 ? 1024 : 2048);   // 32 x 32 multipliers, bf16 or 8-bit
                 if (p.l2_hint & 4) {   // read once, by this warp: evict first
                     asm volatile(
                         "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
-                        ::"r"(sX), "l"(reinterpret_cast<uint64_t>(&tmC2)), "r"(ptx::smem_u32(ebar)),
+                        ::"r"(dstX), "l"(reinterpret_cast<uint64_t>(&tmC2)), "r"(ptx::smem_u32(ebar)),
                         "r"(nt * BN + (csub * kCPW + i) * 32), "r"((mt * CG + (int)cta_rank) * BM + quad * 32), "r"(b0), "r"(b1), "l"(pol_ef)
                         : "memory");
                 } else {
                     asm volatile(
                         "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                        ::"r"(sX), "l"(reinterpret_cast<uint64_t>(&tmC2)), "r"(ptx::smem_u32(ebar)),
+                        ::"r"(dstX), "l"(reinterpret_cast<uint64_t>(&tmC2)), "r"(ptx::smem_u32(ebar)),
                         "r"(nt * BN + (csub * kCPW + i) * 32), "r"((mt * CG + (int)cta_rank) * BM + quad * 32), "r"(b0), "r"(b1)
                         : "memory");
                 }
@@ -441,7 +446,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int pf_t = tile0, pf_i = -1;
         if (p.has_emul) {
             advance(pf_t, pf_i);
-            if (pf_t < p.num_tiles) emul_issue(pf_t, pf_i);
+            if (pf_t < p.num_tiles) emul_issue(pf_t, pf_i, 0);
+            if (p.c2_u8) {
+                advance(pf_t, pf_i);
+                if (pf_t < p.num_tiles) emul_issue(pf_t, pf_i, 1);
+            }
         }
         for (int t = tile0; t < p.num_tiles; t += tile_step) {
             int mt, nt, sp, b0, b1;
@@ -487,13 +496,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 v[4 * j + 3] += bv.w;
                             }
                         }
+                        uint32_t dq[4];  // 8-bit derivative: this half's 16 values = one 16-byte store into the [32][32 B] tile
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {
                             float d8[8];
                             act_fwd_grad8(p.act, v + 8 * j, d8);
-                            sts16(sX, sub * 2 + j, d8);
+                            if (p.c2_u8) {
+                                dq[2 * j] = d8_pack4(d8[0], d8[1], d8[2], d8[3]);
+                                dq[2 * j + 1] = d8_pack4(d8[4], d8[5], d8[6], d8[7]);
+                            } else {
+                                sts16(sX, sub * 2 + j, d8);
+                            }
                             sts16(sC, sub * 2 + j, v + 8 * j);
                         }
+                        if (p.c2_u8)
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sX + (uint32_t)lane * 32u + (uint32_t)sub * 16u),
+                                         "r"(dq[0]), "r"(dq[1]), "r"(dq[2]), "r"(dq[3]) : "memory");
                     }
                 } else {
                     float v[32];
@@ -521,7 +539,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                     if (p.has_emul) {
-                        ptx::mbar_wait(ebar, (uint32_t)nblk & 1u);
+                        const int ebuf = p.c2_u8 ? (nblk & 1) : 0;
+                        ptx::mbar_wait(&emul_bar[ebuf * 16 + e], p.c2_u8 ? (((uint32_t)nblk >> 1) & 1u) : ((uint32_t)nblk & 1u));
+                        if (p.c2_u8) {   // [32 rows][32 bytes], not swizzled: row `lane` = two 16-byte loads
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                uint32_t u[4];
+                                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3])
+                                             : "r"(sX + (uint32_t)ebuf * 1024u + (uint32_t)lane * 32u + (uint32_t)j * 16u));
+#pragma unroll
+                                for (int w = 0; w < 4; ++w) {
+                                    float m4[4];
+                                    d8_unpack4(u[w], m4);
+#pragma unroll
+                                    for (int x = 0; x < 4; ++x) v[16 * j + 4 * w + x] *= m4[x];
+                                }
+                            }
+                        } else {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             bf16x8 q;
@@ -533,9 +567,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                             for (int x = 0; x < 8; ++x) v[8 * j + x] *= m8[x];
                         }
+                        }
                         __syncwarp();  // every lane has its multipliers: the tile may be refilled
                         advance(pf_t, pf_i);
-                        if (pf_t < p.num_tiles) emul_issue(pf_t, pf_i);
+                        if (pf_t < p.num_tiles) emul_issue(pf_t, pf_i, ebuf);
                     } else {
                         if (p.has_c2) {
 #pragma unroll
@@ -797,8 +832,9 @@ int encode_map(CUtensorMap* map, const void* ptr, long long inner, long long row
     strides[0] = (cuuint64_t)ld * esize;
     strides[1] = (cuuint64_t)(batch0 > 1 ? bs0 * esize : rows * ld * esize);
     strides[2] = (cuuint64_t)(batch1 > 1 ? bs1 * esize : strides[1] * (cuuint64_t)batch0);
-    CUresult r = enc(map, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, box_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+    CUresult r = enc(map, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (esize == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), 4,
+                     const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     box_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_NONE : (box_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B),
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         polus_set_error("cuTensorMapEncodeTiled failed (%d): ptr=%p inner=%lld rows=%lld ld=%lld b0=%d/%lld b1=%d/%lld",
@@ -895,7 +931,19 @@ const char* why_unsupported(const polus_gemm_t* g) {
     if (g->Emul && (g->c_dtype != POLUS_BF16 || g->C2 || g->act != POLUS_ACT_NONE || !aligned16(g->Emul)))
         return "Emul requires bf16 C, no C2 and no activation";
     if (g->colsum && g->c_dtype != POLUS_BF16) return "colsum requires bf16 C";
-    if (g->c2_kind != 0 && g->c2_kind != 1) return "c2_kind";
+    if (g->c2_kind < 0 || g->c2_kind > 2) return "c2_kind";
+    if (g->c2_kind == 2) {
+        // 8-bit gelu' (C2 of a GELU forward, or the Emul tile of the dgrad that consumes it): only the 16-epilogue-warp
+        // kernel on 256-wide pair tiles implements it -- the same conditions as the dispatch in polus_gemm_tc
+        static const int epi_env = getenv("POLUS_GEMM_EPI16") ? atoi(getenv("POLUS_GEMM_EPI16")) : 1;
+        static const int cg_env = getenv("POLUS_GEMM_CG") ? atoi(getenv("POLUS_GEMM_CG")) : 0;
+        const int b0 = g->batch0 < 1 ? 1 : g->batch0, b1 = g->batch1 < 1 ? 1 : g->batch1;
+        if (!epi_env || cg_env == 1) return "8-bit derivative needs the 16-warp pair kernel";
+        if (!(g->C2 != nullptr && g->act == POLUS_ACT_GELU) && g->Emul == nullptr) return "8-bit derivative: GELU forward with C2, or Emul";
+        if (g->c_dtype != POLUS_BF16 || g->A.mn_major || g->M <= BM || g->N <= 128 || g->N % 32) return "8-bit derivative: shape";
+        if ((long long)cdiv(g->M, 2 * BM) * cdiv(g->N, 256) * b0 * b1 * 2 < polus_num_sms()) return "8-bit derivative: needs 256-wide tiles";
+        if (g->ldc % 16 || g->cbs0 % 16 || g->cbs1 % 16) return "8-bit derivative: strides must be multiples of 16";
+    }
     return nullptr;
 }
 
@@ -994,11 +1042,12 @@ extern "C" int polus_gemm_tc(const polus_gemm_t* g, void* stream) {
     p.c_f32 = g->c_dtype == POLUS_F32;
     p.accumulate = g->accumulate;
     p.has_c2 = g->C2 != nullptr;
-    p.c2_grad = g->c2_kind == 1;
+    p.c2_grad = g->c2_kind >= 1;
     p.has_emul = g->Emul != nullptr;
     p.colsum = g->colsum;
     static const int l2_env = getenv("POLUS_GEMM_L2HINT") ? atoi(getenv("POLUS_GEMM_L2HINT")) : 0;
     p.l2_hint = l2_env;
+    p.c2_u8 = g->c2_kind == 2;
     p.stg_warp = (p.c_f32 || p.has_c2 || p.has_emul) ? 2 * STG_BLOCK : STG_BLOCK;
     p.n_stages = 0;  // set per instantiation in launch()
 
@@ -1032,12 +1081,15 @@ extern "C" int polus_gemm_tc(const polus_gemm_t* g, void* stream) {
         if (rc) return rc;
         tc2 = tc;
         if (p.has_c2 || p.has_emul) {
-            rc = encode_map(&tc2, p.has_c2 ? g->C2 : const_cast<void*>(g->Emul), g->N, g->M, g->ldc, batch0, g->cbs0, batch1, g->cbs1, 32, 2, 64);
+            void* x2 = p.has_c2 ? g->C2 : const_cast<void*>(g->Emul);
+            if (p.c2_u8) rc = encode_map(&tc2, x2, g->N, g->M, g->ldc, batch0, g->cbs0, batch1, g->cbs1, 32, 1, 32);  // [32][32 B] boxes, no swizzle
+            else rc = encode_map(&tc2, x2, g->N, g->M, g->ldc, batch0, g->cbs0, batch1, g->cbs1, 32, 2, 64);
             if (rc) return rc;
         }
         if (g->B.mn_major) return launch<256, false, true, 2, 16>(ta, tb, tc, tc2, p, st);
         return launch<256, false, false, 2, 16>(ta, tb, tc, tc2, p, st);
     }
+    POLUS_REQUIRE(!p.c2_u8, "polus_gemm_tc: the 8-bit derivative needs the 16-warp pair kernel (M=%d N=%d K=%d)", g->M, g->N, g->K);
     if (cl4) {
         if (g->B.mn_major) return launch<256, false, true, 2, 8, 4>(ta, tb, tc, tc2, p, st);
         return launch<256, false, false, 2, 8, 4>(ta, tb, tc, tc2, p, st);

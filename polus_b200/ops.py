@@ -405,6 +405,24 @@ def _gemm(M, N, K, A, B, c_ptr, ldc, c_dtype, bias=None, act=0, c2=None, alpha=1
     return "tc" if use_tc else "small"
 
 
+def _gemm_tc_supported(M, N, K, A, B, c_ptr, ldc, c_dtype, **kw):
+    """Would polus_gemm_tc take this problem?  (Same fields as _gemm; used to choose the 8-bit derivative format.)"""
+    g = _lib.Gemm()
+    g.M, g.N, g.K, g.batch0, g.batch1 = M, N, K, 1, 1
+    g.A, g.B = A, B
+    g.C, g.ldc, g.cbs0, g.cbs1, g.c_dtype = c_ptr, ldc, 0, 0, c_dtype
+    g.C2, g.bias = kw.get("c2"), kw.get("bias")
+    g.alpha, g.act, g.accumulate, g.split_k = 1.0, kw.get("act", 0), 0, 1
+    g.c2_kind, g.Emul, g.colsum = kw.get("c2_kind", 0), kw.get("emul"), kw.get("colsum")
+    return _lib.call("polus_gemm_tc_supported", C.byref(g)) == 1
+
+
+# gelu' stored as 8-bit fixed point by the FFN-up GEMM and read back by the dgrad GEMM of the next layer (c2_kind = 2):
+# both are bound by SM store bandwidth / multiplier-tile traffic, and a byte per element carries the same aggregate
+# gradient error as bf16 (DESIGN.md section 8).  POLUS_GELU_D8=0 keeps the bf16 copy.
+GELU_D8 = _os.environ.get("POLUS_GELU_D8", "1") != "0"
+
+
 def _act_code(act):
     if callable(act):
         act = getattr(act, "__name__", None)
@@ -431,12 +449,20 @@ def linear(x, W, b=None, activation=None, out_dtype=None, defer_bias_grad=False)
         # with an activation the GEMM epilogue also stores act'(z) (not z): backward is then one multiply, which the
         # dgrad GEMM of the layer that consumes y applies in its own epilogue together with the bias-gradient column
         # sums (FUSE_ACT_BWD) -- no pass over the [M,N] tensor for GeluGrad / BiasAddGrad
-        d = Tensor(lead + (N,), BF16) if (act != 0 and tape is not None) else None
+        d, dkind = None, 1
+        if act != 0 and tape is not None:
+            opA, opB = _operand(xb.ptr, K, False, BF16), _operand(W.shadow.ptr, N, True, BF16)
+            if (GELU_D8 and FUSE_ACT_BWD and act == _lib.ACT["gelu"]
+                    and _gemm_tc_supported(M, N, K, opA, opB, y.ptr, N, BF16, bias=b.ptr if b is not None else None, act=act,
+                                           c2=y.ptr, c2_kind=2)):
+                d, dkind = Tensor(lead + (N,), U8), 2
+            else:
+                d = Tensor(lead + (N,), BF16)
         _gemm(M, N, K, _operand(xb.ptr, K, False, BF16), _operand(W.shadow.ptr, N, True, BF16),
-              y.ptr, N, BF16, bias=b.ptr if b is not None else None, act=act, c2=d.ptr if d is not None else None, c2_kind=1)
+              y.ptr, N, BF16, bias=b.ptr if b is not None else None, act=act, c2=d.ptr if d is not None else None, c2_kind=dkind)
         if tape is not None:
             if d is not None and FUSE_ACT_BWD:
-                y.bwd_fuse = (d, b.grad if b is not None else None)
+                y.bwd_fuse = (d, b.grad if b is not None else None, dkind)
 
             def backward(g, xb=xb, d=d):
                 g = cast(g, BF16)
@@ -448,7 +474,8 @@ def linear(x, W, b=None, activation=None, out_dtype=None, defer_bias_grad=False)
                     # defer_bias_grad: the consumer (layernorm_residual with x_bias=b) already added colsum(g) to b.grad
                     want_bias = b is not None and not (defer_bias_grad and act == 0)
                 if need_dz or want_bias:
-                    _lib.call("polus_act_bwd_colsum", g.ptr, d.ptr if d is not None else None, M, N, _lib.ACT_DERIV if need_dz else 0,
+                    _lib.call("polus_act_bwd_colsum", g.ptr, d.ptr if d is not None else None, M, N,
+                              (_lib.ACT_DERIV_U8 if dkind == 2 else _lib.ACT_DERIV) if need_dz else 0,
                               dz.ptr if need_dz else None, b.grad.ptr if want_bias else None, None, device.stream())
                 # dW[K,N] += x^T dz : A = x (MN-major over K), B = dz (MN-major over N), reduce over M
                 _gemm(K, N, M, _operand(xb.ptr, K, True, BF16), _operand(dz.ptr, N, True, BF16),
@@ -457,10 +484,14 @@ def linear(x, W, b=None, activation=None, out_dtype=None, defer_bias_grad=False)
                 if xb.requires_grad:
                     dx = Tensor(lead + (K,), BF16)
                     fuse = xb.bwd_fuse if (xb.bwd_fuse is not None and xb.consumers == 1) else None
+                    opA, opB = _operand(dz.ptr, N, False, BF16), _operand(W.shadow.ptr, N, False, BF16)
+                    if fuse is not None and fuse[2] == 2 and not _gemm_tc_supported(M, K, N, opA, opB, dx.ptr, K, BF16, emul=fuse[0].ptr,
+                                                                                  colsum=fuse[1].ptr if fuse[1] is not None else None, c2_kind=2):
+                        fuse = None   # this GEMM cannot read the 8-bit derivative: the producer's own backward applies it
                     # dx[M,K] = dz[M,N] . W[K,N]^T : both K-major over N  (* act'(z_prev), + bias-grad column sums when fused)
-                    kind = _gemm(M, K, N, _operand(dz.ptr, N, False, BF16), _operand(W.shadow.ptr, N, False, BF16),
+                    kind = _gemm(M, K, N, opA, opB,
                                  dx.ptr, K, BF16, emul=fuse[0].ptr if fuse else None,
-                                 colsum=fuse[1].ptr if (fuse and fuse[1] is not None) else None)
+                                 colsum=fuse[1].ptr if (fuse and fuse[1] is not None) else None, c2_kind=fuse[2] if fuse else 0)
                     if fuse and kind == "tc":
                         dx.fused_for = id(xb)
                     elif fuse:

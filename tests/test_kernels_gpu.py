@@ -480,6 +480,58 @@ def test_gemm_tc_fused_activation_backward(dev, M, N, K, cg):
     np.testing.assert_allclose(cs_r.numpy(), 0.25 + r_t.numpy().astype(np.float64).sum(0), rtol=1e-4, atol=1e-4 * (np.abs(cs_ref).max() + 1))
 
 
+@pytest.mark.parametrize("M,N,K", [(8192, 3072, 768), (5000, 1536, 256)])
+def test_gemm_tc_gelu_derivative_as_8bit_fixed_point(dev, M, N, K):
+    """polus_gemm_t.c2_kind = 2: the FFN-up GEMM stores gelu' as one byte per element, q = 28 + round(200 gelu'), and the
+    dgrad GEMM of the next layer (or polus_act_bwd_colsum, when that GEMM cannot fuse it) multiplies by (q - 28) * 0.005.
+    Bars: decoded derivative within half a step (0.0025) + fp32 noise of numpy's gelu'; products against the DECODED
+    derivative within the bf16 output tolerance; problems the 16-warp kernel does not take are reported as unsupported."""
+    from oracle import numpy_ref as R
+    from polus_b200 import _lib
+    from polus_b200.tensor import BF16, F32, U8
+    rng = np.random.default_rng(M + N + K)
+    A = dev.bf16_round(rng.standard_normal((M, K)).astype(np.float32))
+    B = dev.bf16_round(rng.standard_normal((N, K)).astype(np.float32) * (1.5 / np.sqrt(K)))
+    bias = (0.1 * rng.standard_normal(N)).astype(np.float32)
+    a_t, b_t, bias_t = T(A, BF16), T(B, BF16), T(bias)
+    y_t, d_t = new((M, N), BF16), new((M, N), U8)
+    g = _lib.Gemm()
+    g.M, g.N, g.K, g.batch0, g.batch1 = M, N, K, 1, 1
+    g.A = _lib.Operand(a_t.ptr, K, 0, 0, 0, _lib.BF16)
+    g.B = _lib.Operand(b_t.ptr, K, 0, 0, 0, _lib.BF16)
+    g.C, g.ldc, g.c_dtype, g.bias, g.alpha, g.act = y_t.ptr, N, _lib.BF16, bias_t.ptr, 1.0, _lib.ACT["gelu"]
+    g.C2, g.c2_kind, g.split_k = d_t.ptr, 2, 1
+    assert call("polus_gemm_tc_supported", C.byref(g)) == 1
+    call("polus_gemm_tc", C.byref(g), st())
+    z = A.astype(np.float64) @ B.T.astype(np.float64) + bias
+    np.testing.assert_allclose(y_t.numpy(), R.ACT["gelu"][0](z), atol=2 * BF16_EPS * (np.abs(z).max() + 1), rtol=0)
+    q = d_t.numpy().astype(np.float64)
+    assert q.min() >= 2 and q.max() <= 254
+    dec = (q - 28.0) * 0.005
+    np.testing.assert_allclose(dec, R.ACT["gelu"][1](z), atol=0.0025 + 2e-4, rtol=0)
+    # backward: C = (dY . W^T) * decoded derivative, column sums of the stored values
+    c_t = new((M, N), BF16)
+    cs_t = T(np.full(N, 0.25, np.float32))
+    g.C, g.C2, g.bias, g.act = c_t.ptr, None, None, 0
+    g.Emul, g.colsum = d_t.ptr, cs_t.ptr
+    assert call("polus_gemm_tc_supported", C.byref(g)) == 1
+    call("polus_gemm_tc", C.byref(g), st())
+    prod = A.astype(np.float64) @ B.T.astype(np.float64)
+    ref = prod * dec
+    np.testing.assert_allclose(c_t.numpy(), ref, atol=2 * BF16_EPS * (np.abs(ref).max() + 1), rtol=0)
+    cs_ref = 0.25 + c_t.numpy().astype(np.float64).sum(0)
+    np.testing.assert_allclose(cs_t.numpy(), cs_ref, rtol=1e-4, atol=1e-4 * (np.abs(cs_ref).max() + 1))
+    # the unfused route: dz = dy * decoded derivative + bias-gradient column sums
+    dy = dev.bf16_round(rng.standard_normal((M, N)).astype(np.float32))
+    dz_t, gb_t = new((M, N), BF16), T(np.zeros(N, np.float32))
+    call("polus_act_bwd_colsum", T(dy, BF16).ptr, d_t.ptr, M, N, _lib.ACT_DERIV_U8, dz_t.ptr, gb_t.ptr, None, st())
+    np.testing.assert_allclose(dz_t.numpy(), dy * dec, atol=2 * BF16_EPS * 6, rtol=0)
+    np.testing.assert_allclose(gb_t.numpy(), (dy * dec).sum(0), rtol=1e-2, atol=1e-2 * np.sqrt(M))
+    # a shape the 16-warp pair kernel does not take (one 128-row tile) must say so instead of misreading the bytes
+    g.M = 128
+    assert call("polus_gemm_tc_supported", C.byref(g)) == 0
+
+
 @pytest.mark.parametrize("M,K,N,act,xdt", [(8192, 128, 4, None, "bf16"), (128, 128, 10, None, "bf16"), (333, 768, 3, "swish", "f32"),
                                            (50, 40, 32, "relu", "f32"), (0, 128, 4, None, "bf16")])
 def test_skinny_linear_fwd_bwd(dev, M, K, N, act, xdt):
