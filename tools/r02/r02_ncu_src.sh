@@ -1,5 +1,5 @@
 #!/bin/bash
-# ncu --set full with source-level stall sampling of ONE GEMM case:  tools/r02_ncu_src.sh NAME "GEMM_ONLY pattern" [GEMM_EXTRA]
+# ncu --set full with source-level stall sampling of ONE GEMM case:  tools/r02/r02_ncu_src.sh NAME "GEMM_ONLY pattern" [GEMM_EXTRA]
 OUT=gpurun_out; mkdir -p $OUT
 name=$1; pat=$2; extra=${3:-0}
 GEMM_EXTRA=$extra GEMM_ONLY="$pat" python tools/gemm_shapes.py 128 > $OUT/plain_$name.log 2>&1 && \

@@ -1,5 +1,5 @@
 #!/bin/bash
-# N-GPU probe of the gradient-exchange settings (run on the GPU box):  tools/scale_probe.sh N [extra bench args]
+# N-GPU probe of the gradient-exchange settings (run on the GPU box):  tools/r02/scale_probe.sh N [extra bench args]
 # One bench line per variant into gpurun_out/r02_scale${N}_<variant>.log; the dp_parity harness runs first.
 N=${1:-2}; shift
 OUT=gpurun_out

@@ -1,5 +1,5 @@
 #!/bin/bash
-# bucket-size probe of the in-step exposed exchange time:  tools/scale_probe2.sh N
+# bucket-size probe of the in-step exposed exchange time:  tools/r02/scale_probe2.sh N
 N=${1:-2}; OUT=gpurun_out; mkdir -p $OUT
 for mb in 64 32 128 16; do
   env POLUS_BUCKET_MB=$mb timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \
