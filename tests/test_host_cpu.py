@@ -116,6 +116,28 @@ def test_shard_rule_is_i_mod_n_before_batching():
 
 
 # ------------------------------------------------------------------ schedule / labels
+def test_warmup_scheduler_matches_hf_torch_polynomial_schedule():
+    """polus/schedulers.py:5-23 = HF `WarmUp` over Keras `PolynomialDecay(power=1, end_learning_rate=1e-7)`.  TensorFlow is
+    not installable here, but transformers ships the torch twin of the same schedule
+    (`get_polynomial_decay_schedule_with_warmup(lr_end=1e-7, power=1.0)`): an implementation that is neither the oracle's
+    nor the product's.  Both must follow it step by step (the device evaluates the same closed form inside polus_adam)."""
+    import torch
+    from transformers.optimization import get_polynomial_decay_schedule_with_warmup
+    from oracle import numpy_ref as R
+    from polus_b200.schedulers import warmup_scheduler
+    for n_steps, lr in ((200, 3e-4), (1000, 5e-5), (37, 1e-3)):
+        sched = warmup_scheduler(n_steps, lr)
+        opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=lr)
+        hf = get_polynomial_decay_schedule_with_warmup(opt, num_warmup_steps=int(n_steps * 0.1), num_training_steps=n_steps,
+                                                       lr_end=1e-7, power=1.0)
+        for step in range(n_steps + 1):
+            want = hf.get_last_lr()[0]
+            assert abs(sched(step) - want) <= 1e-12 * max(1.0, want / 1e-7), (n_steps, step, sched(step), want)
+            assert abs(R.warmup_schedule_lr(step, n_steps, lr) - want) <= 1e-12 * max(1.0, want / 1e-7)
+            opt.step()
+            hf.step()
+
+
 def test_warmup_scheduler_matches_oracle():
     from oracle import numpy_ref as R
     from polus_b200.schedulers import warmup_scheduler
